@@ -1,0 +1,68 @@
+// Context, error plumbing and scratch-memory management shared by all libgpw translation units.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/gpw.h"
+
+namespace gpw {
+
+void set_error(const char* fmt, ...);
+
+#define GPW_CUDA(expr)                                                                        \
+  do {                                                                                        \
+    cudaError_t _e = (expr);                                                                  \
+    if (_e != cudaSuccess) {                                                                  \
+      gpw::set_error("CUDA error %s at %s:%d: %s", cudaGetErrorName(_e), __FILE__, __LINE__, \
+                     cudaGetErrorString(_e));                                                 \
+      return GPW_ECUDA;                                                                       \
+    }                                                                                         \
+  } while (0)
+
+#define GPW_CHECK_LAUNCH() GPW_CUDA(cudaGetLastError())
+
+#define GPW_TRY(expr)          \
+  do {                         \
+    int _r = (expr);           \
+    if (_r != GPW_OK) return _r; \
+  } while (0)
+
+// Grow-only device scratch buffer (one per named slot) so steady-state calls allocate nothing.
+struct Scratch {
+  void* p = nullptr;
+  size_t cap = 0;
+};
+
+struct NttTables {
+  void* tw = nullptr;         // w^e, e < N/2
+  void* coset = nullptr;      // g^j, j < N
+  void* coset_inv = nullptr;  // g^-j / N, j < N
+};
+
+}  // namespace gpw
+
+struct gpw_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  bool own_stream = true;
+  int sm_count = 148;
+  uint64_t launches = 0;
+  std::map<std::string, gpw::Scratch> scratch;
+  std::map<int, gpw::NttTables> ntt;  // by logn
+  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  float msm_acc_ms = 0.f, msm_total_ms = 0.f;
+  uint64_t msm_digits = 0;
+  bool poseidon_consts_loaded = false;
+
+  int get_scratch(const char* name, size_t bytes, void** out);
+};
+
+namespace gpw {
+inline int div_up(size_t a, size_t b) { return (int)((a + b - 1) / b); }
+}  // namespace gpw

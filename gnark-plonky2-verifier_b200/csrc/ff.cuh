@@ -1,0 +1,542 @@
+// BN254 prime-field arithmetic (Fr = scalar field, Fp = base field) for host and sm_100a device.
+//
+// Representation: 8 x 32-bit little-endian limbs, Montgomery form with R = 2^256 - bit-identical in
+// memory to gnark-crypto's fr.Element / fp.Element ([4]uint64 LE limbs, Montgomery), so
+// buffers cross the C ABI without conversion.
+//
+// Device multiply: CIOS Montgomery on the 32-bit IMAD pipe. Partial products are accumulated in two
+// interleaved 8-word accumulators ("even"/"odd" 64-bit columns) so that every mad.lo.cc/madc.hi.cc
+// pair lowers to one IMAD.WIDE.U32(.X) with the carry kept in the CC/predicate chain - no tensor
+// cores (pure modular-integer work, BASELINE.json north_star). The same even/odd schedule is
+// emulated on the host (explicit carry) so the algorithm is unit-tested on CPU against a plain
+// 64-bit CIOS; the GPU self-test compares the PTX path with both.
+#pragma once
+#include <cstdint>
+#include <cstring>
+
+#ifdef __CUDACC__
+#define GPW_HD __host__ __device__ __forceinline__
+#define GPW_D __device__ __forceinline__
+#else
+#define GPW_HD inline
+#define GPW_D inline
+#endif
+
+namespace gpw {
+
+// ---------------------------------------------------------------------------------------------
+// Field parameters (numerically re-derived in tests/test_host_ff.py)
+// ---------------------------------------------------------------------------------------------
+struct FrParams {
+  // r = 0x30644e72e131a029b85045b68181585d2833e84879b9709143e1f593f0000001
+  static constexpr GPW_HD uint32_t mod(int i) {
+    constexpr uint32_t m[8] = {0xf0000001u, 0x43e1f593u, 0x79b97091u, 0x2833e848u,
+                               0x8181585du, 0xb85045b6u, 0xe131a029u, 0x30644e72u};
+    return m[i];
+  }
+  // R mod r
+  static constexpr GPW_HD uint32_t one(int i) {
+    constexpr uint32_t m[8] = {0x4ffffffbu, 0xac96341cu, 0x9f60cd29u, 0x36fc7695u,
+                               0x7879462eu, 0x666ea36fu, 0x9a07df2fu, 0x0e0a77c1u};
+    return m[i];
+  }
+  // R^2 mod r
+  static constexpr GPW_HD uint32_t r2(int i) {
+    constexpr uint32_t m[8] = {0xae216da7u, 0x1bb8e645u, 0xe35c59e3u, 0x53fe3ab1u,
+                               0x53bb8085u, 0x8c49833du, 0x7f4e44a5u, 0x0216d0b1u};
+    return m[i];
+  }
+  static constexpr uint32_t M0 = 0xefffffffu;  // -r^{-1} mod 2^32
+};
+
+struct FpParams {
+  // p = 0x30644e72e131a029b85045b68181585d97816a916871ca8d3c208c16d87cfd47
+  static constexpr GPW_HD uint32_t mod(int i) {
+    constexpr uint32_t m[8] = {0xd87cfd47u, 0x3c208c16u, 0x6871ca8du, 0x97816a91u,
+                               0x8181585du, 0xb85045b6u, 0xe131a029u, 0x30644e72u};
+    return m[i];
+  }
+  static constexpr GPW_HD uint32_t one(int i) {
+    constexpr uint32_t m[8] = {0xc58f0d9du, 0xd35d438du, 0xf5c70b3du, 0x0a78eb28u,
+                               0x7879462cu, 0x666ea36fu, 0x9a07df2fu, 0x0e0a77c1u};
+    return m[i];
+  }
+  static constexpr GPW_HD uint32_t r2(int i) {
+    constexpr uint32_t m[8] = {0x538afa89u, 0xf32cfc5bu, 0xd44501fbu, 0xb5e71911u,
+                               0x0a417ff6u, 0x47ab1effu, 0xcab8351fu, 0x06d89f71u};
+    return m[i];
+  }
+  static constexpr uint32_t M0 = 0xe4866389u;  // -p^{-1} mod 2^32
+};
+
+// ---------------------------------------------------------------------------------------------
+template <class P>
+struct alignas(16) Fe {
+  uint32_t l[8];
+
+  static GPW_HD Fe zero() {
+    Fe r;
+#pragma unroll
+    for (int i = 0; i < 8; i++) r.l[i] = 0;
+    return r;
+  }
+  static GPW_HD Fe one() {
+    Fe r;
+#pragma unroll
+    for (int i = 0; i < 8; i++) r.l[i] = P::one(i);
+    return r;
+  }
+  static GPW_HD Fe r2() {
+    Fe r;
+#pragma unroll
+    for (int i = 0; i < 8; i++) r.l[i] = P::r2(i);
+    return r;
+  }
+  GPW_HD bool is_zero() const {
+    uint32_t o = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) o |= l[i];
+    return o == 0;
+  }
+  GPW_HD bool operator==(const Fe& b) const {
+    uint32_t o = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) o |= (l[i] ^ b.l[i]);
+    return o == 0;
+  }
+  GPW_HD bool operator!=(const Fe& b) const { return !(*this == b); }
+};
+
+// ---- raw 256-bit helpers --------------------------------------------------------------------
+// r = a + b, returns carry
+template <class P>
+GPW_HD uint32_t add_raw(Fe<P>& r, const Fe<P>& a, const Fe<P>& b) {
+#ifdef __CUDA_ARCH__
+  uint32_t c;
+  asm("add.cc.u32 %0, %9, %17;\n\t"
+      "addc.cc.u32 %1, %10, %18;\n\t"
+      "addc.cc.u32 %2, %11, %19;\n\t"
+      "addc.cc.u32 %3, %12, %20;\n\t"
+      "addc.cc.u32 %4, %13, %21;\n\t"
+      "addc.cc.u32 %5, %14, %22;\n\t"
+      "addc.cc.u32 %6, %15, %23;\n\t"
+      "addc.cc.u32 %7, %16, %24;\n\t"
+      "addc.u32 %8, 0, 0;"
+      : "=r"(r.l[0]), "=r"(r.l[1]), "=r"(r.l[2]), "=r"(r.l[3]), "=r"(r.l[4]), "=r"(r.l[5]), "=r"(r.l[6]),
+        "=r"(r.l[7]), "=r"(c)
+      : "r"(a.l[0]), "r"(a.l[1]), "r"(a.l[2]), "r"(a.l[3]), "r"(a.l[4]), "r"(a.l[5]), "r"(a.l[6]), "r"(a.l[7]),
+        "r"(b.l[0]), "r"(b.l[1]), "r"(b.l[2]), "r"(b.l[3]), "r"(b.l[4]), "r"(b.l[5]), "r"(b.l[6]), "r"(b.l[7]));
+  return c;
+#else
+  uint64_t c = 0;
+  for (int i = 0; i < 8; i++) {
+    uint64_t s = (uint64_t)a.l[i] + b.l[i] + c;
+    r.l[i] = (uint32_t)s;
+    c = s >> 32;
+  }
+  return (uint32_t)c;
+#endif
+}
+
+// r = a - b, returns borrow (1 if a < b)
+template <class P>
+GPW_HD uint32_t sub_raw(Fe<P>& r, const Fe<P>& a, const Fe<P>& b) {
+#ifdef __CUDA_ARCH__
+  uint32_t c;
+  asm("sub.cc.u32 %0, %9, %17;\n\t"
+      "subc.cc.u32 %1, %10, %18;\n\t"
+      "subc.cc.u32 %2, %11, %19;\n\t"
+      "subc.cc.u32 %3, %12, %20;\n\t"
+      "subc.cc.u32 %4, %13, %21;\n\t"
+      "subc.cc.u32 %5, %14, %22;\n\t"
+      "subc.cc.u32 %6, %15, %23;\n\t"
+      "subc.cc.u32 %7, %16, %24;\n\t"
+      "subc.u32 %8, 0, 0;"
+      : "=r"(r.l[0]), "=r"(r.l[1]), "=r"(r.l[2]), "=r"(r.l[3]), "=r"(r.l[4]), "=r"(r.l[5]), "=r"(r.l[6]),
+        "=r"(r.l[7]), "=r"(c)
+      : "r"(a.l[0]), "r"(a.l[1]), "r"(a.l[2]), "r"(a.l[3]), "r"(a.l[4]), "r"(a.l[5]), "r"(a.l[6]), "r"(a.l[7]),
+        "r"(b.l[0]), "r"(b.l[1]), "r"(b.l[2]), "r"(b.l[3]), "r"(b.l[4]), "r"(b.l[5]), "r"(b.l[6]), "r"(b.l[7]));
+  return c & 1u;  // subc.u32 0,0 yields 0xffffffff on borrow
+#else
+  uint64_t brw = 0;
+  for (int i = 0; i < 8; i++) {
+    uint64_t d = (uint64_t)a.l[i] - b.l[i] - brw;
+    r.l[i] = (uint32_t)d;
+    brw = (d >> 32) & 1u;
+  }
+  return (uint32_t)brw;
+#endif
+}
+
+template <class P>
+GPW_HD Fe<P> modulus() {
+  Fe<P> m;
+#pragma unroll
+  for (int i = 0; i < 8; i++) m.l[i] = P::mod(i);
+  return m;
+}
+
+// conditional final subtraction: a in [0, 2p) -> [0, p)
+template <class P>
+GPW_HD Fe<P> reduce_once(const Fe<P>& a) {
+  Fe<P> t;
+  uint32_t borrow = sub_raw(t, a, modulus<P>());
+  Fe<P> r;
+#pragma unroll
+  for (int i = 0; i < 8; i++) r.l[i] = borrow ? a.l[i] : t.l[i];
+  return r;
+}
+
+template <class P>
+GPW_HD Fe<P> add(const Fe<P>& a, const Fe<P>& b) {
+  Fe<P> s;
+  add_raw(s, a, b);  // a,b < p < 2^254: no carry out
+  return reduce_once(s);
+}
+
+template <class P>
+GPW_HD Fe<P> sub(const Fe<P>& a, const Fe<P>& b) {
+  Fe<P> d, t;
+  uint32_t borrow = sub_raw(d, a, b);
+  add_raw(t, d, modulus<P>());
+  Fe<P> r;
+#pragma unroll
+  for (int i = 0; i < 8; i++) r.l[i] = borrow ? t.l[i] : d.l[i];
+  return r;
+}
+
+template <class P>
+GPW_HD Fe<P> neg(const Fe<P>& a) {
+  Fe<P> t;
+  sub_raw(t, modulus<P>(), a);
+  Fe<P> r;
+  bool z = a.is_zero();
+#pragma unroll
+  for (int i = 0; i < 8; i++) r.l[i] = z ? 0u : t.l[i];
+  return r;
+}
+
+template <class P>
+GPW_HD Fe<P> dbl(const Fe<P>& a) {
+  return add(a, a);
+}
+
+// ---- Montgomery multiplication: plain 64-bit CIOS (host; also the device cross-check) --------
+template <class P>
+GPW_HD Fe<P> mont_mul_portable(const Fe<P>& a, const Fe<P>& b) {
+  uint32_t t[10];
+#pragma unroll
+  for (int i = 0; i < 10; i++) t[i] = 0;
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    uint64_t c = 0;
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+      uint64_t s = (uint64_t)a.l[j] * b.l[i] + t[j] + c;
+      t[j] = (uint32_t)s;
+      c = s >> 32;
+    }
+    uint64_t s = (uint64_t)t[8] + c;
+    t[8] = (uint32_t)s;
+    t[9] = (uint32_t)(s >> 32);
+    uint32_t m = t[0] * P::M0;
+    c = ((uint64_t)m * P::mod(0) + t[0]) >> 32;
+#pragma unroll
+    for (int j = 1; j < 8; j++) {
+      s = (uint64_t)m * P::mod(j) + t[j] + c;
+      t[j - 1] = (uint32_t)s;
+      c = s >> 32;
+    }
+    s = (uint64_t)t[8] + c;
+    t[7] = (uint32_t)s;
+    t[8] = t[9] + (uint32_t)(s >> 32);
+  }
+  Fe<P> r;
+#pragma unroll
+  for (int i = 0; i < 8; i++) r.l[i] = t[i];
+  return reduce_once(r);
+}
+
+// ---- Montgomery multiplication: even/odd IMAD.WIDE schedule -----------------------------------
+// Running total T = sum even[k] 2^(32k) + sum odd[k] 2^(32(k+1)).
+namespace detail {
+
+// host emulation of the PTX carry-chain primitives (explicit carry flag)
+struct CC {
+  uint32_t c = 0;
+  GPW_HD uint32_t add_cc(uint32_t a, uint32_t b) {
+    uint64_t s = (uint64_t)a + b;
+    c = (uint32_t)(s >> 32);
+    return (uint32_t)s;
+  }
+  GPW_HD uint32_t addc(uint32_t a, uint32_t b) { return a + b + c; }
+  GPW_HD uint32_t mad_lo_cc(uint32_t a, uint32_t b, uint32_t d) {
+    uint64_t s = (uint64_t)(uint32_t)((uint64_t)a * b) + d;
+    c = (uint32_t)(s >> 32);
+    return (uint32_t)s;
+  }
+  GPW_HD uint32_t madc_lo_cc(uint32_t a, uint32_t b, uint32_t d) {
+    uint64_t s = (uint64_t)(uint32_t)((uint64_t)a * b) + d + c;
+    c = (uint32_t)(s >> 32);
+    return (uint32_t)s;
+  }
+  GPW_HD uint32_t madc_hi_cc(uint32_t a, uint32_t b, uint32_t d) {
+    uint64_t s = (((uint64_t)a * b) >> 32) + d + c;
+    c = (uint32_t)(s >> 32);
+    return (uint32_t)s;
+  }
+  GPW_HD uint32_t madc_hi(uint32_t a, uint32_t b, uint32_t d) { return (uint32_t)(((uint64_t)a * b) >> 32) + d + c; }
+};
+
+// Block A (iterations 1..7): fold the pending one-limb shift, then T += a * bi.
+//   e[0] += o[1]; o = (o >> 64) + a_odd * bi (carry-in from the fold); e += a_even * bi; o[7] += carry
+GPW_HD void mul_acc_shift(uint32_t* e, uint32_t* o, const uint32_t* a, uint32_t bi) {
+#ifdef __CUDA_ARCH__
+  asm("add.cc.u32      %0,  %0,  %9;\n\t"
+      "madc.lo.cc.u32  %8,  %17, %24, %10;\n\t"
+      "madc.hi.cc.u32  %9,  %17, %24, %11;\n\t"
+      "madc.lo.cc.u32  %10, %19, %24, %12;\n\t"
+      "madc.hi.cc.u32  %11, %19, %24, %13;\n\t"
+      "madc.lo.cc.u32  %12, %21, %24, %14;\n\t"
+      "madc.hi.cc.u32  %13, %21, %24, %15;\n\t"
+      "madc.lo.cc.u32  %14, %23, %24, 0;\n\t"
+      "madc.hi.u32     %15, %23, %24, 0;\n\t"
+      "mad.lo.cc.u32   %0,  %16, %24, %0;\n\t"
+      "madc.hi.cc.u32  %1,  %16, %24, %1;\n\t"
+      "madc.lo.cc.u32  %2,  %18, %24, %2;\n\t"
+      "madc.hi.cc.u32  %3,  %18, %24, %3;\n\t"
+      "madc.lo.cc.u32  %4,  %20, %24, %4;\n\t"
+      "madc.hi.cc.u32  %5,  %20, %24, %5;\n\t"
+      "madc.lo.cc.u32  %6,  %22, %24, %6;\n\t"
+      "madc.hi.cc.u32  %7,  %22, %24, %7;\n\t"
+      "addc.u32        %15, %15, 0;"
+      : "+r"(e[0]), "+r"(e[1]), "+r"(e[2]), "+r"(e[3]), "+r"(e[4]), "+r"(e[5]), "+r"(e[6]), "+r"(e[7]),
+        "+r"(o[0]), "+r"(o[1]), "+r"(o[2]), "+r"(o[3]), "+r"(o[4]), "+r"(o[5]), "+r"(o[6]), "+r"(o[7])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(a[4]), "r"(a[5]), "r"(a[6]), "r"(a[7]), "r"(bi));
+#else
+  CC k;
+  e[0] = k.add_cc(e[0], o[1]);
+  uint32_t n0 = k.madc_lo_cc(a[1], bi, o[2]);
+  uint32_t n1 = k.madc_hi_cc(a[1], bi, o[3]);
+  uint32_t n2 = k.madc_lo_cc(a[3], bi, o[4]);
+  uint32_t n3 = k.madc_hi_cc(a[3], bi, o[5]);
+  uint32_t n4 = k.madc_lo_cc(a[5], bi, o[6]);
+  uint32_t n5 = k.madc_hi_cc(a[5], bi, o[7]);
+  uint32_t n6 = k.madc_lo_cc(a[7], bi, 0);
+  uint32_t n7 = k.madc_hi(a[7], bi, 0);
+  o[0] = n0; o[1] = n1; o[2] = n2; o[3] = n3; o[4] = n4; o[5] = n5; o[6] = n6; o[7] = n7;
+  e[0] = k.mad_lo_cc(a[0], bi, e[0]);
+  e[1] = k.madc_hi_cc(a[0], bi, e[1]);
+  e[2] = k.madc_lo_cc(a[2], bi, e[2]);
+  e[3] = k.madc_hi_cc(a[2], bi, e[3]);
+  e[4] = k.madc_lo_cc(a[4], bi, e[4]);
+  e[5] = k.madc_hi_cc(a[4], bi, e[5]);
+  e[6] = k.madc_lo_cc(a[6], bi, e[6]);
+  e[7] = k.madc_hi_cc(a[6], bi, e[7]);
+  o[7] = k.addc(o[7], 0);
+#endif
+}
+
+// Block B: T += mi * p  (makes e[0] == 0 mod 2^32)
+template <class P>
+GPW_HD void redc_step(uint32_t* e, uint32_t* o, uint32_t mi) {
+#ifdef __CUDA_ARCH__
+  asm("mad.lo.cc.u32   %8,  %17, %24, %8;\n\t"
+      "madc.hi.cc.u32  %9,  %17, %24, %9;\n\t"
+      "madc.lo.cc.u32  %10, %19, %24, %10;\n\t"
+      "madc.hi.cc.u32  %11, %19, %24, %11;\n\t"
+      "madc.lo.cc.u32  %12, %21, %24, %12;\n\t"
+      "madc.hi.cc.u32  %13, %21, %24, %13;\n\t"
+      "madc.lo.cc.u32  %14, %23, %24, %14;\n\t"
+      "madc.hi.u32     %15, %23, %24, %15;\n\t"
+      "mad.lo.cc.u32   %0,  %16, %24, %0;\n\t"
+      "madc.hi.cc.u32  %1,  %16, %24, %1;\n\t"
+      "madc.lo.cc.u32  %2,  %18, %24, %2;\n\t"
+      "madc.hi.cc.u32  %3,  %18, %24, %3;\n\t"
+      "madc.lo.cc.u32  %4,  %20, %24, %4;\n\t"
+      "madc.hi.cc.u32  %5,  %20, %24, %5;\n\t"
+      "madc.lo.cc.u32  %6,  %22, %24, %6;\n\t"
+      "madc.hi.cc.u32  %7,  %22, %24, %7;\n\t"
+      "addc.u32        %15, %15, 0;"
+      : "+r"(e[0]), "+r"(e[1]), "+r"(e[2]), "+r"(e[3]), "+r"(e[4]), "+r"(e[5]), "+r"(e[6]), "+r"(e[7]),
+        "+r"(o[0]), "+r"(o[1]), "+r"(o[2]), "+r"(o[3]), "+r"(o[4]), "+r"(o[5]), "+r"(o[6]), "+r"(o[7])
+      : "r"(P::mod(0)), "r"(P::mod(1)), "r"(P::mod(2)), "r"(P::mod(3)), "r"(P::mod(4)), "r"(P::mod(5)),
+        "r"(P::mod(6)), "r"(P::mod(7)), "r"(mi));
+#else
+  CC k;
+  o[0] = k.mad_lo_cc(P::mod(1), mi, o[0]);
+  o[1] = k.madc_hi_cc(P::mod(1), mi, o[1]);
+  o[2] = k.madc_lo_cc(P::mod(3), mi, o[2]);
+  o[3] = k.madc_hi_cc(P::mod(3), mi, o[3]);
+  o[4] = k.madc_lo_cc(P::mod(5), mi, o[4]);
+  o[5] = k.madc_hi_cc(P::mod(5), mi, o[5]);
+  o[6] = k.madc_lo_cc(P::mod(7), mi, o[6]);
+  o[7] = k.madc_hi(P::mod(7), mi, o[7]);
+  e[0] = k.mad_lo_cc(P::mod(0), mi, e[0]);
+  e[1] = k.madc_hi_cc(P::mod(0), mi, e[1]);
+  e[2] = k.madc_lo_cc(P::mod(2), mi, e[2]);
+  e[3] = k.madc_hi_cc(P::mod(2), mi, e[3]);
+  e[4] = k.madc_lo_cc(P::mod(4), mi, e[4]);
+  e[5] = k.madc_hi_cc(P::mod(4), mi, e[5]);
+  e[6] = k.madc_lo_cc(P::mod(6), mi, e[6]);
+  e[7] = k.madc_hi_cc(P::mod(6), mi, e[7]);
+  o[7] = k.addc(o[7], 0);
+#endif
+}
+
+GPW_HD uint32_t mulhi32(uint32_t a, uint32_t b) {
+#ifdef __CUDA_ARCH__
+  return __umulhi(a, b);
+#else
+  return (uint32_t)(((uint64_t)a * b) >> 32);
+#endif
+}
+
+}  // namespace detail
+
+template <class P>
+GPW_HD Fe<P> mont_mul_wide(const Fe<P>& a, const Fe<P>& b) {
+  uint32_t ev[8], od[8];
+  // iteration 0: plain products, no accumulation
+#pragma unroll
+  for (int j = 0; j < 8; j += 2) {
+    ev[j] = a.l[j] * b.l[0];
+    ev[j + 1] = detail::mulhi32(a.l[j], b.l[0]);
+    od[j] = a.l[j + 1] * b.l[0];
+    od[j + 1] = detail::mulhi32(a.l[j + 1], b.l[0]);
+  }
+  detail::redc_step<P>(ev, od, ev[0] * P::M0);
+#pragma unroll
+  for (int i = 1; i < 8; i += 2) {
+    // roles swap after every one-limb shift
+    detail::mul_acc_shift(od, ev, a.l, b.l[i]);
+    detail::redc_step<P>(od, ev, od[0] * P::M0);
+    if (i + 1 < 8) {
+      detail::mul_acc_shift(ev, od, a.l, b.l[i + 1]);
+      detail::redc_step<P>(ev, od, ev[0] * P::M0);
+    }
+  }
+  // last call had (E, O) = (od, ev): result[k] = O[k] + E[k+1]
+  Fe<P> r;
+#ifdef __CUDA_ARCH__
+  asm("add.cc.u32  %0, %8,  %16;\n\t"
+      "addc.cc.u32 %1, %9,  %17;\n\t"
+      "addc.cc.u32 %2, %10, %18;\n\t"
+      "addc.cc.u32 %3, %11, %19;\n\t"
+      "addc.cc.u32 %4, %12, %20;\n\t"
+      "addc.cc.u32 %5, %13, %21;\n\t"
+      "addc.cc.u32 %6, %14, %22;\n\t"
+      "addc.u32    %7, %15, 0;"
+      : "=r"(r.l[0]), "=r"(r.l[1]), "=r"(r.l[2]), "=r"(r.l[3]), "=r"(r.l[4]), "=r"(r.l[5]), "=r"(r.l[6]),
+        "=r"(r.l[7])
+      : "r"(ev[0]), "r"(ev[1]), "r"(ev[2]), "r"(ev[3]), "r"(ev[4]), "r"(ev[5]), "r"(ev[6]), "r"(ev[7]),
+        "r"(od[1]), "r"(od[2]), "r"(od[3]), "r"(od[4]), "r"(od[5]), "r"(od[6]), "r"(od[7]));
+#else
+  detail::CC k;
+  r.l[0] = k.add_cc(ev[0], od[1]);
+  for (int i = 1; i < 7; i++) {
+    uint64_t s = (uint64_t)ev[i] + od[i + 1] + k.c;
+    r.l[i] = (uint32_t)s;
+    k.c = (uint32_t)(s >> 32);
+  }
+  r.l[7] = ev[7] + k.c;
+#endif
+  return reduce_once(r);
+}
+
+#ifndef GPW_FF_PORTABLE_MUL
+template <class P>
+GPW_HD Fe<P> mul(const Fe<P>& a, const Fe<P>& b) {
+  return mont_mul_wide(a, b);
+}
+#else
+template <class P>
+GPW_HD Fe<P> mul(const Fe<P>& a, const Fe<P>& b) {
+  return mont_mul_portable(a, b);
+}
+#endif
+
+template <class P>
+GPW_HD Fe<P> sqr(const Fe<P>& a) {
+  return mul(a, a);
+}
+
+template <class P>
+GPW_HD Fe<P> to_mont(const Fe<P>& a) {
+  return mul(a, Fe<P>::r2());
+}
+
+template <class P>
+GPW_HD Fe<P> from_mont(const Fe<P>& a) {
+  Fe<P> o = Fe<P>::zero();
+  o.l[0] = 1;
+  return mul(a, o);
+}
+
+// a^e for a 256-bit exponent given as 8 LE u32 words (square-and-multiply, MSB first)
+template <class P>
+GPW_HD Fe<P> pow_words(const Fe<P>& a, const uint32_t* e, int nwords) {
+  Fe<P> r = Fe<P>::one();
+  bool started = false;
+  for (int w = nwords - 1; w >= 0; w--) {
+    for (int b = 31; b >= 0; b--) {
+      if (started) r = sqr(r);
+      if ((e[w] >> b) & 1u) {
+        r = started ? mul(r, a) : a;
+        started = true;
+      }
+    }
+  }
+  return r;
+}
+
+// Fermat inverse (0 -> 0). Used off the hot path and in batched-inverse tails.
+template <class P>
+GPW_HD Fe<P> inv(const Fe<P>& a) {
+  uint32_t e[8];
+#pragma unroll
+  for (int i = 0; i < 8; i++) e[i] = P::mod(i);
+  e[0] -= 2;  // mod(0) >= 2 for both fields
+  if (a.is_zero()) return a;
+  return pow_words(a, e, 8);
+}
+
+using Fr = Fe<FrParams>;
+using Fp = Fe<FpParams>;
+
+// ---------------------------------------------------------------------------------------------
+// Fp2 = Fp[u]/(u^2+1)   - coordinates of G2
+// ---------------------------------------------------------------------------------------------
+struct alignas(16) Fp2 {
+  Fp c0, c1;
+  static GPW_HD Fp2 zero() { return {Fp::zero(), Fp::zero()}; }
+  static GPW_HD Fp2 one() { return {Fp::one(), Fp::zero()}; }
+  GPW_HD bool is_zero() const { return c0.is_zero() && c1.is_zero(); }
+  GPW_HD bool operator==(const Fp2& b) const { return c0 == b.c0 && c1 == b.c1; }
+  GPW_HD bool operator!=(const Fp2& b) const { return !(*this == b); }
+};
+
+GPW_HD Fp2 add(const Fp2& a, const Fp2& b) { return {add(a.c0, b.c0), add(a.c1, b.c1)}; }
+GPW_HD Fp2 sub(const Fp2& a, const Fp2& b) { return {sub(a.c0, b.c0), sub(a.c1, b.c1)}; }
+GPW_HD Fp2 neg(const Fp2& a) { return {neg(a.c0), neg(a.c1)}; }
+GPW_HD Fp2 dbl(const Fp2& a) { return {dbl(a.c0), dbl(a.c1)}; }
+// Karatsuba: 3 Fp muls
+GPW_HD Fp2 mul(const Fp2& a, const Fp2& b) {
+  Fp t0 = mul(a.c0, b.c0);
+  Fp t1 = mul(a.c1, b.c1);
+  Fp s = mul(add(a.c0, a.c1), add(b.c0, b.c1));
+  return {sub(t0, t1), sub(sub(s, t0), t1)};
+}
+// (a0+a1 u)^2 = (a0+a1)(a0-a1) + 2 a0 a1 u : 2 Fp muls
+GPW_HD Fp2 sqr(const Fp2& a) {
+  Fp t = mul(a.c0, a.c1);
+  Fp r0 = mul(add(a.c0, a.c1), sub(a.c0, a.c1));
+  return {r0, dbl(t)};
+}
+GPW_HD Fp2 inv(const Fp2& a) {
+  Fp n = add(sqr(a.c0), sqr(a.c1));
+  Fp ni = inv(n);
+  return {mul(a.c0, ni), neg(mul(a.c1, ni))};
+}
+
+}  // namespace gpw

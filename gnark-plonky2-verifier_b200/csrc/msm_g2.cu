@@ -1,0 +1,17 @@
+#include "msm_impl.cuh"
+using namespace gpw;
+extern "C" int gpw_msm_g2(gpw_ctx* ctx, const uint64_t* scalars, const uint64_t* points, size_t n, int scalars_mont,
+                          int window_bits, uint64_t* out_affine) {
+  return msm_host_impl<Fp2>(ctx, scalars, points, n, scalars_mont, window_bits, out_affine, "msm2");
+}
+
+extern "C" int gpw_msm_g2_dev(gpw_ctx* ctx, uint64_t scalars_dev, uint64_t points_dev, size_t n, int scalars_mont,
+                              int window_bits, int win_lo, int win_hi, uint64_t* out_affine) {
+  if (!ctx || !out_affine) {
+    set_error("msm: null argument");
+    return GPW_EINVAL;
+  }
+  return msm_dev_impl<Fp2>(ctx, (const Fr*)scalars_dev, (const Affine<Fp2>*)points_dev, n, scalars_mont, window_bits,
+                           win_lo, win_hi, out_affine, "msm2");
+}
+

@@ -1,0 +1,387 @@
+#pragma once
+// K9 - Pippenger multi-scalar multiplication over BN254 G1 / G2 for sm_100a.
+//
+// Replaces gnark-crypto's G1Jac.MultiExp / G2Jac.MultiExp (un-vendored dependency of the reference,
+// reached from groth16.Prove at benchmark.go:249). Output is the unique group element, so parity
+// with any correct implementation is exact.
+//
+// Pipeline (all on one stream, no host round trips until the final 16 window sums):
+//   1. k_msm_count     signed c-bit digits of every scalar -> histogram over (window, |digit|) buckets
+//   2. k_msm_scan      exclusive prefix sum of the histogram (bucket start offsets)
+//   3. k_msm_scatter   counting-sort scatter of (point index | sign) by bucket
+//   4. k_msm_accumulate  THE hot kernel: the sorted entry array is cut into uniform tasks of
+//                      MSM_TASK entries; one thread walks one task doing XYZZ += affine mixed adds
+//                      (8M + 2S each, ~3000 IMADs) with 64 B / 128 B gathers of the affine points.
+//                      Uniform tasks make the work per thread identical even for the heavily skewed
+//                      scalar distribution of a gnark witness (most wires are 0/1 or < 2^64), where
+//                      thread-per-bucket schemes serialise on the hot buckets.
+//   5. k_msm_fixup     buckets that span several tasks: warp-parallel sum of their partials
+//   6. k_msm_window_partial / k_msm_window_final   sum_b (b+1) * B[w][b] per window
+//   7. host: Horner over <= 16 window sums (270 group ops) and one inversion to affine.
+// Zero digits are skipped entirely, so a scalar < 2^64 costs 4-5 adds instead of 16.
+#include "common.cuh"
+#include "ec.cuh"
+
+namespace gpw {
+
+constexpr int MSM_TASK = 64;         // sorted entries per accumulate thread
+constexpr uint32_t KEY_NONE = 0xffffffffu;
+
+template <class T>
+__device__ __forceinline__ T ld_struct(const T* p) {
+  static_assert(sizeof(T) % 16 == 0, "16-byte multiple");
+  T r;
+  const uint4* s = reinterpret_cast<const uint4*>(p);
+  uint4* d = reinterpret_cast<uint4*>(&r);
+#pragma unroll
+  for (int i = 0; i < (int)(sizeof(T) / 16); i++) d[i] = __ldg(s + i);
+  return r;
+}
+
+template <class T>
+__device__ __forceinline__ void st_struct(T* p, const T& v) {
+  const uint4* s = reinterpret_cast<const uint4*>(&v);
+  uint4* d = reinterpret_cast<uint4*>(p);
+#pragma unroll
+  for (int i = 0; i < (int)(sizeof(T) / 16); i++) d[i] = s[i];
+}
+
+__device__ __forceinline__ uint32_t get_bits(const uint32_t* s, int lo, int c) {
+  int w = lo >> 5, off = lo & 31;
+  if (w >= 8) return 0;
+  uint64_t v = s[w];
+  if (w + 1 < 8) v |= (uint64_t)s[w + 1] << 32;
+  return (uint32_t)(v >> off) & ((1u << c) - 1u);
+}
+
+// Calls f(window, bucket_index, negative) for every non-zero signed digit in [win_lo, win_hi).
+template <class Fn>
+__device__ __forceinline__ void for_each_digit(const Fr& s, int c, int nwin, int win_lo, int win_hi, Fn f) {
+  const uint32_t half = 1u << (c - 1);
+  uint32_t carry = 0;
+  for (int w = 0; w < win_hi && w < nwin; w++) {
+    uint32_t raw = get_bits(s.l, w * c, c) + carry;
+    bool negv = raw > half;
+    uint32_t mag = negv ? ((1u << c) - raw) : raw;
+    carry = negv ? 1u : 0u;
+    if (mag != 0 && w >= win_lo) f(w, mag - 1u, negv);
+  }
+}
+
+static __global__ void k_msm_count(const Fr* __restrict__ scalars, size_t n, int mont, int c, int nwin, int win_lo,
+                            int win_hi, uint32_t* __restrict__ counts) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  Fr s = ld_struct(scalars + i);
+  if (mont) s = from_mont(s);
+  const uint32_t half = 1u << (c - 1);
+  for_each_digit(s, c, nwin, win_lo, win_hi,
+                 [&](int w, uint32_t b, bool) { atomicAdd(&counts[(uint32_t)(w - win_lo) * half + b], 1u); });
+}
+
+// single-block exclusive scan of B counters -> offsets[0..B], cursor[0..B)
+static __global__ void __launch_bounds__(1024) k_msm_scan(const uint32_t* __restrict__ counts, uint32_t B,
+                                                   uint32_t* __restrict__ offsets, uint32_t* __restrict__ cursor) {
+  __shared__ uint32_t part[1024];
+  uint32_t tid = threadIdx.x;
+  uint32_t chunk = (B + 1023u) / 1024u;
+  uint32_t lo = tid * chunk, hi = min(lo + chunk, B);
+  uint32_t s = 0;
+  for (uint32_t i = lo; i < hi; i++) s += counts[i];
+  part[tid] = s;
+  __syncthreads();
+  for (uint32_t d = 1; d < 1024; d <<= 1) {
+    uint32_t v = (tid >= d) ? part[tid - d] : 0u;
+    __syncthreads();
+    part[tid] += v;
+    __syncthreads();
+  }
+  uint32_t run = part[tid] - s;  // exclusive prefix of this thread's chunk
+  for (uint32_t i = lo; i < hi; i++) {
+    offsets[i] = run;
+    cursor[i] = run;
+    run += counts[i];
+  }
+  if (tid == 1023) offsets[B] = part[1023];
+}
+
+static __global__ void k_msm_scatter(const Fr* __restrict__ scalars, size_t n, int mont, int c, int nwin, int win_lo,
+                              int win_hi, uint32_t* __restrict__ cursor, uint32_t* __restrict__ sorted) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  Fr s = ld_struct(scalars + i);
+  if (mont) s = from_mont(s);
+  const uint32_t half = 1u << (c - 1);
+  for_each_digit(s, c, nwin, win_lo, win_hi, [&](int w, uint32_t b, bool negv) {
+    uint32_t pos = atomicAdd(&cursor[(uint32_t)(w - win_lo) * half + b], 1u);
+    sorted[pos] = (uint32_t)i | (negv ? 0x80000000u : 0u);
+  });
+}
+
+template <class F>
+__global__ void __launch_bounds__(128)
+    k_msm_accumulate(const Affine<F>* __restrict__ points, const uint32_t* __restrict__ sorted,
+                     const uint32_t* __restrict__ offsets, uint32_t B, XYZZ<F>* __restrict__ buckets,
+                     XYZZ<F>* __restrict__ head, XYZZ<F>* __restrict__ tail, uint32_t* __restrict__ head_key,
+                     uint32_t* __restrict__ tail_key, uint32_t* __restrict__ tail_list,
+                     uint32_t* __restrict__ ntail) {
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t M = offsets[B];
+  const uint64_t p0 = (uint64_t)t * MSM_TASK;
+  if (p0 >= M) return;
+  const uint32_t pos0 = (uint32_t)p0;
+  const uint32_t pos1 = min(pos0 + (uint32_t)MSM_TASK, M);
+  // bucket containing pos0: largest b with offsets[b] <= pos0 (skips empty buckets sharing the offset)
+  uint32_t lo = 0, hi = B;
+  while (hi - lo > 1) {
+    uint32_t mid = (lo + hi) >> 1;
+    if (offsets[mid] <= pos0) lo = mid; else hi = mid;
+  }
+  uint32_t b = lo;
+  uint32_t pos = pos0;
+  uint32_t e_next = sorted[pos];
+  Affine<F> p_next = ld_struct(points + (e_next & 0x7fffffffu));
+  while (pos < pos1) {
+    const uint32_t bstart = offsets[b];
+    const uint32_t bend = offsets[b + 1];
+    const uint32_t run_end = min(bend, pos1);
+    XYZZ<F> acc = XYZZ<F>::inf();
+    while (pos < run_end) {
+      const uint32_t e = e_next;
+      const Affine<F> p = p_next;
+      pos++;
+      if (pos < pos1) {  // prefetch the next point while this add runs
+        e_next = sorted[pos];
+        p_next = ld_struct(points + (e_next & 0x7fffffffu));
+      }
+      add_mixed(acc, p, (e >> 31) != 0);
+    }
+    if (bstart < pos0) {  // bucket began in an earlier task
+      st_struct(head + t, acc);
+      head_key[t] = b;
+    } else if (bend > pos1) {  // bucket continues into later tasks
+      st_struct(tail + t, acc);
+      tail_key[t] = b;
+      tail_list[atomicAdd(ntail, 1u)] = t;
+    } else {
+      st_struct(buckets + b, acc);
+    }
+    if (pos < pos1) {
+      b++;
+      while (offsets[b + 1] <= pos) b++;
+    }
+  }
+}
+
+template <class F>
+__device__ __forceinline__ XYZZ<F> shfl_down_point(const XYZZ<F>& v, int delta) {
+  XYZZ<F> r;
+  const uint32_t* s = reinterpret_cast<const uint32_t*>(&v);
+  uint32_t* d = reinterpret_cast<uint32_t*>(&r);
+#pragma unroll
+  for (int i = 0; i < (int)(sizeof(XYZZ<F>) / 4); i++) d[i] = __shfl_down_sync(0xffffffffu, s[i], delta);
+  return r;
+}
+
+// one warp per bucket that spans several tasks: tail[t0] + head[t0+1] + head[t0+2] + ...
+template <class F>
+__global__ void __launch_bounds__(128)
+    k_msm_fixup(const XYZZ<F>* __restrict__ head, const XYZZ<F>* __restrict__ tail,
+                const uint32_t* __restrict__ head_key, const uint32_t* __restrict__ tail_key,
+                const uint32_t* __restrict__ tail_list, const uint32_t* __restrict__ ntail, uint32_t ntasks,
+                XYZZ<F>* __restrict__ buckets) {
+  const uint32_t lane = threadIdx.x & 31u;
+  const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
+  const uint32_t nt = *ntail;
+  for (uint32_t i = warp; i < nt; i += nwarps) {
+    const uint32_t t0 = tail_list[i];
+    const uint32_t key = tail_key[t0];
+    XYZZ<F> acc = XYZZ<F>::inf();
+    if (lane == 0) acc = tail[t0];
+    for (uint64_t t = (uint64_t)t0 + 1 + lane; t < ntasks && head_key[t] == key; t += 32) {
+      XYZZ<F> h = head[t];
+      add_full(acc, h);
+    }
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) {
+      XYZZ<F> o = shfl_down_point(acc, d);
+      if ((int)lane < d) add_full(acc, o);
+    }
+    if (lane == 0) st_struct(buckets + key, acc);
+  }
+}
+
+// sum_{b in chunk} (b+1) * B[w][b]   (running-sum trick + one small scalar mul per chunk)
+template <class F>
+__global__ void __launch_bounds__(128)
+    k_msm_window_partial(const XYZZ<F>* __restrict__ buckets, uint32_t half, uint32_t chunk, uint32_t nwin,
+                         XYZZ<F>* __restrict__ partials) {
+  const uint32_t gid = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t nchunks = half / chunk;
+  const uint32_t w = gid / nchunks, ci = gid % nchunks;
+  if (w >= nwin) return;
+  const uint32_t lo = ci * chunk;
+  XYZZ<F> acc = XYZZ<F>::inf(), sum = XYZZ<F>::inf();
+  for (int b = (int)(lo + chunk) - 1; b >= (int)lo; b--) {
+    XYZZ<F> bk = buckets[(size_t)w * half + b];
+    add_full(acc, bk);
+    add_full(sum, acc);
+  }
+  if (lo > 0 && !acc.is_inf()) {
+    XYZZ<F> t = mul_small(acc, lo);
+    add_full(sum, t);
+  }
+  st_struct(partials + gid, sum);
+}
+
+template <class F>
+__global__ void __launch_bounds__(128)
+    k_msm_window_final(const XYZZ<F>* __restrict__ partials, uint32_t nchunks, XYZZ<F>* __restrict__ window_sums) {
+  extern __shared__ uint4 smem_raw[];
+  XYZZ<F>* sm = reinterpret_cast<XYZZ<F>*>(smem_raw);
+  const uint32_t w = blockIdx.x, tid = threadIdx.x;
+  XYZZ<F> acc = XYZZ<F>::inf();
+  for (uint32_t i = tid; i < nchunks; i += blockDim.x) {
+    XYZZ<F> p = partials[(size_t)w * nchunks + i];
+    add_full(acc, p);
+  }
+  sm[tid] = acc;
+  __syncthreads();
+  for (uint32_t d = blockDim.x >> 1; d >= 1; d >>= 1) {
+    if (tid < d) {
+      XYZZ<F> o = sm[tid + d];
+      add_full(acc, o);
+      sm[tid] = acc;
+    }
+    __syncthreads();
+  }
+  if (tid == 0) st_struct(window_sums + w, acc);
+}
+
+static int choose_window(size_t n) {
+  int lg = 0;
+  while ((1ull << (lg + 1)) <= n) lg++;
+  int c = lg - 3;
+  if (c > 16) c = 16;
+  if (c < 4) c = 4;
+  return c;
+}
+
+template <class F>
+static int msm_dev_impl(gpw_ctx* ctx, const Fr* scalars, const Affine<F>* points, size_t n, int mont, int c,
+                        int win_lo, int win_hi, uint64_t* out_affine, const char* tag) {
+  constexpr int OUT_WORDS = (int)(sizeof(Affine<F>) / 8);
+  if (n >= (1ull << 31)) {
+    set_error("msm: n=%zu too large (max 2^31-1)", n);
+    return GPW_EINVAL;
+  }
+  if (c == 0) c = choose_window(n ? n : 1);
+  if (c < 2 || c > 16) {
+    set_error("msm: window_bits=%d out of range [2,16]", c);
+    return GPW_EINVAL;
+  }
+  const int nwin = (254 + c) / c;  // ceil(255 / c): room for the final signed-digit carry
+  if (win_lo == 0 && win_hi == 0) win_hi = nwin;
+  if (win_lo < 0 || win_hi > nwin || win_lo >= win_hi) {
+    set_error("msm: bad window range [%d,%d) of %d", win_lo, win_hi, nwin);
+    return GPW_EINVAL;
+  }
+  if (n == 0) {
+    for (int i = 0; i < OUT_WORDS; i++) out_affine[i] = 0;
+    return GPW_OK;
+  }
+  GPW_CUDA(cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  const int nw = win_hi - win_lo;
+  const uint32_t half = 1u << (c - 1);
+  const uint32_t B = (uint32_t)nw * half;
+  const uint64_t max_entries = (uint64_t)n * nw;
+  if (max_entries >= (1ull << 32)) {
+    set_error("msm: n * windows = %llu exceeds 2^32 entries; split the call", (unsigned long long)max_entries);
+    return GPW_EINVAL;
+  }
+  const uint32_t ntasks = (uint32_t)((max_entries + MSM_TASK - 1) / MSM_TASK);
+  const uint32_t chunk = half < 16u ? half : 16u;
+  const uint32_t nchunks = half / chunk;
+
+  uint32_t *counts, *offsets, *cursor, *sorted, *head_key, *tail_key, *tail_list, *ntail;
+  XYZZ<F>*buckets, *head, *tail, *partials, *wsums;
+  std::string T(tag);
+  GPW_TRY(ctx->get_scratch((T + ".counts").c_str(), (size_t)(B + 1) * 4 * 3 + 64, (void**)&counts));
+  offsets = counts + (B + 1);
+  cursor = offsets + (B + 1);
+  ntail = cursor + (B + 1);
+  GPW_TRY(ctx->get_scratch((T + ".sorted").c_str(), (size_t)max_entries * 4 + 16, (void**)&sorted));
+  GPW_TRY(ctx->get_scratch((T + ".keys").c_str(), (size_t)ntasks * 4 * 3, (void**)&head_key));
+  tail_key = head_key + ntasks;
+  tail_list = tail_key + ntasks;
+  GPW_TRY(ctx->get_scratch((T + ".buckets").c_str(), (size_t)B * sizeof(XYZZ<F>), (void**)&buckets));
+  GPW_TRY(ctx->get_scratch((T + ".head").c_str(), (size_t)ntasks * sizeof(XYZZ<F>), (void**)&head));
+  GPW_TRY(ctx->get_scratch((T + ".tail").c_str(), (size_t)ntasks * sizeof(XYZZ<F>), (void**)&tail));
+  GPW_TRY(ctx->get_scratch((T + ".partials").c_str(), (size_t)nw * nchunks * sizeof(XYZZ<F>), (void**)&partials));
+  GPW_TRY(ctx->get_scratch((T + ".wsums").c_str(), (size_t)nw * sizeof(XYZZ<F>), (void**)&wsums));
+
+  GPW_CUDA(cudaEventRecord(ctx->ev[0], st));
+  GPW_CUDA(cudaMemsetAsync(counts, 0, (size_t)(B + 1) * 4 * 3 + 64, st));
+  GPW_CUDA(cudaMemsetAsync(head_key, 0xff, (size_t)ntasks * 4 * 2, st));
+  GPW_CUDA(cudaMemsetAsync(buckets, 0, (size_t)B * sizeof(XYZZ<F>), st));
+  const int TPB = 256;
+  k_msm_count<<<div_up(n, TPB), TPB, 0, st>>>(scalars, n, mont, c, nwin, win_lo, win_hi, counts);
+  GPW_CHECK_LAUNCH();
+  k_msm_scan<<<1, 1024, 0, st>>>(counts, B, offsets, cursor);
+  GPW_CHECK_LAUNCH();
+  k_msm_scatter<<<div_up(n, TPB), TPB, 0, st>>>(scalars, n, mont, c, nwin, win_lo, win_hi, cursor, sorted);
+  GPW_CHECK_LAUNCH();
+  GPW_CUDA(cudaEventRecord(ctx->ev[1], st));
+  k_msm_accumulate<F><<<div_up(ntasks, 128), 128, 0, st>>>(points, sorted, offsets, B, buckets, head, tail, head_key,
+                                                          tail_key, tail_list, ntail);
+  GPW_CHECK_LAUNCH();
+  GPW_CUDA(cudaEventRecord(ctx->ev[2], st));
+  k_msm_fixup<F><<<ctx->sm_count * 4, 128, 0, st>>>(head, tail, head_key, tail_key, tail_list, ntail, ntasks, buckets);
+  GPW_CHECK_LAUNCH();
+  k_msm_window_partial<F><<<div_up((size_t)nw * nchunks, 128), 128, 0, st>>>(buckets, half, chunk, (uint32_t)nw, partials);
+  GPW_CHECK_LAUNCH();
+  k_msm_window_final<F><<<nw, 128, 128 * sizeof(XYZZ<F>), st>>>(partials, nchunks, wsums);
+  GPW_CHECK_LAUNCH();
+  ctx->launches += 7;
+  std::vector<XYZZ<F>> hw(nw);
+  uint32_t M = 0;
+  GPW_CUDA(cudaMemcpyAsync(hw.data(), wsums, (size_t)nw * sizeof(XYZZ<F>), cudaMemcpyDeviceToHost, st));
+  GPW_CUDA(cudaMemcpyAsync(&M, offsets + B, 4, cudaMemcpyDeviceToHost, st));
+  GPW_CUDA(cudaEventRecord(ctx->ev[3], st));
+  GPW_CUDA(cudaStreamSynchronize(st));
+  GPW_CUDA(cudaEventElapsedTime(&ctx->msm_acc_ms, ctx->ev[1], ctx->ev[2]));
+  GPW_CUDA(cudaEventElapsedTime(&ctx->msm_total_ms, ctx->ev[0], ctx->ev[3]));
+  ctx->msm_digits = M;
+  // Horner over the window sums on the host: R = sum_w 2^(c (w)) W_w
+  XYZZ<F> R = XYZZ<F>::inf();
+  for (int w = nw - 1; w >= 0; w--) {
+    for (int k = 0; k < c; k++) R = dbl(R);
+    add_full(R, hw[w]);
+  }
+  for (int k = 0; k < c * win_lo; k++) R = dbl(R);
+  Affine<F> a = to_affine(R);
+  memcpy(out_affine, &a, sizeof(a));
+  return GPW_OK;
+}
+
+template <class F>
+static int msm_host_impl(gpw_ctx* ctx, const uint64_t* scalars, const uint64_t* points, size_t n, int mont, int c,
+                         uint64_t* out, const char* tag) {
+  if (!ctx || (!scalars && n) || (!points && n) || !out) {
+    set_error("msm: null argument");
+    return GPW_EINVAL;
+  }
+  GPW_CUDA(cudaSetDevice(ctx->device));
+  Fr* ds = nullptr;
+  Affine<F>* dp = nullptr;
+  std::string T(tag);
+  GPW_TRY(ctx->get_scratch((T + ".in_scalars").c_str(), n * sizeof(Fr) + 16, (void**)&ds));
+  GPW_TRY(ctx->get_scratch((T + ".in_points").c_str(), n * sizeof(Affine<F>) + 16, (void**)&dp));
+  GPW_CUDA(cudaMemcpyAsync(ds, scalars, n * sizeof(Fr), cudaMemcpyHostToDevice, ctx->stream));
+  GPW_CUDA(cudaMemcpyAsync(dp, points, n * sizeof(Affine<F>), cudaMemcpyHostToDevice, ctx->stream));
+  return msm_dev_impl<F>(ctx, ds, dp, n, mont, c, 0, 0, out, tag);
+}
+
+}  // namespace gpw

@@ -1,0 +1,366 @@
+// K8 - radix-2 NTT over BN254 Fr for sm_100a.
+//
+// Replaces gnark-crypto fr/fft Domain.FFT / FFTInverse (+ OnCoset), un-vendored dependency of the
+// reference, as used by groth16's computeH (7 transforms per proof). Conventions follow
+// gnark-crypto: 2-adicity 28, w_N = w_28^(2^(28-logN)), coset generator 5.
+//
+// One kernel serves every pass of both algorithms: a pass owns `k` consecutive index bits
+// [lobits, lobits + k); a CTA stages 2^k x C elements (C = 4 neighbouring columns, so every global
+// access is a full 128 B line made of 32 B-sector-sized elements) in shared memory, runs the k
+// butterfly stages there and writes back - one HBM read + one write per pass, 3 passes for 2^23.
+//   DIF (natural -> bit-reversed): passes walk the index bits from the top, stages high bit -> low bit,
+//        butterfly (u + v, (u - v) w)
+//   DIT (bit-reversed -> natural): passes walk from the bottom, stages low bit -> high bit,
+//        butterfly (u + v w, u - v w)
+// The twiddle for the pair at global bit g with j = index mod 2^g is w^(j << (L - 1 - g)), read from a
+// table of w^e, e < N/2 (inverse transforms use w^-e = -w^(N/2 - e), the sign folded into the
+// butterfly). Coset / 1/N scaling is fused into the first pass's load or the last pass's store.
+// The arithmetic is integer-pipe bound (11.5 Montgomery multiplies per element), not HBM bound.
+#include "common.cuh"
+#include "ff.cuh"
+
+namespace gpw {
+
+constexpr int NTT_MAX_K = 8;
+constexpr int NTT_COLS = 4;
+
+__device__ __forceinline__ Fr ld_fr(const Fr* p) {
+  Fr r;
+  const uint4* s = reinterpret_cast<const uint4*>(p);
+  uint4* d = reinterpret_cast<uint4*>(&r);
+  d[0] = s[0];
+  d[1] = s[1];
+  return r;
+}
+__device__ __forceinline__ void st_fr(Fr* p, const Fr& v) {
+  const uint4* s = reinterpret_cast<const uint4*>(&v);
+  uint4* d = reinterpret_cast<uint4*>(p);
+  d[0] = s[0];
+  d[1] = s[1];
+}
+
+__device__ __forceinline__ uint32_t bitrev(uint32_t x, int bits) { return bits ? (__brev(x) >> (32 - bits)) : 0u; }
+
+struct NttPass {
+  int L;        // log2 N
+  int lobits;   // index bits below the tile bits
+  int k;        // stages in this pass
+  int cols;     // columns per CTA (power of two <= NTT_COLS)
+  int col_in_lo;  // 1: columns are consecutive `lo` values; 0: consecutive tiles (lobits == 0)
+  int dit;      // 0 = DIF stage order / butterfly, 1 = DIT
+  int inverse;  // use w^-e
+  const Fr* scale_in;   // optional elementwise table applied on load  (index: position or bitrev(position))
+  const Fr* scale_out;  // optional elementwise table applied on store
+  int scale_in_bitrev, scale_out_bitrev;
+};
+
+__global__ void __launch_bounds__(512) k_ntt_pass(Fr* __restrict__ data, const Fr* __restrict__ tw, NttPass P) {
+  extern __shared__ uint4 smem_raw[];
+  Fr* sm = reinterpret_cast<Fr*>(smem_raw);
+  const int k = P.k, cols = P.cols;
+  const uint32_t tile = 1u << k;
+  const uint32_t nelem = tile * cols;
+  const uint32_t tid = threadIdx.x;
+  // CTA -> (hi, lo_base) or (tile_base)
+  uint64_t cta = blockIdx.x;
+  uint32_t lo_base, hi;
+  if (P.col_in_lo) {
+    uint32_t lo_groups = (1u << P.lobits) / cols;
+    lo_base = (uint32_t)(cta % lo_groups) * cols;
+    hi = (uint32_t)(cta / lo_groups);
+  } else {
+    lo_base = 0;
+    hi = (uint32_t)cta * cols;
+  }
+  auto gindex = [&](uint32_t t, uint32_t c) -> uint32_t {
+    if (P.col_in_lo) return (hi << (P.lobits + k)) | (t << P.lobits) | (lo_base + c);
+    return ((hi + c) << k) | t;
+  };
+  // load
+  for (uint32_t e = tid; e < nelem; e += blockDim.x) {
+    uint32_t c = e % cols, t = e / cols;
+    uint32_t gi = gindex(t, c);
+    Fr v = ld_fr(data + gi);
+    if (P.scale_in) {
+      uint32_t si = P.scale_in_bitrev ? bitrev(gi, P.L) : gi;
+      v = mul(v, ld_fr(P.scale_in + si));
+    }
+    st_fr(sm + e, v);
+  }
+  __syncthreads();
+  const uint32_t halfN = 1u << (P.L - 1);
+  for (int q = 0; q < k; q++) {
+    const int lb = P.dit ? q : (k - 1 - q);  // local pair bit
+    const uint32_t mask = (1u << lb) - 1u;
+    const int shift = P.L - 1 - (lb + P.lobits);
+    for (uint32_t bf = tid; bf < nelem / 2; bf += blockDim.x) {
+      uint32_t c = bf % cols, pi = bf / cols;
+      uint32_t t0 = ((pi & ~mask) << 1) | (pi & mask);
+      uint32_t t1 = t0 | (1u << lb);
+      uint32_t lo = P.col_in_lo ? (lo_base + c) : 0u;
+      uint32_t j = ((t0 & mask) << P.lobits) | lo;
+      uint32_t e = j << shift;  // < N/2
+      Fr u = ld_fr(sm + t0 * cols + c);
+      Fr v = ld_fr(sm + t1 * cols + c);
+      Fr r0, r1;
+      if (!P.dit) {
+        r0 = add(u, v);
+        if (e == 0) {
+          r1 = sub(u, v);
+        } else if (!P.inverse) {
+          r1 = mul(sub(u, v), ld_fr(tw + e));
+        } else {
+          r1 = mul(sub(v, u), ld_fr(tw + (halfN - e)));  // w^-e = -w^(N/2-e)
+        }
+      } else {
+        if (e == 0) {
+          r0 = add(u, v);
+          r1 = sub(u, v);
+        } else if (!P.inverse) {
+          Fr vw = mul(v, ld_fr(tw + e));
+          r0 = add(u, vw);
+          r1 = sub(u, vw);
+        } else {
+          Fr vw = mul(v, ld_fr(tw + (halfN - e)));
+          r0 = sub(u, vw);
+          r1 = add(u, vw);
+        }
+      }
+      st_fr(sm + t0 * cols + c, r0);
+      st_fr(sm + t1 * cols + c, r1);
+    }
+    __syncthreads();
+  }
+  for (uint32_t e = tid; e < nelem; e += blockDim.x) {
+    uint32_t c = e % cols, t = e / cols;
+    uint32_t gi = gindex(t, c);
+    Fr v = ld_fr(sm + e);
+    if (P.scale_out) {
+      uint32_t si = P.scale_out_bitrev ? bitrev(gi, P.L) : gi;
+      v = mul(v, ld_fr(P.scale_out + si));
+    }
+    st_fr(data + gi, v);
+  }
+}
+
+__global__ void k_bitrev_permute(Fr* __restrict__ data, int L) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (1u << L)) return;
+  uint32_t j = bitrev(i, L);
+  if (i < j) {
+    Fr a = ld_fr(data + i), b = ld_fr(data + j);
+    st_fr(data + i, b);
+    st_fr(data + j, a);
+  }
+}
+
+__global__ void k_scale_const(Fr* __restrict__ data, uint32_t n, Fr cst) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  st_fr(data + i, mul(ld_fr(data + i), cst));
+}
+
+// table[i] = base^i * c0 for i < n: each thread seeds base^(i0) by square-and-multiply, then walks
+__global__ void k_power_table(Fr* __restrict__ table, uint32_t n, Fr base, Fr c0, uint32_t per_thread) {
+  uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  uint64_t i0 = (uint64_t)t * per_thread;
+  if (i0 >= n) return;
+  uint32_t ew[1] = {(uint32_t)i0};
+  Fr cur = mul(pow_words(base, ew, 1), c0);
+  uint32_t end = (uint32_t)min((uint64_t)n, i0 + per_thread);
+  for (uint32_t i = (uint32_t)i0; i < end; i++) {
+    st_fr(table + i, cur);
+    cur = mul(cur, base);
+  }
+}
+
+// ---- host side --------------------------------------------------------------------------------
+static Fr fr_from_u64(uint64_t v) {
+  Fr a = Fr::zero();
+  a.l[0] = (uint32_t)v;
+  a.l[1] = (uint32_t)(v >> 32);
+  return to_mont(a);
+}
+
+static Fr fr_pow_u64(Fr a, uint64_t e) {
+  uint32_t w[2] = {(uint32_t)e, (uint32_t)(e >> 32)};
+  return pow_words(a, w, 2);
+}
+
+// w_28 = 5^((r-1)/2^28)   
+static Fr root_of_unity(int logn) {
+  // (r - 1) / 2^28 as 8 LE words
+  Fr m = modulus<FrParams>();
+  uint32_t e[8];
+  for (int i = 0; i < 8; i++) e[i] = m.l[i];
+  e[0] -= 1;
+  // shift right by 28
+  uint32_t s[8];
+  for (int i = 0; i < 8; i++) {
+    uint64_t v = e[i];
+    if (i + 1 < 8) v |= (uint64_t)e[i + 1] << 32;
+    s[i] = (uint32_t)(v >> 28);
+  }
+  Fr w = pow_words(fr_from_u64(5), s, 8);
+  for (int i = 0; i < 28 - logn; i++) w = sqr(w);
+  return w;
+}
+
+static int ensure_tables(gpw_ctx* ctx, int L, NttTables** out) {
+  auto it = ctx->ntt.find(L);
+  if (it != ctx->ntt.end()) {
+    *out = &it->second;
+    return GPW_OK;
+  }
+  NttTables t;
+  const uint32_t N = 1u << L;
+  const uint32_t halfN = N >> 1;
+  cudaStream_t st = ctx->stream;
+  GPW_CUDA(cudaMalloc(&t.tw, (size_t)(halfN ? halfN : 1) * sizeof(Fr)));
+  GPW_CUDA(cudaMalloc(&t.coset, (size_t)N * sizeof(Fr)));
+  GPW_CUDA(cudaMalloc(&t.coset_inv, (size_t)N * sizeof(Fr)));
+  Fr w = root_of_unity(L);
+  Fr g = fr_from_u64(5);
+  Fr ginv = inv(g);
+  Fr ninv = inv(fr_from_u64(N));
+  const uint32_t per = 64;
+  if (halfN) {
+    k_power_table<<<div_up(div_up(halfN, per), 128), 128, 0, st>>>((Fr*)t.tw, halfN, w, Fr::one(), per);
+    GPW_CHECK_LAUNCH();
+  }
+  k_power_table<<<div_up(div_up(N, per), 128), 128, 0, st>>>((Fr*)t.coset, N, g, Fr::one(), per);
+  GPW_CHECK_LAUNCH();
+  k_power_table<<<div_up(div_up(N, per), 128), 128, 0, st>>>((Fr*)t.coset_inv, N, ginv, ninv, per);
+  GPW_CHECK_LAUNCH();
+  ctx->launches += 3;
+  ctx->ntt[L] = t;
+  *out = &ctx->ntt[L];
+  return GPW_OK;
+}
+
+static int launch_pass(gpw_ctx* ctx, Fr* data, const NttTables* tb, NttPass P) {
+  const uint32_t N = 1u << P.L;
+  int cols = NTT_COLS;
+  if (P.lobits == 0) {
+    P.col_in_lo = 0;
+    while ((uint64_t)cols << P.k > N) cols >>= 1;
+  } else {
+    P.col_in_lo = 1;
+    while (cols > (1 << P.lobits)) cols >>= 1;
+  }
+  P.cols = cols;
+  const uint32_t nelem = (1u << P.k) * cols;
+  const uint32_t ctas = N / nelem;
+  int threads = (int)(nelem / 2);
+  if (threads > 512) threads = 512;
+  if (threads < 32) threads = 32;
+  k_ntt_pass<<<ctas, threads, nelem * sizeof(Fr), ctx->stream>>>(data, (const Fr*)tb->tw, P);
+  GPW_CHECK_LAUNCH();
+  ctx->launches += 1;
+  return GPW_OK;
+}
+
+static int ntt_dev_impl(gpw_ctx* ctx, Fr* data, int L, int inverse, int coset, int in_bitrev, int out_bitrev) {
+  if (L < 0 || L > 27) {
+    set_error("ntt: logn=%d out of range [0,27]", L);
+    return GPW_EINVAL;
+  }
+  GPW_CUDA(cudaSetDevice(ctx->device));
+  NttTables* tb;
+  GPW_TRY(ensure_tables(ctx, L, &tb));
+  const uint32_t N = 1u << L;
+  cudaStream_t st = ctx->stream;
+  if (L == 0) {
+    return GPW_OK;  // size-1 transform is the identity (coset scale g^0 = 1, 1/N = 1)
+  }
+  if (in_bitrev && out_bitrev) {  // rare: make the input natural first
+    k_bitrev_permute<<<div_up(N, 256), 256, 0, st>>>(data, L);
+    GPW_CHECK_LAUNCH();
+    ctx->launches += 1;
+    in_bitrev = 0;
+  }
+  const bool dit = in_bitrev != 0;
+  // split L stages into passes of <= NTT_MAX_K, avoiding a pass with lobits == 1 (needs >= 2 columns in lo)
+  std::vector<int> ks;
+  {
+    int rem = L;
+    while (rem > 0) {
+      int k = rem > NTT_MAX_K ? NTT_MAX_K : rem;
+      if (rem - k == 1) k -= 1;  // never leave a single bit for the last pass
+      ks.push_back(k);
+      rem -= k;
+    }
+  }
+  // scaling tables: forward coset pre-scales by g^j (natural index j); inverse post-scales by g^-j / N
+  // (or by 1/N alone).
+  const Fr* pre = nullptr;
+  const Fr* post = nullptr;
+  if (!inverse && coset) pre = (const Fr*)tb->coset;
+  if (inverse && coset) post = (const Fr*)tb->coset_inv;
+  int bits_done = 0;
+  for (size_t pi = 0; pi < ks.size(); pi++) {
+    NttPass P{};
+    P.L = L;
+    P.k = ks[pi];
+    P.dit = dit ? 1 : 0;
+    P.inverse = inverse;
+    // DIF walks from the top bit down, DIT from bit 0 up
+    P.lobits = dit ? bits_done : (L - bits_done - P.k);
+    if (pi == 0 && pre) {
+      P.scale_in = pre;
+      P.scale_in_bitrev = in_bitrev;  // data index is bitrev(j) when the input is bit-reversed
+    }
+    if (pi + 1 == ks.size() && post) {
+      P.scale_out = post;
+      P.scale_out_bitrev = dit ? 0 : 1;  // DIF leaves output bit-reversed: position p holds coefficient bitrev(p)
+    }
+    GPW_TRY(launch_pass(ctx, data, tb, P));
+    bits_done += P.k;
+  }
+  if (inverse && !coset) {
+    k_scale_const<<<div_up(N, 256), 256, 0, st>>>(data, N, inv(fr_from_u64(N)));
+    GPW_CHECK_LAUNCH();
+    ctx->launches += 1;
+  }
+  const bool is_bitrev_now = !dit;
+  if (is_bitrev_now != (out_bitrev != 0)) {
+    k_bitrev_permute<<<div_up(N, 256), 256, 0, st>>>(data, L);
+    GPW_CHECK_LAUNCH();
+    ctx->launches += 1;
+  }
+  return GPW_OK;
+}
+
+}  // namespace gpw
+
+using namespace gpw;
+
+extern "C" int gpw_ntt_fr_dev(gpw_ctx* ctx, uint64_t data_dev, int logn, int inverse, int coset, int in_bitrev,
+                              int out_bitrev) {
+  if (!ctx || !data_dev) {
+    set_error("ntt: null argument");
+    return GPW_EINVAL;
+  }
+  return ntt_dev_impl(ctx, (Fr*)data_dev, logn, inverse, coset, in_bitrev, out_bitrev);
+}
+
+extern "C" int gpw_ntt_fr(gpw_ctx* ctx, uint64_t* data, int logn, int inverse, int coset, int in_bitrev,
+                          int out_bitrev) {
+  if (!ctx || !data) {
+    set_error("ntt: null argument");
+    return GPW_EINVAL;
+  }
+  if (logn < 0 || logn > 27) {
+    set_error("ntt: logn=%d out of range [0,27]", logn);
+    return GPW_EINVAL;
+  }
+  GPW_CUDA(cudaSetDevice(ctx->device));
+  size_t bytes = ((size_t)1 << logn) * sizeof(Fr);
+  Fr* d;
+  GPW_TRY(ctx->get_scratch("ntt.io", bytes, (void**)&d));
+  GPW_CUDA(cudaMemcpyAsync(d, data, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  GPW_TRY(ntt_dev_impl(ctx, d, logn, inverse, coset, in_bitrev, out_bitrev));
+  GPW_CUDA(cudaMemcpyAsync(data, d, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  GPW_CUDA(cudaStreamSynchronize(ctx->stream));
+  return GPW_OK;
+}

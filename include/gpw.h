@@ -1,0 +1,130 @@
+/* libgpw - B200-native hot path of the Plonky2 -> gnark (Groth16 over BN254) wrap prover.
+ *
+ * C ABI (extern "C", plain pointers and sizes). This is the boundary the reference's Go code would
+ * bind through cgo (INTEGRATION.md shows the stubs). Each entry point cites the reference interface
+ * it replaces. Conventions:
+ *   - every function returns 0 on success, a negative GPW_E* code on failure; gpw_last_error() gives
+ *     the text (thread-local). No exceptions cross the boundary.
+ *   - field elements are 4 x uint64 little-endian limbs. "mont" = Montgomery form with R = 2^256,
+ *     i.e. the in-memory form of gnark-crypto's fr.Element / fp.Element; "canonical" =
+ *     the plain integer.
+ *   - G1 affine = {X, Y} fp (64 B), G2 affine = {X.A0, X.A1, Y.A0, Y.A1} fp (128 B), Montgomery form,
+ *     (0,0) = infinity - gnark-crypto's G1Affine / G2Affine layout.
+ *   - functions without a suffix take HOST buffers (copies are inside the call); functions with the
+ *     _dev suffix take DEVICE addresses (as returned by cudaMalloc / torch's data_ptr()) and enqueue
+ *     on the context's stream without synchronising unless stated.
+ *   - a gpw_ctx is bound to one GPU; one ctx per GPU / per host thread. There is no CPU fallback:
+ *     every compute entry point fails with GPW_ENODEV when no CUDA device is usable.
+ */
+#ifndef GPW_H
+#define GPW_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GPW_OK 0
+#define GPW_EINVAL (-1)
+#define GPW_ENODEV (-2)
+#define GPW_ECUDA (-3)
+#define GPW_ENOMEM (-4)
+#define GPW_EHINT (-5)   /* a hint rejected its input (reference: panic / error return) */
+#define GPW_EUNSAT (-6)  /* witness does not satisfy the constraint system */
+#define GPW_ENCCL (-7)
+
+typedef struct gpw_ctx gpw_ctx;
+
+/* ---- library / context -------------------------------------------------------------------- */
+int gpw_version(void);
+const char* gpw_last_error(void);
+int gpw_device_count(void);
+int gpw_ctx_create(int device, gpw_ctx** out);
+void gpw_ctx_destroy(gpw_ctx* ctx);
+/* Use an externally owned cudaStream_t (e.g. torch.cuda.current_stream().cuda_stream); 0 = own stream. */
+int gpw_ctx_set_stream(gpw_ctx* ctx, void* cuda_stream);
+int gpw_ctx_sync(gpw_ctx* ctx);
+/* Number of gpw kernels launched through this ctx since creation (bench.py's gpu_launches). */
+uint64_t gpw_ctx_launch_count(const gpw_ctx* ctx);
+
+/* ---- host-side arithmetic (no GPU): setup glue and the unit tests of the shared host/device code */
+/* field: 0 = Fr, 1 = Fp. impl: 0 = even/odd IMAD.WIDE schedule (host emulation), 1 = plain CIOS.  */
+int gpw_host_ff_mul(int field, int impl, const uint64_t* a_mont, const uint64_t* b_mont, uint64_t* out_mont, size_t n);
+int gpw_host_ff_to_mont(int field, const uint64_t* a, uint64_t* out, size_t n);
+int gpw_host_ff_from_mont(int field, const uint64_t* a, uint64_t* out, size_t n);
+int gpw_host_ff_inv(int field, const uint64_t* a_mont, uint64_t* out_mont, size_t n);
+/* group: 1 = G1, 2 = G2. out = k * P with k a canonical 256-bit scalar; affine in/out, mont. */
+int gpw_host_ec_scalar_mul(int group, const uint64_t* point_affine, const uint64_t* scalar_canonical, uint64_t* out_affine);
+int gpw_host_ec_add(int group, const uint64_t* p_affine, const uint64_t* q_affine, uint64_t* out_affine);
+int gpw_host_ec_is_on_curve(int group, const uint64_t* p_affine);
+/* n points [k_i]G for k_i = k0 + i (fixed generator); used to make synthetic bases cheaply. */
+int gpw_host_ec_generator_multiples(int group, uint64_t k0, size_t n, uint64_t* out_affine);
+
+/* ---- GPU self-test of the field kernels: runs the PTX multiply and the portable multiply on the
+ * device on n seeded pairs, compares both with the host result. Returns 0 if all agree. */
+int gpw_selftest_ff(gpw_ctx* ctx, size_t n, uint64_t seed);
+
+/* ---- K9: Pippenger MSM over BN254 G1 / G2 ---------------------------------------------------
+ * Replaces gnark-crypto G1Jac.MultiExp / G2Jac.MultiExp (ecc/bn254, un-vendored; reached from
+ * groth16.Prove at benchmark.go:249 and plonk.Prove at benchmark.go:162).
+ * scalars: n x 4 u64 (Montgomery if scalars_mont != 0, else canonical); points: n affine, mont.
+ * out_affine: the sum as one affine point (8 u64 for G1, 16 for G2), (0,0) for infinity.
+ * window_bits: Pippenger window c in [4,16], 0 = choose from n.                                 */
+int gpw_msm_g1(gpw_ctx* ctx, const uint64_t* scalars, const uint64_t* points, size_t n, int scalars_mont,
+               int window_bits, uint64_t* out_affine);
+int gpw_msm_g2(gpw_ctx* ctx, const uint64_t* scalars, const uint64_t* points, size_t n, int scalars_mont,
+               int window_bits, uint64_t* out_affine);
+/* Device-resident variants. Synchronise the stream before returning (the window sums are folded on
+ * the host). win_lo/win_hi select a sub-range of windows [win_lo, win_hi) for the multi-GPU window
+ * split (pass 0, 0 for all): the returned point is then sum_{w in range} 2^(c w) W_w.            */
+int gpw_msm_g1_dev(gpw_ctx* ctx, uint64_t scalars_dev, uint64_t points_dev, size_t n, int scalars_mont,
+                   int window_bits, int win_lo, int win_hi, uint64_t* out_affine);
+int gpw_msm_g2_dev(gpw_ctx* ctx, uint64_t scalars_dev, uint64_t points_dev, size_t n, int scalars_mont,
+                   int window_bits, int win_lo, int win_hi, uint64_t* out_affine);
+/* Time (ms, CUDA events on the ctx stream) spent in the bucket-accumulation kernel of the most
+ * recent MSM on this ctx, and the number of non-zero digits it processed. */
+int gpw_msm_last_stats(gpw_ctx* ctx, float* accumulate_ms, float* total_ms, uint64_t* nonzero_digits);
+
+/* ---- K8: radix-2 NTT over BN254 Fr ------------------------------------------------------------
+ * Replaces gnark-crypto fr/fft Domain.FFT / FFTInverse (+ OnCoset) as used by groth16 computeH.
+ * data: 2^logn Fr elements, Montgomery form, transformed in place.
+ *   forward:  A_k = sum_j a_j w^(jk)            (coset: a_j <- a_j g^j first, g = 5)
+ *   inverse:  a_j = N^-1 sum_k A_k w^(-jk)      (coset: a_j <- a_j g^-j afterwards)
+ * in_bitrev / out_bitrev select bit-reversed index order on either side (DIF: nat->bitrev,
+ * DIT: bitrev->nat; nat->nat adds one permutation pass).                                       */
+int gpw_ntt_fr(gpw_ctx* ctx, uint64_t* data, int logn, int inverse, int coset, int in_bitrev, int out_bitrev);
+int gpw_ntt_fr_dev(gpw_ctx* ctx, uint64_t data_dev, int logn, int inverse, int coset, int in_bitrev, int out_bitrev);
+
+/* ---- K3: Poseidon over BN254 Fr (t = 4) ---------------------------------------------------------
+ * Replaces poseidon.BN254Chip.Poseidon (poseidon/bn254.go:39-45). states: n x 4 Fr in / out.   */
+int gpw_poseidon_bn254(gpw_ctx* ctx, const uint64_t* states_in, uint64_t* states_out, size_t n, int mont);
+int gpw_poseidon_bn254_dev(gpw_ctx* ctx, uint64_t in_dev, uint64_t out_dev, size_t n, int mont);
+/* Merkle path walk of fri.verifyMerkleProofToCapWithCapIndex (fri/fri.go:97-144): for each of n paths,
+ * leaf digest (Fr) + depth siblings + index bits (LSB first, as a u64) -> root. canonical in/out. */
+int gpw_merkle_paths_bn254(gpw_ctx* ctx, const uint64_t* leaf_digests, const uint64_t* siblings, const uint64_t* index_bits,
+                           size_t n_paths, int depth, uint64_t* roots_out);
+/* BN254Chip.HashOrNoop (poseidon/bn254.go:47-94): n leaves of leaf_len Goldilocks elements -> digest. */
+int gpw_hash_or_noop_bn254(gpw_ctx* ctx, const uint64_t* leaves, size_t n, int leaf_len, uint64_t* digests_out);
+
+/* ---- K1: the four Goldilocks solver hints (goldilocks/base.go:223,284,316,339) -------------------
+ * Batched; bit-exact (q, r). mul_add: inputs a,b,c (n each, u64 < p) -> q,r (u64).
+ * reduce: x as 4 x u64 canonical (n x 4) -> q (n x 4, only the low 192 bits can be non-zero), r.
+ * Returns GPW_EHINT if any input violates the reference's precondition (first bad index in
+ * gpw_last_error()).                                                                            */
+int gpw_gl_mul_add_hint(gpw_ctx* ctx, const uint64_t* a, const uint64_t* b, const uint64_t* c, size_t n, uint64_t* q, uint64_t* r);
+int gpw_gl_reduce_hint(gpw_ctx* ctx, const uint64_t* x4, size_t n, uint64_t* q4, uint64_t* r);
+int gpw_gl_inverse_hint(gpw_ctx* ctx, const uint64_t* x, size_t n, uint64_t* inv);
+int gpw_gl_split_limbs_hint(gpw_ctx* ctx, const uint64_t* x, size_t n, uint64_t* hi, uint64_t* lo);
+
+/* ---- K2: Poseidon over Goldilocks (width 12) ------------------------------------------------------
+ * Replaces poseidon.GoldilocksChip.Poseidon (poseidon/goldilocks.go:30-37). states: n x 12 u64.
+ * If trace_out != NULL it receives, per permutation, the (q, r) outputs of every hint in the
+ * reference's order (see DESIGN.md "Poseidon-GL trace layout"), trace_stride u64 per permutation.  */
+int gpw_poseidon_gl(gpw_ctx* ctx, const uint64_t* states_in, uint64_t* states_out, size_t n);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GPW_H */
