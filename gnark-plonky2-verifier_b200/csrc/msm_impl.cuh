@@ -79,30 +79,94 @@ static __global__ void k_msm_count(const Fr* __restrict__ scalars, size_t n, int
                  [&](int w, uint32_t b, bool) { atomicAdd(&counts[(uint32_t)(w - win_lo) * half + b], 1u); });
 }
 
-// single-block exclusive scan of B counters -> offsets[0..B], cursor[0..B)
-static __global__ void __launch_bounds__(1024) k_msm_scan(const uint32_t* __restrict__ counts, uint32_t B,
-                                                   uint32_t* __restrict__ offsets, uint32_t* __restrict__ cursor) {
-  __shared__ uint32_t part[1024];
-  uint32_t tid = threadIdx.x;
-  uint32_t chunk = (B + 1023u) / 1024u;
-  uint32_t lo = tid * chunk, hi = min(lo + chunk, B);
-  uint32_t s = 0;
-  for (uint32_t i = lo; i < hi; i++) s += counts[i];
-  part[tid] = s;
+// exclusive scan of B counters -> offsets[0..B], cursor[0..B): per-block sums, scan of the block sums,
+// per-block exclusive scan + block offset. SCAN_BLOCK counters per block.
+constexpr uint32_t SCAN_THREADS = 256;
+constexpr uint32_t SCAN_PER_THREAD = 8;
+constexpr uint32_t SCAN_BLOCK = SCAN_THREADS * SCAN_PER_THREAD;
+
+static __device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t* sh, uint32_t& total) {
+  const uint32_t tid = threadIdx.x, lane = tid & 31u, wid = tid >> 5;
+  uint32_t x = v;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    uint32_t y = __shfl_up_sync(0xffffffffu, x, d);
+    if ((int)lane >= d) x += y;
+  }
+  if (lane == 31) sh[wid] = x;
   __syncthreads();
-  for (uint32_t d = 1; d < 1024; d <<= 1) {
-    uint32_t v = (tid >= d) ? part[tid - d] : 0u;
+  if (wid == 0) {
+    uint32_t w = lane < (blockDim.x >> 5) ? sh[lane] : 0u;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      uint32_t y = __shfl_up_sync(0xffffffffu, w, d);
+      if ((int)lane >= d) w += y;
+    }
+    sh[lane] = w;  // inclusive scan of warp totals
+  }
+  __syncthreads();
+  uint32_t warp_off = wid ? sh[wid - 1] : 0u;
+  total = sh[(blockDim.x >> 5) - 1];
+  return warp_off + x - v;
+}
+
+static __global__ void __launch_bounds__(SCAN_THREADS) k_msm_scan_sums(const uint32_t* __restrict__ counts, uint32_t B,
+                                                                        uint32_t* __restrict__ block_sums) {
+  __shared__ uint32_t sh[32];
+  uint32_t base = blockIdx.x * SCAN_BLOCK + threadIdx.x * SCAN_PER_THREAD;
+  uint32_t s = 0;
+#pragma unroll
+  for (uint32_t k = 0; k < SCAN_PER_THREAD; k++)
+    if (base + k < B) s += counts[base + k];
+  uint32_t total;
+  block_exclusive_scan(s, sh, total);
+  if (threadIdx.x == 0) block_sums[blockIdx.x] = total;
+}
+
+// single block: exclusive scan of nblocks block sums in place (nblocks <= SCAN_BLOCK * 64)
+static __global__ void __launch_bounds__(SCAN_THREADS) k_msm_scan_blocks(uint32_t* __restrict__ block_sums, uint32_t nblocks,
+                                                                          uint32_t* __restrict__ total_out) {
+  __shared__ uint32_t sh[32];
+  __shared__ uint32_t carry;
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  for (uint32_t base = 0; base < nblocks; base += SCAN_THREADS) {
+    uint32_t i = base + threadIdx.x;
+    uint32_t v = i < nblocks ? block_sums[i] : 0u;
+    uint32_t total;
+    uint32_t ex = block_exclusive_scan(v, sh, total);
+    uint32_t c = carry;
+    if (i < nblocks) block_sums[i] = c + ex;
     __syncthreads();
-    part[tid] += v;
+    if (threadIdx.x == 0) carry = c + total;
     __syncthreads();
   }
-  uint32_t run = part[tid] - s;  // exclusive prefix of this thread's chunk
-  for (uint32_t i = lo; i < hi; i++) {
-    offsets[i] = run;
-    cursor[i] = run;
-    run += counts[i];
+  if (threadIdx.x == 0) *total_out = carry;
+}
+
+static __global__ void __launch_bounds__(SCAN_THREADS) k_msm_scan_final(const uint32_t* __restrict__ counts, uint32_t B,
+                                                                         const uint32_t* __restrict__ block_sums,
+                                                                         uint32_t* __restrict__ offsets,
+                                                                         uint32_t* __restrict__ cursor) {
+  __shared__ uint32_t sh[32];
+  uint32_t base = blockIdx.x * SCAN_BLOCK + threadIdx.x * SCAN_PER_THREAD;
+  uint32_t v[SCAN_PER_THREAD];
+  uint32_t s = 0;
+#pragma unroll
+  for (uint32_t k = 0; k < SCAN_PER_THREAD; k++) {
+    v[k] = (base + k < B) ? counts[base + k] : 0u;
+    s += v[k];
   }
-  if (tid == 1023) offsets[B] = part[1023];
+  uint32_t total;
+  uint32_t run = block_sums[blockIdx.x] + block_exclusive_scan(s, sh, total);
+#pragma unroll
+  for (uint32_t k = 0; k < SCAN_PER_THREAD; k++) {
+    if (base + k < B) {
+      offsets[base + k] = run;
+      cursor[base + k] = run;
+    }
+    run += v[k];
+  }
 }
 
 static __global__ void k_msm_scatter(const Fr* __restrict__ scalars, size_t n, int mont, int c, int nwin, int win_lo,
@@ -183,19 +247,48 @@ __device__ __forceinline__ XYZZ<F> shfl_down_point(const XYZZ<F>& v, int delta) 
   return r;
 }
 
-// one warp per bucket that spans several tasks: tail[t0] + head[t0+1] + head[t0+2] + ...
+constexpr uint32_t FIXUP_SERIAL_MAX = 24;  // spans up to this many tasks are summed by one thread
+
+// Buckets that span several tasks: tail[t0] + head[t0+1] + head[t0+2] + ...  One thread per bucket; the
+// rare long spans (hot buckets of a skewed scalar distribution) are deferred to the warp kernel below.
 template <class F>
 __global__ void __launch_bounds__(128)
     k_msm_fixup(const XYZZ<F>* __restrict__ head, const XYZZ<F>* __restrict__ tail,
                 const uint32_t* __restrict__ head_key, const uint32_t* __restrict__ tail_key,
                 const uint32_t* __restrict__ tail_list, const uint32_t* __restrict__ ntail, uint32_t ntasks,
-                XYZZ<F>* __restrict__ buckets) {
+                uint32_t* __restrict__ big_list, uint32_t* __restrict__ nbig, XYZZ<F>* __restrict__ buckets) {
+  const uint32_t nt = *ntail;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < nt; i += gridDim.x * blockDim.x) {
+    const uint32_t t0 = tail_list[i];
+    const uint32_t key = tail_key[t0];
+    uint32_t span = 0;
+    while (span <= FIXUP_SERIAL_MAX && (uint64_t)t0 + 1 + span < ntasks && head_key[t0 + 1 + span] == key) span++;
+    if (span > FIXUP_SERIAL_MAX) {
+      big_list[atomicAdd(nbig, 1u)] = t0;
+      continue;
+    }
+    XYZZ<F> acc = ld_struct(tail + t0);
+    for (uint32_t k = 0; k < span; k++) {
+      XYZZ<F> h = ld_struct(head + t0 + 1 + k);
+      add_full(acc, h);
+    }
+    st_struct(buckets + key, acc);
+  }
+}
+
+// one warp per long-span bucket
+template <class F>
+__global__ void __launch_bounds__(128)
+    k_msm_fixup_big(const XYZZ<F>* __restrict__ head, const XYZZ<F>* __restrict__ tail,
+                    const uint32_t* __restrict__ head_key, const uint32_t* __restrict__ tail_key,
+                    const uint32_t* __restrict__ big_list, const uint32_t* __restrict__ nbig, uint32_t ntasks,
+                    XYZZ<F>* __restrict__ buckets) {
   const uint32_t lane = threadIdx.x & 31u;
   const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
-  const uint32_t nt = *ntail;
+  const uint32_t nt = *nbig;
   for (uint32_t i = warp; i < nt; i += nwarps) {
-    const uint32_t t0 = tail_list[i];
+    const uint32_t t0 = big_list[i];
     const uint32_t key = tail_key[t0];
     XYZZ<F> acc = XYZZ<F>::inf();
     if (lane == 0) acc = tail[t0];
@@ -203,7 +296,7 @@ __global__ void __launch_bounds__(128)
       XYZZ<F> h = head[t];
       add_full(acc, h);
     }
-#pragma unroll
+#pragma unroll 1
     for (int d = 16; d >= 1; d >>= 1) {
       XYZZ<F> o = shfl_down_point(acc, d);
       if ((int)lane < d) add_full(acc, o);
@@ -305,17 +398,21 @@ static int msm_dev_impl(gpw_ctx* ctx, const Fr* scalars, const Affine<F>* points
   const uint32_t chunk = half < 16u ? half : 16u;
   const uint32_t nchunks = half / chunk;
 
-  uint32_t *counts, *offsets, *cursor, *sorted, *head_key, *tail_key, *tail_list, *ntail;
+  uint32_t *counts, *offsets, *cursor, *sorted, *head_key, *tail_key, *tail_list, *ntail, *nbig, *big_list, *block_sums;
   XYZZ<F>*buckets, *head, *tail, *partials, *wsums;
   std::string T(tag);
   GPW_TRY(ctx->get_scratch((T + ".counts").c_str(), (size_t)(B + 1) * 4 * 3 + 64, (void**)&counts));
   offsets = counts + (B + 1);
   cursor = offsets + (B + 1);
   ntail = cursor + (B + 1);
+  nbig = ntail + 1;
+  const uint32_t nscan_blocks = (B + SCAN_BLOCK - 1) / SCAN_BLOCK;
+  GPW_TRY(ctx->get_scratch((T + ".scanblk").c_str(), (size_t)nscan_blocks * 4 + 16, (void**)&block_sums));
   GPW_TRY(ctx->get_scratch((T + ".sorted").c_str(), (size_t)max_entries * 4 + 16, (void**)&sorted));
-  GPW_TRY(ctx->get_scratch((T + ".keys").c_str(), (size_t)ntasks * 4 * 3, (void**)&head_key));
+  GPW_TRY(ctx->get_scratch((T + ".keys").c_str(), (size_t)ntasks * 4 * 4, (void**)&head_key));
   tail_key = head_key + ntasks;
   tail_list = tail_key + ntasks;
+  big_list = tail_list + ntasks;
   GPW_TRY(ctx->get_scratch((T + ".buckets").c_str(), (size_t)B * sizeof(XYZZ<F>), (void**)&buckets));
   GPW_TRY(ctx->get_scratch((T + ".head").c_str(), (size_t)ntasks * sizeof(XYZZ<F>), (void**)&head));
   GPW_TRY(ctx->get_scratch((T + ".tail").c_str(), (size_t)ntasks * sizeof(XYZZ<F>), (void**)&tail));
@@ -329,7 +426,11 @@ static int msm_dev_impl(gpw_ctx* ctx, const Fr* scalars, const Affine<F>* points
   const int TPB = 256;
   k_msm_count<<<div_up(n, TPB), TPB, 0, st>>>(scalars, n, mont, c, nwin, win_lo, win_hi, counts);
   GPW_CHECK_LAUNCH();
-  k_msm_scan<<<1, 1024, 0, st>>>(counts, B, offsets, cursor);
+  k_msm_scan_sums<<<nscan_blocks, SCAN_THREADS, 0, st>>>(counts, B, block_sums);
+  GPW_CHECK_LAUNCH();
+  k_msm_scan_blocks<<<1, SCAN_THREADS, 0, st>>>(block_sums, nscan_blocks, offsets + B);
+  GPW_CHECK_LAUNCH();
+  k_msm_scan_final<<<nscan_blocks, SCAN_THREADS, 0, st>>>(counts, B, block_sums, offsets, cursor);
   GPW_CHECK_LAUNCH();
   k_msm_scatter<<<div_up(n, TPB), TPB, 0, st>>>(scalars, n, mont, c, nwin, win_lo, win_hi, cursor, sorted);
   GPW_CHECK_LAUNCH();
@@ -338,13 +439,16 @@ static int msm_dev_impl(gpw_ctx* ctx, const Fr* scalars, const Affine<F>* points
                                                           tail_key, tail_list, ntail);
   GPW_CHECK_LAUNCH();
   GPW_CUDA(cudaEventRecord(ctx->ev[2], st));
-  k_msm_fixup<F><<<ctx->sm_count * 4, 128, 0, st>>>(head, tail, head_key, tail_key, tail_list, ntail, ntasks, buckets);
+  k_msm_fixup<F><<<ctx->sm_count * 8, 128, 0, st>>>(head, tail, head_key, tail_key, tail_list, ntail, ntasks, big_list,
+                                                    nbig, buckets);
+  GPW_CHECK_LAUNCH();
+  k_msm_fixup_big<F><<<ctx->sm_count * 4, 128, 0, st>>>(head, tail, head_key, tail_key, big_list, nbig, ntasks, buckets);
   GPW_CHECK_LAUNCH();
   k_msm_window_partial<F><<<div_up((size_t)nw * nchunks, 128), 128, 0, st>>>(buckets, half, chunk, (uint32_t)nw, partials);
   GPW_CHECK_LAUNCH();
   k_msm_window_final<F><<<nw, 128, 128 * sizeof(XYZZ<F>), st>>>(partials, nchunks, wsums);
   GPW_CHECK_LAUNCH();
-  ctx->launches += 7;
+  ctx->launches += 10;
   std::vector<XYZZ<F>> hw(nw);
   uint32_t M = 0;
   GPW_CUDA(cudaMemcpyAsync(hw.data(), wsums, (size_t)nw * sizeof(XYZZ<F>), cudaMemcpyDeviceToHost, st));

@@ -60,6 +60,15 @@ SYMBOLS = {
     "gpw_msm_last_stats": (C.c_int, [_vp, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_uint64)]),
     "gpw_ntt_fr": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
     "gpw_ntt_fr_dev": (C.c_int, [_vp, C.c_uint64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
+    "gpw_fr_h_pointwise_dev": (C.c_int, [_vp, C.c_uint64, C.c_uint64, C.c_uint64, C.c_size_t, _vp]),
+    "gpw_fr_convert_dev": (C.c_int, [_vp, C.c_uint64, C.c_size_t, C.c_int]),
+    "gpw_ec_generator_multiples_dev": (C.c_int, [_vp, C.c_int, C.c_uint64, C.c_size_t, C.c_uint64]),
+    "gpw_groth16_pk_synthetic": (C.c_int, [_vp, C.c_size_t, C.c_size_t, C.c_int, C.c_uint64, C.POINTER(_vp)]),
+    "gpw_groth16_pk_free": (None, [_vp]),
+    "gpw_groth16_pk_info": (C.c_int, [_vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_int)]),
+    "gpw_groth16_compute_h_dev": (C.c_int, [_vp, C.c_uint64, C.c_uint64, C.c_uint64, C.c_int]),
+    "gpw_groth16_prove_dev": (C.c_int, [_vp, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64, _vp, _vp, _vp]),
+    "gpw_groth16_last_stats": (C.c_int, [_vp, C.POINTER(C.c_float), C.POINTER(C.c_float)]),
     "gpw_poseidon_bn254": (C.c_int, [_vp, _vp, _vp, C.c_size_t, C.c_int]),
     "gpw_poseidon_bn254_dev": (C.c_int, [_vp, C.c_uint64, C.c_uint64, C.c_size_t, C.c_int]),
     "gpw_merkle_paths_bn254": (C.c_int, [_vp, _vp, _vp, _vp, C.c_size_t, C.c_int, _vp]),
@@ -266,6 +275,22 @@ class Context:
     def ntt_dev(self, data_ptr, logn, inverse=False, coset=False, in_bitrev=False, out_bitrev=False):
         _check(_lib.gpw_ntt_fr_dev(self._h, data_ptr, logn, int(inverse), int(coset), int(in_bitrev), int(out_bitrev)))
 
+    def h_pointwise_dev(self, a_ptr, b_ptr, c_ptr, n, k_mont):
+        k = _u64(k_mont, (4,))
+        _check(_lib.gpw_fr_h_pointwise_dev(self._h, a_ptr, b_ptr, c_ptr, n, _p(k)))
+
+    def fr_convert_dev(self, ptr, n, to_mont=True):
+        _check(_lib.gpw_fr_convert_dev(self._h, ptr, n, int(to_mont)))
+
+    def generator_multiples_dev(self, group, k0, n, out_ptr):
+        _check(_lib.gpw_ec_generator_multiples_dev(self._h, group, k0, n, out_ptr))
+
+    def compute_h_dev(self, a_ptr, b_ptr, c_ptr, logn):
+        _check(_lib.gpw_groth16_compute_h_dev(self._h, a_ptr, b_ptr, c_ptr, logn))
+
+    def groth16_pk_synthetic(self, m, n_pub, logn, seed=0):
+        return ProvingKey(self, m, n_pub, logn, seed)
+
     # -- Poseidon / Merkle ---------------------------------------------------------------------------
     def poseidon_bn254(self, states, mont=False):
         states = _u64(states, (-1, 16))
@@ -324,3 +349,37 @@ class Context:
         hi, lo = np.empty_like(x), np.empty_like(x)
         _check(_lib.gpw_gl_split_limbs_hint(self._h, _p(x), x.size, _p(hi), _p(lo)))
         return hi, lo
+
+
+class ProvingKey:
+    """gpw_pk: device-resident Groth16 proving key (synthetic, known discrete logs)."""
+
+    def __init__(self, ctx, m, n_pub, logn, seed=0):
+        h = _vp()
+        _check(_lib.gpw_groth16_pk_synthetic(ctx._h, m, n_pub, logn, seed, C.byref(h)))
+        self._h, self.ctx, self.m, self.n_pub, self.logn, self.seed = h, ctx, m, n_pub, logn, seed
+
+    def close(self):
+        if self._h:
+            _lib.gpw_groth16_pk_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def prove_dev(self, w_ptr, a_ptr, b_ptr, c_ptr, r_int, s_int):
+        """-> (Ar[8], Bs[16], Krs[8]) affine Montgomery limbs"""
+        r = ints_to_limbs([r_int])[0]
+        s = ints_to_limbs([s_int])[0]
+        out = np.zeros(32, dtype=np.uint64)
+        _check(_lib.gpw_groth16_prove_dev(self._h, w_ptr, a_ptr, b_ptr, c_ptr, _p(r), _p(s), _p(out)))
+        return out[:8].copy(), out[8:24].copy(), out[24:].copy()
+
+    def last_stats(self):
+        h = C.c_float()
+        ms = (C.c_float * 5)()
+        _check(_lib.gpw_groth16_last_stats(self._h, C.byref(h), ms))
+        return {"compute_h_ms": h.value, "msm_ms": dict(zip(("A", "B1", "B2", "K", "Z"), [float(x) for x in ms]))}

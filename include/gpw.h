@@ -97,6 +97,32 @@ int gpw_msm_last_stats(gpw_ctx* ctx, float* accumulate_ms, float* total_ms, uint
 int gpw_ntt_fr(gpw_ctx* ctx, uint64_t* data, int logn, int inverse, int coset, int in_bitrev, int out_bitrev);
 int gpw_ntt_fr_dev(gpw_ctx* ctx, uint64_t data_dev, int logn, int inverse, int coset, int in_bitrev, int out_bitrev);
 
+/* ---- Groth16 prover glue (gnark backend/groth16 bn254 Prove, benchmark.go:249) -----------
+ * computeH pointwise step on the coset: a[i] = (a[i] * b[i] - c[i]) * k, all Fr Montgomery, device.   */
+int gpw_fr_h_pointwise_dev(gpw_ctx* ctx, uint64_t a_dev, uint64_t b_dev, uint64_t c_dev, size_t n, const uint64_t* k_mont);
+/* In-place canonical <-> Montgomery conversion of n Fr elements on the device (to_mont != 0: into Montgomery). */
+int gpw_fr_convert_dev(gpw_ctx* ctx, uint64_t a_dev, size_t n, int to_mont);
+/* out[i] = [k0 + i] G (affine, mont) for the fixed generator of G1 (group 1) or G2 (group 2), written to
+ * device memory: synthetic proving-key bases for benchmarks / tests (what gnark's DummySetup provides). */
+int gpw_ec_generator_multiples_dev(gpw_ctx* ctx, int group, uint64_t k0, size_t n, uint64_t out_dev);
+
+/* Proving key handle (device-resident bases). gnark: groth16.ProvingKey (benchmark.go:214-217).           */
+typedef struct gpw_pk gpw_pk;
+/* Synthetic key with the shapes / cost of a real one and KNOWN discrete logs (see csrc/groth16.cu): the
+ * analogue of groth16.DummySetup (benchmark.go:214). m wires (wire 0 = constant one), the first n_pub are
+ * public, FFT domain 2^logN.                                                                            */
+int gpw_groth16_pk_synthetic(gpw_ctx* ctx, size_t m, size_t n_pub, int logN, uint64_t seed, gpw_pk** out);
+void gpw_groth16_pk_free(gpw_pk* pk);
+int gpw_groth16_pk_info(const gpw_pk* pk, uint64_t* m, uint64_t* n_pub, int* logN);
+/* computeH: a <- coefficients of (A.B - C)/Z_H, natural order; a, b, c are N = 2^logN evaluations on H.  */
+int gpw_groth16_compute_h_dev(gpw_ctx* ctx, uint64_t a_dev, uint64_t b_dev, uint64_t c_dev, int logN);
+/* groth16.Prove after the solve (benchmark.go:249): computeH + the five MSMs + assembly. r, s canonical.
+ * out = Ar (8 u64) | Bs (16 u64) | Krs (8 u64), affine Montgomery coordinates.                          */
+int gpw_groth16_prove_dev(gpw_pk* pk, uint64_t w_dev, uint64_t a_dev, uint64_t b_dev, uint64_t c_dev,
+                          const uint64_t* r_canonical, const uint64_t* s_canonical, uint64_t* out_proof);
+/* ms spent in computeH and in each of the MSMs {A, B1, B2, K, Z} of the last prove (CUDA events).        */
+int gpw_groth16_last_stats(const gpw_pk* pk, float* h_ms, float* msm_ms5);
+
 /* ---- K3: Poseidon over BN254 Fr (t = 4) ---------------------------------------------------------
  * Replaces poseidon.BN254Chip.Poseidon (poseidon/bn254.go:39-45). states: n x 4 Fr in / out.   */
 int gpw_poseidon_bn254(gpw_ctx* ctx, const uint64_t* states_in, uint64_t* states_out, size_t n, int mont);
@@ -120,8 +146,7 @@ int gpw_gl_split_limbs_hint(gpw_ctx* ctx, const uint64_t* x, size_t n, uint64_t*
 
 /* ---- K2: Poseidon over Goldilocks (width 12) ------------------------------------------------------
  * Replaces poseidon.GoldilocksChip.Poseidon (poseidon/goldilocks.go:30-37). states: n x 12 u64.
- * If trace_out != NULL it receives, per permutation, the (q, r) outputs of every hint in the
- * reference's order (see DESIGN.md "Poseidon-GL trace layout"), trace_stride u64 per permutation.  */
+ * (plain permutation; the per-hint (q, r) witness trace is produced by the tape executor.)        */
 int gpw_poseidon_gl(gpw_ctx* ctx, const uint64_t* states_in, uint64_t* states_out, size_t n);
 
 #ifdef __cplusplus
