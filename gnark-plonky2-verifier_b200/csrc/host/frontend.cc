@@ -1,0 +1,373 @@
+#include "frontend.h"
+
+#include <algorithm>
+
+namespace gpw {
+namespace fe {
+
+Fr fr_from_u64(uint64_t v) {
+  Fr a = Fr::zero();
+  a.l[0] = (uint32_t)v;
+  a.l[1] = (uint32_t)(v >> 32);
+  return to_mont(a);
+}
+
+Fr fr_from_limbs(const uint64_t l[4]) {
+  Fr a;
+  memcpy(a.l, l, 32);
+  return to_mont(a);
+}
+
+void fr_to_limbs(const Fr& a, uint64_t l[4]) {
+  Fr c = from_mont(a);
+  memcpy(l, c.l, 32);
+}
+
+Fr fr_from_dec(const std::string& s) {
+  Fr acc = Fr::zero();
+  const Fr ten = fr_from_u64(10);
+  for (char ch : s) {
+    if (ch < '0' || ch > '9') throw std::invalid_argument("fr_from_dec: not a decimal string: " + s);
+    acc = add(mul(acc, ten), fr_from_u64((uint64_t)(ch - '0')));
+  }
+  return acc;
+}
+
+API::API() {
+  wire_level_.push_back(0);  // ONE
+  wire_bool_.push_back(1);
+  coeffs_.push_back(Fr::one());       // COEFF_ONE
+  coeffs_.push_back(neg(Fr::one()));  // COEFF_NEG_ONE
+  coeff_ids_[coeffs_[0]] = 0;
+  coeff_ids_[coeffs_[1]] = 1;
+  le_off_.push_back(0);
+}
+
+uint32_t API::new_wire(uint32_t level) {
+  uint32_t w = next_wire_++;
+  wire_level_.push_back(level);
+  wire_bool_.push_back(0);
+  if (level > max_level_) max_level_ = level;
+  return w;
+}
+
+Variable API::PublicInput() {
+  if (inputs_closed_ || n_secret_) throw std::logic_error("public inputs must be declared first");
+  n_public_++;
+  return wire_var(new_wire(0));
+}
+
+Variable API::SecretInput() {
+  if (inputs_closed_) throw std::logic_error("inputs already closed");
+  n_secret_++;
+  return wire_var(new_wire(0));
+}
+
+Variable API::wire_var(uint32_t w) const {
+  Variable v;
+  v.t.push_back({w, Fr::one()});
+  return v;
+}
+
+Variable API::Const(uint64_t v) const { return ConstFr(fr_from_u64(v)); }
+
+Variable API::ConstFr(const Fr& c) const {
+  Variable v;
+  if (!c.is_zero()) v.t.push_back({0, c});
+  return v;
+}
+
+bool API::const_value(const Variable& v, Fr* out) const {
+  if (v.t.empty()) {
+    *out = Fr::zero();
+    return true;
+  }
+  if (v.t.size() == 1 && v.t[0].wire == 0) {
+    *out = v.t[0].coeff;
+    return true;
+  }
+  return false;
+}
+
+Variable API::Add(const Variable& a, const Variable& b) const {
+  Variable r;
+  r.t.reserve(a.t.size() + b.t.size());
+  size_t i = 0, j = 0;
+  while (i < a.t.size() && j < b.t.size()) {
+    if (a.t[i].wire < b.t[j].wire) r.t.push_back(a.t[i++]);
+    else if (a.t[i].wire > b.t[j].wire) r.t.push_back(b.t[j++]);
+    else {
+      Fr c = add(a.t[i].coeff, b.t[j].coeff);
+      if (!c.is_zero()) r.t.push_back({a.t[i].wire, c});
+      i++, j++;
+    }
+  }
+  while (i < a.t.size()) r.t.push_back(a.t[i++]);
+  while (j < b.t.size()) r.t.push_back(b.t[j++]);
+  return r;
+}
+
+Variable API::Neg(const Variable& a) const {
+  Variable r = a;
+  for (auto& t : r.t) t.coeff = neg(t.coeff);
+  return r;
+}
+
+Variable API::Sub(const Variable& a, const Variable& b) const { return Add(a, Neg(b)); }
+
+Variable API::MulConst(const Variable& a, const Fr& c) const {
+  Variable r;
+  if (c.is_zero()) return r;
+  if (c == Fr::one()) return a;
+  r.t.reserve(a.t.size());
+  for (const auto& t : a.t) r.t.push_back({t.wire, mul(t.coeff, c)});
+  return r;
+}
+
+uint32_t API::level_of(const Variable& v) const {
+  uint32_t l = 0;
+  for (const auto& t : v.t) l = std::max(l, wire_level_[t.wire]);
+  return l;
+}
+
+uint32_t API::intern_coeff(const Fr& c) {
+  auto it = coeff_ids_.find(c);
+  if (it != coeff_ids_.end()) return it->second;
+  uint32_t id = (uint32_t)coeffs_.size();
+  coeffs_.push_back(c);
+  coeff_ids_[c] = id;
+  return id;
+}
+
+uint32_t API::intern_le(const Variable& v) {
+  if (v.t.size() == 1 && v.t[0].wire == 0 && v.t[0].coeff == Fr::one()) {
+    if (le_one_ != NO_LE) return le_one_;
+  }
+  uint32_t id = (uint32_t)le_off_.size() - 1;
+  for (const auto& t : v.t) {
+    le_wire_.push_back(t.wire);
+    le_coeff_.push_back(intern_coeff(t.coeff));
+  }
+  le_off_.push_back((uint32_t)le_wire_.size());
+  if (v.t.size() == 1 && v.t[0].wire == 0 && v.t[0].coeff == Fr::one()) le_one_ = id;
+  return id;
+}
+
+void API::add_constraint(const Variable& l, const Variable& r, const Variable& o) {
+  cons_.push_back(intern_le(l));
+  cons_.push_back(intern_le(r));
+  cons_.push_back(intern_le(o));
+}
+
+Variable API::Mul(const Variable& a, const Variable& b) {
+  Fr c;
+  if (const_value(a, &c)) return MulConst(b, c);
+  if (const_value(b, &c)) return MulConst(a, c);
+  uint32_t lvl = std::max(level_of(a), level_of(b)) + 1;
+  uint32_t w = new_wire(lvl);
+  uint32_t la = intern_le(a), lb = intern_le(b);
+  tape_.push_back({OP_MUL, w, 1, {la, lb, NO_LE}, lvl});
+  Variable out = wire_var(w);
+  cons_.push_back(la);
+  cons_.push_back(lb);
+  cons_.push_back(intern_le(out));
+  counts_.mul++;
+  return out;
+}
+
+std::vector<Variable> API::NewHint(Op op, uint32_t nout, const Variable* a, const Variable* b, const Variable* c) {
+  uint32_t lvl = 0;
+  uint32_t le[3] = {NO_LE, NO_LE, NO_LE};
+  const Variable* in[3] = {a, b, c};
+  for (int i = 0; i < 3; i++)
+    if (in[i]) {
+      lvl = std::max(lvl, level_of(*in[i]));
+      le[i] = intern_le(*in[i]);
+    }
+  lvl += 1;
+  uint32_t first = next_wire_;
+  std::vector<Variable> outs;
+  outs.reserve(nout);
+  for (uint32_t i = 0; i < nout; i++) outs.push_back(wire_var(new_wire(lvl)));
+  tape_.push_back({(uint8_t)op, first, nout, {le[0], le[1], le[2]}, lvl});
+  switch (op) {
+    case OP_HINT_MULADD: counts_.muladd++; break;
+    case OP_HINT_REDUCE: counts_.reduce++; break;
+    case OP_HINT_GLINV: counts_.glinv++; break;
+    case OP_HINT_SPLIT: counts_.split++; break;
+    case OP_INVZERO: counts_.invzero++; break;
+    case OP_BITS: counts_.bits++; break;
+    case OP_DIV: counts_.div++; break;
+    case OP_DECOMP: counts_.decomp++; break;
+    default: break;
+  }
+  return outs;
+}
+
+Variable API::IsZero(const Variable& a) {
+  Fr c;
+  if (const_value(a, &c)) return Const(c.is_zero() ? 1 : 0);
+  // x = 1/a (0 if a == 0);  m = 1 - a x;  a m = 0      (gnark r1cs builder IsZero)
+  Variable x = NewHint(OP_INVZERO, 1, &a)[0];
+  Variable na = Neg(a);
+  uint32_t lvl = std::max(level_of(a), level_of(x)) + 1;
+  uint32_t m = new_wire(lvl);
+  wire_bool_[m] = 1;
+  Variable one = Const(1);
+  uint32_t l0 = intern_le(na), l1 = intern_le(x), l2 = intern_le(one);
+  tape_.push_back({OP_MUL, m, 1, {l0, l1, l2}, lvl});  // m = (-a) x + 1
+  Variable mv = wire_var(m);
+  cons_.push_back(l0);
+  cons_.push_back(l1);
+  cons_.push_back(intern_le(Sub(mv, one)));
+  add_constraint(a, mv, Variable());
+  counts_.mul++;
+  return mv;
+}
+
+void API::AssertIsBoolean(const Variable& b) {
+  Fr c;
+  if (const_value(b, &c)) {
+    if (!(c.is_zero() || c == Fr::one())) throw std::logic_error("AssertIsBoolean: constant is not 0/1");
+    return;
+  }
+  if (b.t.size() == 1 && b.t[0].coeff == Fr::one() && wire_bool_[b.t[0].wire]) return;
+  add_constraint(b, Sub(Const(1), b), Variable());
+  if (b.t.size() == 1 && b.t[0].coeff == Fr::one()) wire_bool_[b.t[0].wire] = 1;
+}
+
+Variable API::Select(const Variable& b, const Variable& i1, const Variable& i2) {
+  Fr c;
+  if (const_value(b, &c)) {
+    if (c == Fr::one()) return i1;
+    if (c.is_zero()) return i2;
+    throw std::logic_error("Select: constant condition is not boolean");
+  }
+  AssertIsBoolean(b);
+  Variable d = Sub(i1, i2);
+  if (d.is_zero()) return i2;
+  return Add(Mul(b, d), i2);
+}
+
+Variable API::Lookup2(const Variable& b0, const Variable& b1, const Variable& i0, const Variable& i1,
+                      const Variable& i2, const Variable& i3) {
+  Variable s0 = Select(b0, i1, i0);
+  Variable s1 = Select(b0, i3, i2);
+  return Select(b1, s1, s0);
+}
+
+std::vector<Variable> API::ToBinary(const Variable& v, int n) {
+  Fr c;
+  if (const_value(v, &c)) {
+    uint64_t l[4];
+    fr_to_limbs(c, l);
+    std::vector<Variable> bits;
+    for (int i = 0; i < n; i++) bits.push_back(Const((l[i >> 6] >> (i & 63)) & 1));
+    for (int i = n; i < 256; i++)
+      if ((l[i >> 6] >> (i & 63)) & 1) throw std::logic_error("ToBinary: constant does not fit");
+    return bits;
+  }
+  std::vector<Variable> bits = NewHint(OP_BITS, (uint32_t)n, &v);
+  for (auto& b : bits) AssertIsBoolean(b);
+  AssertIsEqual(FromBinary(bits, 0, bits.size()), v);
+  return bits;
+}
+
+Variable API::FromBinary(const std::vector<Variable>& bits, size_t lo, size_t hi) const {
+  Variable acc;
+  Fr p = Fr::one();
+  for (size_t i = lo; i < hi; i++) {
+    acc = Add(acc, MulConst(bits[i], p));
+    p = dbl(p);
+  }
+  return acc;
+}
+
+Variable API::DivUnchecked(const Variable& a, const Variable& b) {
+  Fr c;
+  if (const_value(b, &c)) {
+    if (c.is_zero()) throw std::logic_error("DivUnchecked: division by constant zero");
+    return MulConst(a, inv(c));
+  }
+  Variable out = NewHint(OP_DIV, 1, &a, &b)[0];
+  add_constraint(out, b, a);
+  return out;
+}
+
+void API::AssertIsEqual(const Variable& a, const Variable& b) {
+  Fr ca, cb;
+  if (const_value(a, &ca) && const_value(b, &cb)) {
+    if (ca != cb) throw std::logic_error("AssertIsEqual: constants differ");
+    return;
+  }
+  add_constraint(a, Const(1), b);
+}
+
+void API::RangeCheckCollect(const Variable& v, int bits) {
+  if (bits % 16 != 0) throw std::logic_error("v.bits is not nbBits aligned");  // goldilocks/base.go:433-435
+  rc_.push_back({intern_le(v), bits});
+}
+
+uint64_t API::NumRangeCheckedLimbs() const {
+  uint64_t n = 0;
+  for (auto& p : rc_) n += (uint64_t)p.second / 16;
+  return n;
+}
+
+void API::Finalize() {
+  if (finalized_) throw std::logic_error("Finalize called twice");
+  finalized_ = true;
+  if (rc_.empty()) return;
+  // 1. limb decomposition of every collected value; all of it runs as ONE wide level after the main tape
+  const uint32_t decomp_level = max_level_ + 1;
+  limb_wire_start_ = next_wire_;
+  std::vector<Variable> all_limbs;
+  all_limbs.reserve(NumRangeCheckedLimbs());
+  for (auto& p : rc_) {
+    uint32_t k = (uint32_t)p.second / 16;
+    uint32_t first = next_wire_;
+    Variable acc;
+    Fr pw = Fr::one();
+    const Fr b16 = fr_from_u64(1u << 16);
+    for (uint32_t i = 0; i < k; i++) {
+      uint32_t w = new_wire(decomp_level);
+      Variable lv = wire_var(w);
+      all_limbs.push_back(lv);
+      acc.t.push_back({w, pw});
+      pw = mul(pw, b16);
+    }
+    tape_.push_back({OP_DECOMP, first, k, {p.first, NO_LE, NO_LE}, decomp_level});
+    counts_.decomp++;
+    // recomposition: sum limb_i 2^(16 i) == v
+    cons_.push_back(intern_le(acc));
+    cons_.push_back(intern_le(Const(1)));
+    cons_.push_back(p.first);
+  }
+  n_limb_wires_ = next_wire_ - limb_wire_start_;
+  // 2. multiplicities of the 2^16 table entries
+  const uint32_t count_level = decomp_level + 1;
+  count_wire_start_ = next_wire_;
+  for (uint32_t i = 0; i < 65536; i++) new_wire(count_level);
+  tape_.push_back({OP_COUNT, count_wire_start_, 65536, {NO_LE, NO_LE, NO_LE}, count_level});
+  // 3. commitment -> challenge X
+  commit_level_ = count_level + 1;
+  commit_wire_ = new_wire(commit_level_);
+  tape_.push_back({OP_COMMIT, commit_wire_, 1, {NO_LE, NO_LE, NO_LE}, commit_level_});
+  Variable X = wire_var(commit_wire_);
+  // 4. sum_i e_i / (X - i)  ==  sum_j 1 / (X - f_j)
+  Variable lhs, rhs;
+  Variable one = Const(1);
+  for (uint32_t i = 0; i < 65536; i++) {
+    Variable e = wire_var(count_wire_start_ + i);
+    Variable q = DivUnchecked(e, Sub(X, Const(i)));
+    lhs.t.push_back(q.t[0]);
+  }
+  for (auto& f : all_limbs) {
+    Variable q = DivUnchecked(one, Sub(X, f));
+    rhs.t.push_back(q.t[0]);
+  }
+  AssertIsEqual(lhs, rhs);
+}
+
+}  // namespace fe
+}  // namespace gpw

@@ -1,0 +1,304 @@
+// TEST INFRASTRUCTURE ONLY (built into tests/hostlib/libgpw_circuit_test.so; never linked into libgpw.so and not
+// reachable from any product entry point): a sequential host interpreter of the solver tape, used to validate
+// the C++ gadget library and the frontend on machines without a GPU, and as the reference the CUDA tape
+// executor is compared against wire-for-wire. It is NOT a fallback: the product solves witnesses on the GPU only.
+#include <cstdio>
+#include <cstring>
+#include <fstream>
+#include <sstream>
+#include <string>
+#include <vector>
+
+#include "../../gnark-plonky2-verifier_b200/csrc/gl.cuh"
+#include "../../gnark-plonky2-verifier_b200/csrc/host/frontend.h"
+#include "../../gnark-plonky2-verifier_b200/csrc/host/gadgets.h"
+
+using namespace gpw;
+using namespace gpw::fe;
+
+struct Circuit {
+  API api;
+  gadgets::CommonCircuitData cd;
+  std::vector<Fr> w;
+  std::string err;
+};
+
+static thread_local std::string g_err;
+
+static Fr eval_le(const Circuit& c, uint32_t le) {
+  const auto& off = c.api.LeOffsets();
+  const auto& wi = c.api.LeWires();
+  const auto& ci = c.api.LeCoeffIds();
+  const auto& co = c.api.Coeffs();
+  Fr acc = Fr::zero();
+  for (uint32_t k = off[le]; k < off[le + 1]; k++) {
+    const Fr& v = c.w[wi[k]];
+    if (ci[k] == API::COEFF_ONE) acc = add(acc, v);
+    else if (ci[k] == API::COEFF_NEG_ONE) acc = sub(acc, v);
+    else acc = add(acc, mul(co[ci[k]], v));
+  }
+  return acc;
+}
+
+static void canon(const Fr& a, uint64_t l[4]) { fr_to_limbs(a, l); }
+
+extern "C" {
+
+const char* ct_last_error() { return g_err.c_str(); }
+
+void* ct_compile(const char* common_json) {
+  try {
+    Circuit* c = new Circuit();
+    c->cd = gadgets::ReadCommonCircuitData(common_json);
+    gadgets::DefineVerifierCircuit(&c->api, c->cd);
+    return c;
+  } catch (const std::exception& e) {
+    g_err = e.what();
+    return nullptr;
+  }
+}
+
+// Small self-contained circuits for unit tests of the gadget port. kind: 0 = Poseidon-GL permutation of 12 secret
+// inputs, outputs asserted equal to 12 public inputs; 1 = Poseidon-BN254 (4 secret in, 4 public out);
+// 2 = QE mul + div (secret a, b; public out a*b and a/b); 3 = RangeCheck of one secret input.
+void* ct_compile_small(int kind) {
+  try {
+    Circuit* c = new Circuit();
+    API* api = &c->api;
+    gadgets::GlChip gl(api);
+    if (kind == 0) {
+      std::vector<Variable> out, in;
+      for (int i = 0; i < 12; i++) out.push_back(api->PublicInput());
+      for (int i = 0; i < 12; i++) in.push_back(api->SecretInput());
+      api->EndInputs();
+      gadgets::PoseidonGlChip p(api);
+      gadgets::GlState st;
+      for (int i = 0; i < 12; i++) st[i] = in[i];
+      st = p.Poseidon(st);
+      for (int i = 0; i < 12; i++) api->AssertIsEqual(st[i], out[i]);
+    } else if (kind == 1) {
+      std::vector<Variable> out, in;
+      for (int i = 0; i < 4; i++) out.push_back(api->PublicInput());
+      for (int i = 0; i < 4; i++) in.push_back(api->SecretInput());
+      api->EndInputs();
+      gadgets::PoseidonBn254Chip p(api);
+      auto st = p.Poseidon({in[0], in[1], in[2], in[3]});
+      for (int i = 0; i < 4; i++) api->AssertIsEqual(st[i], out[i]);
+    } else if (kind == 2) {
+      std::vector<Variable> out, in;
+      for (int i = 0; i < 4; i++) out.push_back(api->PublicInput());
+      for (int i = 0; i < 4; i++) in.push_back(api->SecretInput());
+      api->EndInputs();
+      gadgets::QE a = {in[0], in[1]}, b = {in[2], in[3]};
+      gadgets::QE m = gl.MulExtension(a, b);
+      auto d = gl.DivExtension(a, b);
+      api->AssertIsEqual(m[0], out[0]);
+      api->AssertIsEqual(m[1], out[1]);
+      api->AssertIsEqual(d.first[0], out[2]);
+      api->AssertIsEqual(d.first[1], out[3]);
+    } else if (kind == 3) {
+      Variable x = api->SecretInput();
+      api->EndInputs();
+      gl.RangeCheck(x);
+    } else {
+      throw std::runtime_error("unknown small circuit kind");
+    }
+    api->Finalize();
+    return c;
+  } catch (const std::exception& e) {
+    g_err = e.what();
+    return nullptr;
+  }
+}
+
+void ct_free(void* h) { delete (Circuit*)h; }
+
+// stats: [wires, public, secret, constraints, tape, levels, commit_level, limb_wires, muladd, reduce, glinv, split,
+//         invzero, bits, div, decomp, mul, coeffs, le_terms, limb_wire_start, count_wire_start, commit_wire]
+void ct_stats(void* h, uint64_t* out) {
+  Circuit* c = (Circuit*)h;
+  const auto& k = c->api.Counts();
+  uint64_t v[] = {c->api.NumWires(), c->api.NumPublic(), c->api.NumSecret(), c->api.NumConstraints(), c->api.Tape().size(),
+                  c->api.NumLevels(), c->api.CommitLevel(), c->api.NumLimbWires(), k.muladd, k.reduce, k.glinv, k.split,
+                  k.invzero, k.bits, k.div, k.decomp, k.mul, c->api.Coeffs().size(), c->api.LeWires().size(),
+                  c->api.LimbWireStart(), c->api.CountWireStart(), c->api.CommitWire()};
+  memcpy(out, v, sizeof(v));
+}
+
+// number of tape instructions per level (out has NumLevels entries)
+void ct_level_histogram(void* h, uint32_t* out) {
+  Circuit* c = (Circuit*)h;
+  for (uint32_t i = 0; i < c->api.NumLevels(); i++) out[i] = 0;
+  for (const auto& in : c->api.Tape()) out[in.level]++;
+}
+
+// inputs: canonical limbs. Returns 0 ok, <0 on hint precondition failure. x_commit: challenge used for OP_COMMIT.
+int ct_solve_inputs(void* h, const uint64_t* pub, size_t npub, const uint64_t* sec, size_t nsec, const uint64_t* x_commit) {
+  Circuit* c = (Circuit*)h;
+  API& api = c->api;
+  if (npub != api.NumPublic() || nsec != api.NumSecret()) {
+    g_err = "input count mismatch: circuit wants " + std::to_string(api.NumPublic()) + " public / " +
+            std::to_string(api.NumSecret()) + " secret";
+    return -1;
+  }
+  c->w.assign(api.NumWires(), Fr::zero());
+  c->w[0] = Fr::one();
+  for (size_t i = 0; i < npub; i++) c->w[1 + i] = fr_from_limbs(pub + 4 * i);
+  for (size_t i = 0; i < nsec; i++) c->w[1 + npub + i] = fr_from_limbs(sec + 4 * i);
+  std::vector<uint32_t> hist;
+  // the post-commitment DIVs are independent of each other: invert their denominators with Montgomery's trick
+  std::vector<const Instr*> divs;
+  for (const auto& in : api.Tape()) {
+    if (in.op == OP_DIV && in.level > api.CommitLevel() && api.CommitLevel() != 0) {
+      divs.push_back(&in);
+      continue;
+    }
+    switch (in.op) {
+      case OP_MUL: {
+        Fr r = mul(eval_le(*c, in.le[0]), eval_le(*c, in.le[1]));
+        if (in.le[2] != NO_LE) r = add(r, eval_le(*c, in.le[2]));
+        c->w[in.out] = r;
+        break;
+      }
+      case OP_HINT_MULADD: {
+        uint64_t a[4], b[4], d[4];
+        canon(eval_le(*c, in.le[0]), a);
+        canon(eval_le(*c, in.le[1]), b);
+        canon(eval_le(*c, in.le[2]), d);
+        if (a[1] | a[2] | a[3] | b[1] | b[2] | b[3] | d[1] | d[2] | d[3] || a[0] >= gl::P || b[0] >= gl::P || d[0] >= gl::P) {
+          g_err = "MulAddHint: operand is not in the field";  // base.go:228-232
+          return -5;
+        }
+        uint64_t q, r;
+        gl::mul_add_hint(a[0], b[0], d[0], q, r);
+        c->w[in.out] = fr_from_u64(q);
+        c->w[in.out + 1] = fr_from_u64(r);
+        break;
+      }
+      case OP_HINT_REDUCE: {
+        uint64_t x[4], q[4], r;
+        canon(eval_le(*c, in.le[0]), x);
+        gl::reduce_hint(x, q, r);
+        c->w[in.out] = fr_from_limbs(q);
+        c->w[in.out + 1] = fr_from_u64(r);
+        break;
+      }
+      case OP_HINT_GLINV: {
+        uint64_t x[4];
+        canon(eval_le(*c, in.le[0]), x);
+        if (x[1] | x[2] | x[3] || x[0] >= gl::P) {
+          g_err = "InverseHint: input is not in the field";
+          return -5;
+        }
+        c->w[in.out] = fr_from_u64(gl::inverse(x[0]));
+        break;
+      }
+      case OP_HINT_SPLIT: {
+        uint64_t x[4];
+        canon(eval_le(*c, in.le[0]), x);
+        if (x[1] | x[2] | x[3] || x[0] >= gl::P) {
+          g_err = "SplitLimbsHint: input is not in the field";
+          return -5;
+        }
+        c->w[in.out] = fr_from_u64(x[0] >> 32);
+        c->w[in.out + 1] = fr_from_u64(x[0] & 0xffffffffull);
+        break;
+      }
+      case OP_INVZERO: c->w[in.out] = inv(eval_le(*c, in.le[0])); break;
+      case OP_BITS: {
+        uint64_t x[4];
+        canon(eval_le(*c, in.le[0]), x);
+        for (uint32_t i = 0; i < in.nout; i++) c->w[in.out + i] = fr_from_u64((x[i >> 6] >> (i & 63)) & 1);
+        break;
+      }
+      case OP_DIV: c->w[in.out] = mul(eval_le(*c, in.le[0]), inv(eval_le(*c, in.le[1]))); break;
+      case OP_DECOMP: {
+        uint64_t x[4];
+        canon(eval_le(*c, in.le[0]), x);
+        for (uint32_t i = 0; i < in.nout; i++) c->w[in.out + i] = fr_from_u64((x[(16 * i) >> 6] >> ((16 * i) & 63)) & 0xffff);
+        break;
+      }
+      case OP_COUNT: {
+        hist.assign(65536, 0);
+        for (uint32_t i = 0; i < api.NumLimbWires(); i++) {
+          uint64_t x[4];
+          canon(c->w[api.LimbWireStart() + i], x);
+          hist[x[0] & 0xffff]++;
+        }
+        for (uint32_t i = 0; i < 65536; i++) c->w[in.out + i] = fr_from_u64(hist[i]);
+        break;
+      }
+      case OP_COMMIT: c->w[in.out] = fr_from_limbs(x_commit); break;
+      default: g_err = "unknown opcode"; return -1;
+    }
+  }
+  if (!divs.empty()) {
+    std::vector<Fr> den(divs.size()), pref(divs.size());
+    Fr run = Fr::one();
+    for (size_t i = 0; i < divs.size(); i++) {
+      den[i] = eval_le(*c, divs[i]->le[1]);
+      pref[i] = run;
+      run = mul(run, den[i]);
+    }
+    Fr irun = inv(run);
+    for (size_t i = divs.size(); i-- > 0;) {
+      Fr di = mul(irun, pref[i]);
+      irun = mul(irun, den[i]);
+      c->w[divs[i]->out] = mul(eval_le(*c, divs[i]->le[0]), di);
+    }
+  }
+  return 0;
+}
+
+int ct_solve_testdata(void* h, const char* proof_json, const char* vo_json, const uint64_t* x_commit) {
+  Circuit* c = (Circuit*)h;
+  try {
+    gadgets::InputValues iv = gadgets::ParseProofInputs(c->cd, proof_json, vo_json);
+    return ct_solve_inputs(h, (const uint64_t*)iv.pub.data(), iv.pub.size(), (const uint64_t*)iv.sec.data(), iv.sec.size(), x_commit);
+  } catch (const std::exception& e) {
+    g_err = e.what();
+    return -1;
+  }
+}
+
+// number of unsatisfied constraints; first_bad receives the index of the first one (or -1)
+uint64_t ct_check(void* h, int64_t* first_bad) {
+  Circuit* c = (Circuit*)h;
+  const auto& cons = c->api.Constraints();
+  uint64_t bad = 0;
+  *first_bad = -1;
+  for (size_t k = 0; k < cons.size() / 3; k++) {
+    Fr l = eval_le(*c, cons[3 * k]), r = eval_le(*c, cons[3 * k + 1]), o = eval_le(*c, cons[3 * k + 2]);
+    if (mul(l, r) != o) {
+      if (!bad) *first_bad = (int64_t)k;
+      bad++;
+    }
+  }
+  return bad;
+}
+
+// outputs of every hint of one kind, in tape order; each output as 4 canonical limbs. Returns the number of u64 written.
+size_t ct_hint_outputs(void* h, int op, uint64_t* out, size_t cap_u64) {
+  Circuit* c = (Circuit*)h;
+  size_t n = 0;
+  for (const auto& in : c->api.Tape()) {
+    if (in.op != op) continue;
+    for (uint32_t i = 0; i < in.nout; i++) {
+      if (n + 4 > cap_u64) return n;
+      canon(c->w[in.out + i], out + n);
+      n += 4;
+    }
+  }
+  return n;
+}
+
+void ct_wire_values(void* h, uint64_t first, uint64_t count, uint64_t* out) {
+  Circuit* c = (Circuit*)h;
+  for (uint64_t i = 0; i < count; i++) canon(c->w[first + i], out + 4 * i);
+}
+
+void ct_wires_mont(void* h, uint64_t* out) {
+  Circuit* c = (Circuit*)h;
+  memcpy(out, c->w.data(), c->w.size() * sizeof(Fr));
+}
+}

@@ -1,0 +1,121 @@
+"""The C++ gadget library + frontend (the product's host side) validated on CPU through the TEST-ONLY sequential
+tape interpreter (tests/hostlib): every constraint of the compiled verifier circuit is satisfied on the real
+testdata/step proof, and the ordered outputs of all 449k reference hints equal the oracle's trace."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import gpw
+from oracle.engine import Api
+from oracle.poseidon import GoldilocksChip, BN254Chip
+from oracle import goldilocks as ogl
+from oracle.verifier import verify_testdata
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HOSTLIB = os.path.join(ROOT, "tests", "hostlib")
+NAMES = ("wires public secret constraints tape levels commit_level limb_wires muladd reduce glinv split invzero bits "
+         "div decomp mul coeffs le_terms limb_start count_start commit_wire").split()
+OPS = {"muladd": 1, "reduce": 2, "inverse": 3, "split": 4}
+
+
+@pytest.fixture(scope="module")
+def lib():
+    subprocess.check_call(["make", "-C", HOSTLIB], stdout=subprocess.DEVNULL)
+    lib = C.CDLL(os.path.join(HOSTLIB, "libgpw_circuit_test.so"))
+    lib.ct_compile.restype = C.c_void_p
+    lib.ct_compile.argtypes = [C.c_char_p]
+    lib.ct_compile_small.restype = C.c_void_p
+    lib.ct_compile_small.argtypes = [C.c_int]
+    lib.ct_free.argtypes = [C.c_void_p]
+    lib.ct_last_error.restype = C.c_char_p
+    lib.ct_stats.argtypes = [C.c_void_p, C.c_void_p]
+    lib.ct_solve_inputs.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p]
+    lib.ct_solve_testdata.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p, C.c_void_p]
+    lib.ct_check.restype = C.c_uint64
+    lib.ct_check.argtypes = [C.c_void_p, C.c_void_p]
+    lib.ct_hint_outputs.restype = C.c_size_t
+    lib.ct_hint_outputs.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t]
+    return lib
+
+
+def stats(lib, h):
+    a = np.zeros(len(NAMES), dtype=np.uint64)
+    lib.ct_stats(h, a.ctypes.data)
+    return dict(zip(NAMES, map(int, a)))
+
+
+def solve(lib, h, pub, sec, x=123456789):
+    pl, sl, xl = gpw.ints_to_limbs(pub), gpw.ints_to_limbs(sec), gpw.ints_to_limbs([x])
+    rc = lib.ct_solve_inputs(h, pl.ctypes.data, len(pub), sl.ctypes.data, len(sec), xl.ctypes.data)
+    fb = C.c_int64()
+    bad = lib.ct_check(h, C.byref(fb)) if rc == 0 else None
+    return rc, bad
+
+
+def test_small_circuits_satisfied_and_reject_wrong_outputs(lib, kats):
+    # Poseidon-GL KAT (poseidon/goldilocks_test.go:37-59): 130 MulAdd + 630 Reduce + 890 SplitLimbs per permutation
+    h = lib.ct_compile_small(0)
+    st = stats(lib, h)
+    assert (st["muladd"], st["reduce"], st["split"]) == (130, 630, 890)
+    out = [int(x) for x in kats["poseidon_gl_perm_zero"]]
+    assert solve(lib, h, out, [0] * 12) == (0, 0)
+    rc, bad = solve(lib, h, [out[0] ^ 1] + out[1:], [0] * 12)
+    assert rc == 0 and bad == 1
+    lib.ct_free(h)
+    # Poseidon-BN254 KATs (poseidon/bn254_test.go:31-97)
+    h = lib.ct_compile_small(1)
+    for case in kats["poseidon_bn254"]:
+        assert solve(lib, h, [int(x) for x in case["out"]], [int(x) for x in case["in"]]) == (0, 0)
+    lib.ct_free(h)
+    # QE mul / div (goldilocks/quadratic_extension_test.go)
+    h = lib.ct_compile_small(2)
+    a = tuple(map(int, kats["qe_mul"]["a"]))
+    b = tuple(map(int, kats["qe_mul"]["b"]))
+    c = ogl.Chip(Api(trace=False))
+    m = c.MulExtension(a, b)
+    d, _ = c.DivExtension(a, b)
+    assert m == tuple(map(int, kats["qe_mul"]["out"]))
+    assert solve(lib, h, list(m) + list(d), list(a) + list(b)) == (0, 0)
+    lib.ct_free(h)
+    # RangeCheck accepts 0, 1, p-1 and the hint rejects p (goldilocks/base_test.go:26-44)
+    h = lib.ct_compile_small(3)
+    for x in (0, 1, ogl.P - 1):
+        assert solve(lib, h, [], [x]) == (0, 0)
+    rc, _ = solve(lib, h, [], [ogl.P])
+    assert rc == -5 and b"SplitLimbsHint" in lib.ct_last_error()
+    lib.ct_free(h)
+
+
+def test_full_verifier_circuit_on_step(lib, testdata_dir):
+    d = os.path.join(testdata_dir, "step")
+    rd = lambda f: open(os.path.join(d, f), "rb").read()
+    h = lib.ct_compile(rd("common_circuit_data.json"))
+    assert h, lib.ct_last_error()
+    st = stats(lib, h)
+    # same hint counts as the oracle's run of the reference dataflow
+    assert (st["muladd"], st["reduce"], st["split"], st["glinv"]) == (44186, 151410, 251232, 1849)
+    assert st["limb_wires"] == 2462493 and st["public"] == 36
+    assert 5_000_000 < st["constraints"] < 6_500_000
+    x = gpw.ints_to_limbs([0x1234567890abcdef1234567890abcdef])
+    rc = lib.ct_solve_testdata(h, rd("proof_with_public_inputs.json"), rd("verifier_only_circuit_data.json"), x.ctypes.data)
+    assert rc == 0, lib.ct_last_error()
+    fb = C.c_int64()
+    assert lib.ct_check(h, C.byref(fb)) == 0, "first unsatisfied constraint: %d" % fb.value
+    # ordered hint outputs == oracle trace
+    api, _ = verify_testdata(d)
+    for kind, op in OPS.items():
+        exp = [o for k, _, outs in api.hints if k == kind for o in outs]
+        buf = np.zeros((len(exp), 4), dtype=np.uint64)
+        n = lib.ct_hint_outputs(h, op, buf.ctypes.data, buf.size)
+        assert n == buf.size
+        assert gpw.limbs_to_ints(buf) == exp, kind
+    # a tampered proof must leave constraints unsatisfied
+    import json
+    p = json.loads(rd("proof_with_public_inputs.json"))
+    p["proof"]["openings"]["plonk_zs"][0][0] ^= 1
+    rc = lib.ct_solve_testdata(h, json.dumps(p).encode(), rd("verifier_only_circuit_data.json"), x.ctypes.data)
+    assert rc == 0 and lib.ct_check(h, C.byref(fb)) > 0
+    lib.ct_free(h)
