@@ -369,5 +369,39 @@ void API::Finalize() {
   AssertIsEqual(lhs, rhs);
 }
 
+void API::ScheduleALAP() {
+  if (tape_.empty()) return;
+  const uint32_t L = max_level_;
+  std::vector<uint32_t> producer(next_wire_, NO_LE);  // wire -> tape index
+  for (uint32_t i = 0; i < tape_.size(); i++)
+    for (uint32_t k = 0; k < tape_[i].nout; k++) producer[tape_[i].out + k] = i;
+  std::vector<uint32_t> alap(tape_.size(), L);
+  int64_t count_idx = -1, commit_idx = -1;
+  for (uint32_t i = 0; i < tape_.size(); i++) {
+    if (tape_[i].op == OP_COUNT) count_idx = i;
+    if (tape_[i].op == OP_COMMIT) commit_idx = i;
+  }
+  for (size_t ii = tape_.size(); ii-- > 0;) {
+    const Instr& in = tape_[ii];
+    if (in.op == OP_COMMIT && count_idx >= 0) alap[count_idx] = std::min(alap[count_idx], alap[ii] - 1);
+    if (in.op == OP_COUNT) continue;  // its inputs (all DECOMP outputs) are handled below
+    if (in.op == OP_DECOMP && count_idx >= 0) alap[ii] = std::min(alap[ii], alap[count_idx] - 1);
+    for (int j = 0; j < 3; j++) {
+      if (in.le[j] == NO_LE) continue;
+      for (uint32_t k = le_off_[in.le[j]]; k < le_off_[in.le[j] + 1]; k++) {
+        uint32_t p = producer[le_wire_[k]];
+        if (p != NO_LE) alap[p] = std::min(alap[p], alap[ii] - 1);
+      }
+    }
+  }
+  (void)commit_idx;
+  for (uint32_t i = 0; i < tape_.size(); i++) {
+    if (alap[i] < tape_[i].level) throw std::logic_error("ALAP level below ASAP level");
+    tape_[i].level = alap[i];
+    for (uint32_t k = 0; k < tape_[i].nout; k++) wire_level_[tape_[i].out + k] = alap[i];
+    if (tape_[i].op == OP_COMMIT) commit_level_ = alap[i];
+  }
+}
+
 }  // namespace fe
 }  // namespace gpw

@@ -106,6 +106,11 @@ class API {
   // Runs the deferred range-check construction (goldilocks/base.go:423-442 + gnark rangecheck commit):
   // limb decomposition, multiplicity histogram, commitment, log-derivative sums. Call once, at the end.
   void Finalize();
+  // Re-levels the tape "as late as possible": an instruction moves to (min level of its consumers) - 1. The
+  // long sequential spine of the verifier (challenger sponge -> FRI) keeps its levels, while the ~80 % of
+  // instructions that are leaves of the dataflow (range-check splits, IsZero inverses, selects, limb
+  // decompositions) sink to a handful of very wide final levels that the GPU runs across all SMs.
+  void ScheduleALAP();
 
   // ---- compiled circuit -----------------------------------------------------------------------------
   uint32_t NumWires() const { return next_wire_; }

@@ -1,0 +1,395 @@
+// End-to-end wrap prover for one Plonky2 proof: JSON -> witness (GPU tape) -> BSB22-style commitment of the
+// range-check limbs -> log-derivative argument -> R1CS evaluation -> Groth16 proof.
+// This is the drop-in for the reference's
+//     witness, _ := frontend.NewWitness(&assignment, ecc.BN254.ScalarField())
+//     proof, _   := groth16.Prove(r1cs, pk, witness)            (benchmark.go:240-249)
+// with the circuit from gpw_circuit_compile_verifier standing in for frontend.Compile (benchmark.go:55) and
+// gpw_wrap_key_synthetic for groth16.DummySetup (benchmark.go:214).
+#include <cstring>
+
+#include "common.cuh"
+#include "ec.cuh"
+#include "host_ec.cuh"
+#include "host/frontend.h"
+
+struct gpw_circuit;
+extern "C" {
+int gpw_circuit_info(const gpw_circuit* c, uint64_t* info16);
+int gpw_circuit_parse_inputs(const gpw_circuit* c, const char* p, const char* v, uint64_t* out, size_t cap);
+int gpw_witness_solve_phase1_dev(gpw_circuit* c, uint64_t inputs_dev, int n_proofs, uint64_t wires_dev, size_t wire_stride);
+int gpw_witness_solve_phase2_dev(gpw_circuit* c, const uint64_t* ch, int n_proofs, uint64_t wires_dev, size_t wire_stride);
+int gpw_r1cs_eval_dev(gpw_circuit* c, uint64_t wires_dev, uint64_t a_dev, uint64_t b_dev, uint64_t c_dev, uint64_t* n_unsat);
+int gpw_circuit_supports(const gpw_circuit* c, int side, uint32_t* out, size_t cap, size_t* n);
+}
+
+namespace gpw {
+
+// ---- SHA-256 + expand_message_xmd (RFC 9380) -> Fr : the commitment challenge ---------------------------------
+// gnark derives the BSB22 challenge with gnark-crypto's fr.Hash(msg, dst = "bsb22-commitment", 1): expand_message_xmd
+// over SHA-256 to 48 bytes, interpreted big-endian and reduced mod r (recalled from gnark v0.9.1 - the sources are not
+// in the reference tree).
+struct Sha256 {
+  uint32_t h[8];
+  uint8_t buf[64];
+  uint64_t len = 0;
+  size_t fill = 0;
+  Sha256() {
+    static const uint32_t iv[8] = {0x6a09e667, 0xbb67ae85, 0x3c6ef372, 0xa54ff53a, 0x510e527f, 0x9b05688c, 0x1f83d9ab, 0x5be0cd19};
+    memcpy(h, iv, sizeof(iv));
+  }
+  static uint32_t rotr(uint32_t x, int n) { return (x >> n) | (x << (32 - n)); }
+  void block(const uint8_t* p) {
+    static const uint32_t K[64] = {
+        0x428a2f98, 0x71374491, 0xb5c0fbcf, 0xe9b5dba5, 0x3956c25b, 0x59f111f1, 0x923f82a4, 0xab1c5ed5, 0xd807aa98, 0x12835b01,
+        0x243185be, 0x550c7dc3, 0x72be5d74, 0x80deb1fe, 0x9bdc06a7, 0xc19bf174, 0xe49b69c1, 0xefbe4786, 0x0fc19dc6, 0x240ca1cc,
+        0x2de92c6f, 0x4a7484aa, 0x5cb0a9dc, 0x76f988da, 0x983e5152, 0xa831c66d, 0xb00327c8, 0xbf597fc7, 0xc6e00bf3, 0xd5a79147,
+        0x06ca6351, 0x14292967, 0x27b70a85, 0x2e1b2138, 0x4d2c6dfc, 0x53380d13, 0x650a7354, 0x766a0abb, 0x81c2c92e, 0x92722c85,
+        0xa2bfe8a1, 0xa81a664b, 0xc24b8b70, 0xc76c51a3, 0xd192e819, 0xd6990624, 0xf40e3585, 0x106aa070, 0x19a4c116, 0x1e376c08,
+        0x2748774c, 0x34b0bcb5, 0x391c0cb3, 0x4ed8aa4a, 0x5b9cca4f, 0x682e6ff3, 0x748f82ee, 0x78a5636f, 0x84c87814, 0x8cc70208,
+        0x90befffa, 0xa4506ceb, 0xbef9a3f7, 0xc67178f2};
+    uint32_t w[64];
+    for (int i = 0; i < 16; i++) w[i] = (uint32_t)p[4 * i] << 24 | (uint32_t)p[4 * i + 1] << 16 | (uint32_t)p[4 * i + 2] << 8 | p[4 * i + 3];
+    for (int i = 16; i < 64; i++) {
+      uint32_t s0 = rotr(w[i - 15], 7) ^ rotr(w[i - 15], 18) ^ (w[i - 15] >> 3);
+      uint32_t s1 = rotr(w[i - 2], 17) ^ rotr(w[i - 2], 19) ^ (w[i - 2] >> 10);
+      w[i] = w[i - 16] + s0 + w[i - 7] + s1;
+    }
+    uint32_t a = h[0], b = h[1], c = h[2], d = h[3], e = h[4], f = h[5], g = h[6], hh = h[7];
+    for (int i = 0; i < 64; i++) {
+      uint32_t S1 = rotr(e, 6) ^ rotr(e, 11) ^ rotr(e, 25);
+      uint32_t ch = (e & f) ^ (~e & g);
+      uint32_t t1 = hh + S1 + ch + K[i] + w[i];
+      uint32_t S0 = rotr(a, 2) ^ rotr(a, 13) ^ rotr(a, 22);
+      uint32_t mj = (a & b) ^ (a & c) ^ (b & c);
+      uint32_t t2 = S0 + mj;
+      hh = g; g = f; f = e; e = d + t1; d = c; c = b; b = a; a = t1 + t2;
+    }
+    h[0] += a; h[1] += b; h[2] += c; h[3] += d; h[4] += e; h[5] += f; h[6] += g; h[7] += hh;
+  }
+  void update(const uint8_t* p, size_t n) {
+    len += n;
+    while (n) {
+      size_t k = std::min(n, 64 - fill);
+      memcpy(buf + fill, p, k);
+      fill += k; p += k; n -= k;
+      if (fill == 64) { block(buf); fill = 0; }
+    }
+  }
+  void final(uint8_t out[32]) {
+    uint64_t bits = len * 8;
+    uint8_t pad = 0x80;
+    update(&pad, 1);
+    uint8_t z = 0;
+    while (fill != 56) update(&z, 1);
+    uint8_t lb[8];
+    for (int i = 0; i < 8; i++) lb[i] = (uint8_t)(bits >> (56 - 8 * i));
+    update(lb, 8);
+    for (int i = 0; i < 8; i++) { out[4 * i] = h[i] >> 24; out[4 * i + 1] = h[i] >> 16; out[4 * i + 2] = h[i] >> 8; out[4 * i + 3] = h[i]; }
+  }
+};
+
+static void sha256(const std::vector<uint8_t>& m, uint8_t out[32]) {
+  Sha256 s;
+  s.update(m.data(), m.size());
+  s.final(out);
+}
+
+// expand_message_xmd(msg, dst, 48) then big-endian mod r -> canonical limbs
+void hash_to_fr(const uint8_t* msg, size_t msg_len, const char* dst, uint64_t out_canonical[4]) {
+  const size_t L = 48, dst_len = strlen(dst);
+  std::vector<uint8_t> dst_prime(dst, dst + dst_len);
+  dst_prime.push_back((uint8_t)dst_len);
+  std::vector<uint8_t> m(64, 0);  // Z_pad
+  m.insert(m.end(), msg, msg + msg_len);
+  m.push_back(0);
+  m.push_back((uint8_t)L);
+  m.push_back(0);
+  m.insert(m.end(), dst_prime.begin(), dst_prime.end());
+  uint8_t b0[32], b1[32], b2[32];
+  sha256(m, b0);
+  std::vector<uint8_t> t(b0, b0 + 32);
+  t.push_back(1);
+  t.insert(t.end(), dst_prime.begin(), dst_prime.end());
+  sha256(t, b1);
+  std::vector<uint8_t> t2(32);
+  for (int i = 0; i < 32; i++) t2[i] = b0[i] ^ b1[i];
+  t2.push_back(2);
+  t2.insert(t2.end(), dst_prime.begin(), dst_prime.end());
+  sha256(t2, b2);
+  uint8_t u[48];
+  memcpy(u, b1, 32);
+  memcpy(u + 32, b2, 16);
+  // big-endian 384-bit integer mod r, via Horner in Fr (Montgomery arithmetic)
+  Fr acc = Fr::zero();
+  const Fr c256 = fe::fr_from_u64(256);
+  for (size_t i = 0; i < L; i++) acc = add(mul(acc, c256), fe::fr_from_u64(u[i]));
+  fe::fr_to_limbs(acc, out_canonical);
+}
+
+__global__ void k_gather_fr(const Fr* __restrict__ w, const uint32_t* __restrict__ idx, size_t n, Fr* __restrict__ out) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint4* s = reinterpret_cast<const uint4*>(w + idx[i]);
+  uint4* d = reinterpret_cast<uint4*>(out + i);
+  d[0] = s[0];
+  d[1] = s[1];
+}
+
+}  // namespace gpw
+
+using namespace gpw;
+
+extern "C" {
+int gpw_ec_generator_multiples_dev(gpw_ctx* ctx, int group, uint64_t k0, size_t n, uint64_t out_dev);
+int gpw_msm_g1_dev(gpw_ctx* ctx, uint64_t s, uint64_t p, size_t n, int mont, int c, int lo, int hi, uint64_t* out);
+int gpw_msm_g2_dev(gpw_ctx* ctx, uint64_t s, uint64_t p, size_t n, int mont, int c, int lo, int hi, uint64_t* out);
+int gpw_groth16_compute_h_dev(gpw_ctx* ctx, uint64_t a_dev, uint64_t b_dev, uint64_t c_dev, int logN);
+}
+
+// Proving key for a compiled circuit. Bases are synthetic (known discrete logs, documented below) - the analogue of
+// groth16.DummySetup - but have exactly the shapes a real key has for THIS circuit: A / B bases only for wires that
+// occur in some L / R row (gnark's pk.InfinityA / InfinityB filtering), K bases for private non-committed wires, a
+// Pedersen commitment basis (+ its sigma-twin for the proof of knowledge) for the committed wires, Z for h.
+struct gpw_wrap_key {
+  gpw_ctx* ctx = nullptr;
+  gpw_circuit* circ = nullptr;
+  uint32_t m = 0, n_pub = 0, n_cons = 0;
+  int logN = 0;
+  uint32_t limb_start = 0, n_committed = 0, commit_wire = 0;
+  uint32_t nA = 0, nB = 0;
+  uint32_t *suppA = nullptr, *suppB = nullptr;  // device wire-id lists
+  G1Affine *A = nullptr, *B1 = nullptr, *K = nullptr, *Z = nullptr, *CK = nullptr, *CKs = nullptr;
+  G2Affine* B2 = nullptr;
+  G1Affine alpha1, beta1, delta1;
+  G2Affine beta2, delta2;
+  Fr *wires = nullptr, *va = nullptr, *vb = nullptr, *vc = nullptr, *gathA = nullptr, *gathB = nullptr;
+  uint64_t* inputs_dev = nullptr;
+  uint32_t n_inputs = 0;
+  uint64_t seed = 0;
+  float t_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+};
+
+static int wk_alloc(void** p, size_t bytes) {
+  cudaError_t e = cudaMalloc(p, bytes ? bytes : 16);
+  if (e != cudaSuccess) {
+    set_error("cudaMalloc(%zu) failed: %s", bytes, cudaGetErrorString(e));
+    return GPW_ENOMEM;
+  }
+  return GPW_OK;
+}
+
+extern "C" void gpw_wrap_key_free(gpw_wrap_key* k) {
+  if (!k) return;
+  cudaSetDevice(k->ctx->device);
+  void* ps[] = {k->suppA, k->suppB, k->A, k->B1, k->K, k->Z, k->CK, k->CKs, k->B2, k->wires, k->va, k->vb, k->vc, k->gathA, k->gathB,
+                k->inputs_dev};
+  for (void* p : ps) cudaFree(p);
+  delete k;
+}
+
+template <class F>
+static Affine<F> gen_mul_host(uint64_t k) {
+  uint32_t kw[8] = {(uint32_t)k, (uint32_t)(k >> 32), 0, 0, 0, 0, 0, 0};
+  return to_affine(host_scalar_mul(generator<F>(), kw));
+}
+
+// Discrete logs (all bases are [k]G): A_j = [1 + j], B1_j = [2^32 + j], B2_j = [1 + j] (G2), K_i = [2^33 + i],
+// Z_j = [2^34 + j], CK_i = [2^35 + i], CKs_i = [2^36 + i]; alpha = [seed+1], beta = [seed+2], delta = [seed+3].
+// (j indexes the compacted A / B support lists, i is the wire id.)
+extern "C" int gpw_wrap_key_synthetic(gpw_ctx* ctx, gpw_circuit* circ, uint64_t seed, gpw_wrap_key** out) {
+  if (!ctx || !circ || !out) {
+    set_error("wrap_key: null argument");
+    return GPW_EINVAL;
+  }
+  GPW_CUDA(cudaSetDevice(ctx->device));
+  uint64_t info[16];
+  GPW_TRY(gpw_circuit_info(circ, info));
+  gpw_wrap_key* k = new gpw_wrap_key();
+  k->ctx = ctx;
+  k->circ = circ;
+  k->seed = seed;
+  k->m = (uint32_t)info[0];
+  k->n_pub = (uint32_t)info[1];
+  k->n_inputs = (uint32_t)(info[1] + info[2]);
+  k->n_cons = (uint32_t)info[3];
+  k->limb_start = (uint32_t)info[7];
+  k->n_committed = info[6] ? (uint32_t)(info[6] + 65536) : 0;
+  k->commit_wire = (uint32_t)info[9];
+  k->logN = 1;
+  while ((1ull << k->logN) < k->n_cons) k->logN++;
+  const size_t N = (size_t)1 << k->logN;
+  std::vector<uint32_t> sa(k->m), sb(k->m);
+  size_t na = 0, nb = 0;
+  GPW_TRY(gpw_circuit_supports(circ, 0, sa.data(), sa.size(), &na));
+  GPW_TRY(gpw_circuit_supports(circ, 1, sb.data(), sb.size(), &nb));
+  k->nA = (uint32_t)na;
+  k->nB = (uint32_t)nb;
+  int rc = 0;
+  if ((rc = wk_alloc((void**)&k->suppA, na * 4)) || (rc = wk_alloc((void**)&k->suppB, nb * 4)) ||
+      (rc = wk_alloc((void**)&k->A, na * sizeof(G1Affine))) || (rc = wk_alloc((void**)&k->B1, nb * sizeof(G1Affine))) ||
+      (rc = wk_alloc((void**)&k->B2, nb * sizeof(G2Affine))) || (rc = wk_alloc((void**)&k->K, (size_t)k->m * sizeof(G1Affine))) ||
+      (rc = wk_alloc((void**)&k->Z, N * sizeof(G1Affine))) || (rc = wk_alloc((void**)&k->CK, (size_t)k->n_committed * sizeof(G1Affine))) ||
+      (rc = wk_alloc((void**)&k->CKs, (size_t)k->n_committed * sizeof(G1Affine))) || (rc = wk_alloc((void**)&k->wires, (size_t)k->m * sizeof(Fr))) ||
+      (rc = wk_alloc((void**)&k->va, N * sizeof(Fr))) || (rc = wk_alloc((void**)&k->vb, N * sizeof(Fr))) ||
+      (rc = wk_alloc((void**)&k->vc, N * sizeof(Fr))) || (rc = wk_alloc((void**)&k->gathA, na * sizeof(Fr))) ||
+      (rc = wk_alloc((void**)&k->gathB, nb * sizeof(Fr))) || (rc = wk_alloc((void**)&k->inputs_dev, (size_t)k->n_inputs * 32))) {
+    gpw_wrap_key_free(k);
+    return rc;
+  }
+  GPW_CUDA(cudaMemcpy(k->suppA, sa.data(), na * 4, cudaMemcpyHostToDevice));
+  GPW_CUDA(cudaMemcpy(k->suppB, sb.data(), nb * 4, cudaMemcpyHostToDevice));
+  GPW_TRY(gpw_ec_generator_multiples_dev(ctx, 1, 1, na, (uint64_t)k->A));
+  GPW_TRY(gpw_ec_generator_multiples_dev(ctx, 1, 1ull << 32, nb, (uint64_t)k->B1));
+  GPW_TRY(gpw_ec_generator_multiples_dev(ctx, 2, 1, nb, (uint64_t)k->B2));
+  GPW_TRY(gpw_ec_generator_multiples_dev(ctx, 1, 1ull << 33, k->m, (uint64_t)k->K));
+  GPW_TRY(gpw_ec_generator_multiples_dev(ctx, 1, 1ull << 34, N - 1, (uint64_t)k->Z));
+  GPW_TRY(gpw_ec_generator_multiples_dev(ctx, 1, (1ull << 35) + k->limb_start, k->n_committed, (uint64_t)k->CK));
+  GPW_TRY(gpw_ec_generator_multiples_dev(ctx, 1, (1ull << 36) + k->limb_start, k->n_committed, (uint64_t)k->CKs));
+  k->alpha1 = gen_mul_host<Fp>(seed + 1);
+  k->beta1 = gen_mul_host<Fp>(seed + 2);
+  k->delta1 = gen_mul_host<Fp>(seed + 3);
+  k->beta2 = gen_mul_host<Fp2>(seed + 2);
+  k->delta2 = gen_mul_host<Fp2>(seed + 3);
+  GPW_CUDA(cudaStreamSynchronize(ctx->stream));
+  *out = k;
+  return GPW_OK;
+}
+
+// info: [m, n_pub, n_cons, logN, nA, nB, n_committed, limb_start]
+extern "C" int gpw_wrap_key_info(const gpw_wrap_key* k, uint64_t* info8) {
+  if (!k || !info8) return GPW_EINVAL;
+  uint64_t v[8] = {k->m, k->n_pub, k->n_cons, (uint64_t)k->logN, k->nA, k->nB, k->n_committed, k->limb_start};
+  memcpy(info8, v, sizeof(v));
+  return GPW_OK;
+}
+
+extern "C" uint64_t gpw_wrap_key_wires_dev(const gpw_wrap_key* k) { return k ? (uint64_t)k->wires : 0; }
+
+static void ser_g1_be(const G1Affine& p, uint8_t out[64]) {
+  Fp x = from_mont(p.x), y = from_mont(p.y);
+  for (int i = 0; i < 8; i++)
+    for (int b = 0; b < 4; b++) {
+      out[31 - (4 * i + b)] = (uint8_t)(x.l[i] >> (8 * b));
+      out[63 - (4 * i + b)] = (uint8_t)(y.l[i] >> (8 * b));
+    }
+}
+
+// One wrap proof. inputs: n_inputs x 4 u64 canonical on the HOST (gpw_circuit_parse_inputs order). r, s canonical.
+// out_proof (u64 x 64): Ar (8) | Bs (16) | Krs (8) | commitment D (8) | commitment PoK (8) | challenge (4, canonical) |
+//                       n_unsatisfied (1) | reserved.  If check != 0 the R1CS is verified on the device (a*b == c on every
+// row) and GPW_EUNSAT is returned on failure.
+extern "C" int gpw_wrap_prove(gpw_wrap_key* k, const uint64_t* inputs, const uint64_t* r_canon, const uint64_t* s_canon, int check,
+                              uint64_t* out_proof) {
+  if (!k || !inputs || !r_canon || !s_canon || !out_proof) {
+    set_error("wrap_prove: null argument");
+    return GPW_EINVAL;
+  }
+  gpw_ctx* ctx = k->ctx;
+  GPW_CUDA(cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  const size_t N = (size_t)1 << k->logN;
+  cudaEvent_t ev[7];
+  for (auto& e : ev) GPW_CUDA(cudaEventCreate(&e));
+  memset(out_proof, 0, 64 * 8);
+  GPW_CUDA(cudaEventRecord(ev[0], st));
+  GPW_CUDA(cudaMemcpyAsync(k->inputs_dev, inputs, (size_t)k->n_inputs * 32, cudaMemcpyHostToDevice, st));
+  GPW_TRY(gpw_witness_solve_phase1_dev(k->circ, (uint64_t)k->inputs_dev, 1, (uint64_t)k->wires, k->m));
+  GPW_CUDA(cudaEventRecord(ev[1], st));
+  // commitment to the committed wires (range-check limbs + multiplicities) and its proof of knowledge
+  G1Affine D{Fp::zero(), Fp::zero()}, PoK{Fp::zero(), Fp::zero()};
+  uint64_t X[4] = {0, 0, 0, 0};
+  if (k->n_committed) {
+    uint64_t sc = (uint64_t)(k->wires + k->limb_start);
+    GPW_TRY(gpw_msm_g1_dev(ctx, sc, (uint64_t)k->CK, k->n_committed, 1, 0, 0, 0, (uint64_t*)&D));
+    GPW_TRY(gpw_msm_g1_dev(ctx, sc, (uint64_t)k->CKs, k->n_committed, 1, 0, 0, 0, (uint64_t*)&PoK));
+    uint8_t ser[64];
+    ser_g1_be(D, ser);
+    hash_to_fr(ser, 64, "bsb22-commitment", X);
+  }
+  GPW_CUDA(cudaEventRecord(ev[2], st));
+  GPW_TRY(gpw_witness_solve_phase2_dev(k->circ, X, 1, (uint64_t)k->wires, k->m));
+  GPW_CUDA(cudaEventRecord(ev[3], st));
+  // R1CS evaluation vectors, zero padded to the FFT domain
+  GPW_CUDA(cudaMemsetAsync(k->va, 0, N * sizeof(Fr), st));
+  GPW_CUDA(cudaMemsetAsync(k->vb, 0, N * sizeof(Fr), st));
+  GPW_CUDA(cudaMemsetAsync(k->vc, 0, N * sizeof(Fr), st));
+  uint64_t n_bad = 0;
+  int rc = gpw_r1cs_eval_dev(k->circ, (uint64_t)k->wires, (uint64_t)k->va, (uint64_t)k->vb, (uint64_t)k->vc, &n_bad);
+  if (rc != GPW_OK && (check || rc != GPW_EUNSAT)) return rc;
+  GPW_CUDA(cudaEventRecord(ev[4], st));
+  GPW_TRY(gpw_groth16_compute_h_dev(ctx, (uint64_t)k->va, (uint64_t)k->vb, (uint64_t)k->vc, k->logN));
+  GPW_CUDA(cudaEventRecord(ev[5], st));
+  // gather the scalars of the A / B supports
+  k_gather_fr<<<div_up(k->nA, 256), 256, 0, st>>>(k->wires, k->suppA, k->nA, k->gathA);
+  GPW_CHECK_LAUNCH();
+  k_gather_fr<<<div_up(k->nB, 256), 256, 0, st>>>(k->wires, k->suppB, k->nB, k->gathB);
+  GPW_CHECK_LAUNCH();
+  ctx->launches += 2;
+  G1Affine mA, mB1, mK1, mK2, mZ;
+  G2Affine mB2;
+  GPW_TRY(gpw_msm_g1_dev(ctx, (uint64_t)k->gathA, (uint64_t)k->A, k->nA, 1, 0, 0, 0, (uint64_t*)&mA));
+  GPW_TRY(gpw_msm_g1_dev(ctx, (uint64_t)k->gathB, (uint64_t)k->B1, k->nB, 1, 0, 0, 0, (uint64_t*)&mB1));
+  GPW_TRY(gpw_msm_g2_dev(ctx, (uint64_t)k->gathB, (uint64_t)k->B2, k->nB, 1, 0, 0, 0, (uint64_t*)&mB2));
+  // K: private wires that are not committed = [1 + n_pub, limb_start) U [limb_start + n_committed, m), minus the challenge wire
+  const uint32_t k_lo = 1 + k->n_pub;
+  const uint32_t c_lo = k->n_committed ? k->limb_start : k->m, c_hi = c_lo + k->n_committed;
+  GPW_TRY(gpw_msm_g1_dev(ctx, (uint64_t)(k->wires + k_lo), (uint64_t)(k->K + k_lo), c_lo - k_lo, 1, 0, 0, 0, (uint64_t*)&mK1));
+  mK2 = G1Affine{Fp::zero(), Fp::zero()};
+  if (c_hi < k->m)
+    GPW_TRY(gpw_msm_g1_dev(ctx, (uint64_t)(k->wires + c_hi), (uint64_t)(k->K + c_hi), k->m - c_hi, 1, 0, 0, 0, (uint64_t*)&mK2));
+  GPW_TRY(gpw_msm_g1_dev(ctx, (uint64_t)k->va, (uint64_t)k->Z, N - 1, 1, 0, 0, 0, (uint64_t*)&mZ));
+  GPW_CUDA(cudaEventRecord(ev[6], st));
+  GPW_CUDA(cudaStreamSynchronize(st));
+  for (int i = 0; i < 6; i++) GPW_CUDA(cudaEventElapsedTime(&k->t_ms[i], ev[i], ev[i + 1]));
+  for (auto& e : ev) cudaEventDestroy(e);
+  // assembly (gnark groth16.Prove)
+  uint32_t rw[8], sw[8];
+  memcpy(rw, r_canon, 32);
+  memcpy(sw, s_canon, 32);
+  G1XYZZ Ar = G1XYZZ::from_affine(k->alpha1);
+  add_mixed(Ar, mA, false);
+  add_full(Ar, host_scalar_mul(k->delta1, rw));
+  G1XYZZ Bs1 = G1XYZZ::from_affine(k->beta1);
+  add_mixed(Bs1, mB1, false);
+  add_full(Bs1, host_scalar_mul(k->delta1, sw));
+  G2XYZZ Bs = G2XYZZ::from_affine(k->beta2);
+  add_mixed(Bs, mB2, false);
+  add_full(Bs, host_scalar_mul(k->delta2, sw));
+  G1Affine ArA = to_affine(Ar), Bs1A = to_affine(Bs1);
+  G1XYZZ Krs = G1XYZZ::from_affine(mK1);
+  add_mixed(Krs, mK2, false);
+  add_mixed(Krs, mZ, false);
+  add_full(Krs, host_scalar_mul(ArA, sw));
+  add_full(Krs, host_scalar_mul(Bs1A, rw));
+  Fr rf, sf;
+  memcpy(&rf, r_canon, 32);
+  memcpy(&sf, s_canon, 32);
+  Fr rs = from_mont(mul(to_mont(rf), to_mont(sf)));
+  uint32_t rsw[8];
+  memcpy(rsw, &rs, 32);
+  add_full(Krs, neg(host_scalar_mul(k->delta1, rsw)));
+  G1Affine KrsA = to_affine(Krs);
+  G2Affine BsA = to_affine(Bs);
+  memcpy(out_proof, &ArA, 64);
+  memcpy(out_proof + 8, &BsA, 128);
+  memcpy(out_proof + 24, &KrsA, 64);
+  memcpy(out_proof + 32, &D, 64);
+  memcpy(out_proof + 40, &PoK, 64);
+  // note: slots 40..47 hold the PoK; the challenge and the unsatisfied count follow
+  memcpy(out_proof + 48, X, 32);
+  out_proof[52] = n_bad;
+  return GPW_OK;
+}
+
+// ms: [inputs + solve phase 1, commitment MSMs + hash, solve phase 2, R1CS evaluation, computeH, gathers + MSMs]
+extern "C" int gpw_wrap_last_stats(const gpw_wrap_key* k, float* ms6) {
+  if (!k || !ms6) return GPW_EINVAL;
+  for (int i = 0; i < 6; i++) ms6[i] = k->t_ms[i];
+  return GPW_OK;
+}
+
+extern "C" int gpw_hash_to_fr(const uint8_t* msg, size_t len, const char* dst, uint64_t* out_canonical) {
+  if (!msg || !dst || !out_canonical) return GPW_EINVAL;
+  hash_to_fr(msg, len, dst, out_canonical);
+  return GPW_OK;
+}

@@ -383,3 +383,6 @@ class ProvingKey:
         ms = (C.c_float * 5)()
         _check(_lib.gpw_groth16_last_stats(self._h, C.byref(h), ms))
         return {"compute_h_ms": h.value, "msm_ms": dict(zip(("A", "B1", "B2", "K", "Z"), [float(x) for x in ms]))}
+
+
+from .wrap import Circuit, WrapKey, hash_to_fr  # noqa: E402,F401  (binds the circuit / wrap part of include/gpw.h)

@@ -1,0 +1,157 @@
+"""Host-side mirror of the reference's top-level flow (benchmark.go:27-78, 192-304) over the C ABI:
+
+    circuit = Circuit.compile_verifier(ctx, common_circuit_data_json)      # frontend.Compile          (:55)
+    key     = WrapKey(ctx, circuit, seed)                                   # groth16.DummySetup        (:214)
+    inputs  = circuit.parse_inputs(proof_json, verifier_only_json)          # variables.Deserialize*    (:30-31)
+    proof   = key.prove(inputs, r, s)                                       # NewWitness + groth16.Prove (:240-249)
+
+Plumbing only - all computation happens in libgpw.so on the GPU.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib, _check, _p, _vp, ints_to_limbs, SYMBOLS
+
+_NEW = {
+    "gpw_circuit_compile_verifier": (C.c_int, [_vp, C.c_char_p, C.POINTER(_vp)]),
+    "gpw_circuit_compile_gadget": (C.c_int, [_vp, C.c_char_p, C.POINTER(_vp)]),
+    "gpw_circuit_free": (None, [_vp]),
+    "gpw_circuit_info": (C.c_int, [_vp, _vp]),
+    "gpw_circuit_parse_inputs": (C.c_int, [_vp, C.c_char_p, C.c_char_p, _vp, C.c_size_t]),
+    "gpw_witness_solve_phase1_dev": (C.c_int, [_vp, C.c_uint64, C.c_int, C.c_uint64, C.c_size_t]),
+    "gpw_witness_solve_phase2_dev": (C.c_int, [_vp, _vp, C.c_int, C.c_uint64, C.c_size_t]),
+    "gpw_r1cs_eval_dev": (C.c_int, [_vp, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64, C.POINTER(C.c_uint64)]),
+    "gpw_circuit_supports": (C.c_int, [_vp, C.c_int, _vp, C.c_size_t, C.POINTER(C.c_size_t)]),
+    "gpw_circuit_hint_wires": (C.c_int, [_vp, C.c_int, _vp, C.c_size_t, C.POINTER(C.c_size_t)]),
+    "gpw_wrap_key_synthetic": (C.c_int, [_vp, _vp, C.c_uint64, C.POINTER(_vp)]),
+    "gpw_wrap_key_free": (None, [_vp]),
+    "gpw_wrap_key_info": (C.c_int, [_vp, _vp]),
+    "gpw_wrap_key_wires_dev": (C.c_uint64, [_vp]),
+    "gpw_wrap_prove": (C.c_int, [_vp, _vp, _vp, _vp, C.c_int, _vp]),
+    "gpw_wrap_last_stats": (C.c_int, [_vp, _vp]),
+    "gpw_hash_to_fr": (C.c_int, [C.c_char_p, C.c_size_t, C.c_char_p, _vp]),
+}
+for _name, (_res, _args) in _NEW.items():
+    _fn = getattr(_lib, _name)
+    _fn.restype = _res
+    _fn.argtypes = _args
+SYMBOLS.update(_NEW)
+
+INFO_NAMES = ("wires public secret constraints instructions levels limb_wires limb_start count_start commit_wire "
+              "narrow_segments wide_segments muladd reduce inverse split").split()
+OP_MULADD, OP_REDUCE, OP_INVERSE, OP_SPLIT = 1, 2, 3, 4
+
+
+def hash_to_fr(msg: bytes, dst: bytes = b"bsb22-commitment"):
+    out = np.zeros(4, dtype=np.uint64)
+    _check(_lib.gpw_hash_to_fr(msg, len(msg), dst, _p(out)))
+    return sum(int(out[i]) << (64 * i) for i in range(4))
+
+
+class Circuit:
+    def __init__(self, ctx, handle):
+        self.ctx, self._h = ctx, handle
+        a = np.zeros(16, dtype=np.uint64)
+        _check(_lib.gpw_circuit_info(self._h, _p(a)))
+        self.info = dict(zip(INFO_NAMES, map(int, a)))
+        self.n_inputs = self.info["public"] + self.info["secret"]
+        self.n_wires = self.info["wires"]
+
+    @classmethod
+    def compile_verifier(cls, ctx, common_circuit_data_json):
+        if isinstance(common_circuit_data_json, str):
+            common_circuit_data_json = common_circuit_data_json.encode()
+        h = _vp()
+        _check(_lib.gpw_circuit_compile_verifier(ctx._h, common_circuit_data_json, C.byref(h)))
+        return cls(ctx, h)
+
+    @classmethod
+    def compile_gadget(cls, ctx, name):
+        h = _vp()
+        _check(_lib.gpw_circuit_compile_gadget(ctx._h, name.encode(), C.byref(h)))
+        return cls(ctx, h)
+
+    def close(self):
+        if self._h:
+            _lib.gpw_circuit_free(self._h)
+            self._h = None
+
+    def parse_inputs(self, proof_json, verifier_only_json):
+        if isinstance(proof_json, str):
+            proof_json = proof_json.encode()
+        if isinstance(verifier_only_json, str):
+            verifier_only_json = verifier_only_json.encode()
+        out = np.zeros((self.n_inputs, 4), dtype=np.uint64)
+        _check(_lib.gpw_circuit_parse_inputs(self._h, proof_json, verifier_only_json, _p(out), out.size))
+        return out
+
+    def inputs_from_ints(self, public, secret):
+        assert len(public) == self.info["public"] and len(secret) == self.info["secret"]
+        return ints_to_limbs(list(public) + list(secret))
+
+    def solve_phase1_dev(self, inputs_ptr, n_proofs, wires_ptr, wire_stride):
+        _check(_lib.gpw_witness_solve_phase1_dev(self._h, inputs_ptr, n_proofs, wires_ptr, wire_stride))
+
+    def solve_phase2_dev(self, challenges, n_proofs, wires_ptr, wire_stride):
+        ch = ints_to_limbs(list(challenges)) if challenges is not None else None
+        _check(_lib.gpw_witness_solve_phase2_dev(self._h, _p(ch), n_proofs, wires_ptr, wire_stride))
+
+    def r1cs_eval_dev(self, wires_ptr, a_ptr=0, b_ptr=0, c_ptr=0):
+        """-> number of unsatisfied constraints (raises GpwError(-6) if any)"""
+        n = C.c_uint64()
+        _check(_lib.gpw_r1cs_eval_dev(self._h, wires_ptr, a_ptr, b_ptr, c_ptr, C.byref(n)))
+        return n.value
+
+    def hint_wires(self, op):
+        n = C.c_size_t()
+        _check(_lib.gpw_circuit_hint_wires(self._h, op, None, 0, C.byref(n)))
+        out = np.zeros(n.value, dtype=np.uint32)
+        _check(_lib.gpw_circuit_hint_wires(self._h, op, _p(out), out.size, C.byref(n)))
+        return out
+
+    def supports(self, side):
+        out = np.zeros(self.n_wires, dtype=np.uint32)
+        n = C.c_size_t()
+        _check(_lib.gpw_circuit_supports(self._h, side, _p(out), out.size, C.byref(n)))
+        return out[:n.value].copy()
+
+
+class WrapKey:
+    KEY_INFO = "m n_pub n_cons logN nA nB n_committed limb_start".split()
+
+    def __init__(self, ctx, circuit, seed=0x5EED):
+        h = _vp()
+        _check(_lib.gpw_wrap_key_synthetic(ctx._h, circuit._h, seed, C.byref(h)))
+        self._h, self.ctx, self.circuit, self.seed = h, ctx, circuit, seed
+        a = np.zeros(8, dtype=np.uint64)
+        _check(_lib.gpw_wrap_key_info(self._h, _p(a)))
+        self.info = dict(zip(self.KEY_INFO, map(int, a)))
+
+    def close(self):
+        if self._h:
+            _lib.gpw_wrap_key_free(self._h)
+            self._h = None
+
+    @property
+    def wires_ptr(self):
+        return int(_lib.gpw_wrap_key_wires_dev(self._h))
+
+    def prove(self, inputs, r_int, s_int, check=True):
+        """inputs: (n_inputs, 4) u64 canonical, host. -> dict with Ar, Bs, Krs, commitment, pok (affine Montgomery limbs),
+        challenge (int), n_unsatisfied"""
+        inputs = np.ascontiguousarray(inputs, dtype=np.uint64)
+        assert inputs.shape == (self.circuit.n_inputs, 4)
+        r = ints_to_limbs([r_int])[0]
+        s = ints_to_limbs([s_int])[0]
+        out = np.zeros(64, dtype=np.uint64)
+        _check(_lib.gpw_wrap_prove(self._h, _p(inputs), _p(r), _p(s), int(check), _p(out)))
+        return {"Ar": out[0:8].copy(), "Bs": out[8:24].copy(), "Krs": out[24:32].copy(), "commitment": out[32:40].copy(),
+                "pok": out[40:48].copy(), "challenge": sum(int(out[48 + i]) << (64 * i) for i in range(4)),
+                "n_unsatisfied": int(out[52]), "raw": out}
+
+    def last_stats(self):
+        ms = (C.c_float * 6)()
+        _check(_lib.gpw_wrap_last_stats(self._h, ms))
+        names = ("solve_phase1_ms", "commitment_ms", "solve_phase2_ms", "r1cs_eval_ms", "compute_h_ms", "msm_ms")
+        return dict(zip(names, [float(x) for x in ms]))

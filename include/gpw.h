@@ -123,6 +123,51 @@ int gpw_groth16_prove_dev(gpw_pk* pk, uint64_t w_dev, uint64_t a_dev, uint64_t b
 /* ms spent in computeH and in each of the MSMs {A, B1, B2, K, Z} of the last prove (CUDA events).        */
 int gpw_groth16_last_stats(const gpw_pk* pk, float* h_ms, float* msm_ms5);
 
+/* ---- Circuit compile + witness synthesis (K1-K7 as one levelled tape) ---------------------------------------
+ * gpw_circuit = the compiled verifier circuit (R1CS + solver tape on the device). Replaces
+ * frontend.Compile(ecc.BN254.ScalarField(), r1cs.NewBuilder, &circuit) at benchmark.go:55 for
+ * verifier.ExampleVerifierCircuit (verifier/util.go:10-24); the proof and the verifier-only data are runtime
+ * (secret) inputs as in the reference's own test circuits (fri/fri_test.go:17-21), PublicInputs are public.  */
+typedef struct gpw_circuit gpw_circuit;
+int gpw_circuit_compile_verifier(gpw_ctx* ctx, const char* common_circuit_data_json, gpw_circuit** out);
+/* Stand-alone gadget circuits shaped like the reference's unit-test circuits: "poseidon_gl", "poseidon_bn254",
+ * "qe_mul_div", "range_check" (poseidon/goldilocks_test.go, poseidon/bn254_test.go, goldilocks/*_test.go).       */
+int gpw_circuit_compile_gadget(gpw_ctx* ctx, const char* name, gpw_circuit** out);
+void gpw_circuit_free(gpw_circuit* c);
+/* info16: wires, public, secret, constraints, instructions, levels, limb_wires, limb_start, count_start, commit_wire,
+ * narrow segments, wide segments, #MulAddHint, #ReduceHint, #InverseHint, #SplitLimbsHint                          */
+int gpw_circuit_info(const gpw_circuit* c, uint64_t* info16);
+/* types.ReadProofWithPublicInputs + variables.Deserialize* (types/deserialize.go:92, variables/deserialize.go:114-156):
+ * the two JSON documents -> flat canonical input vector (public then secret, 4 u64 each).                          */
+int gpw_circuit_parse_inputs(const gpw_circuit* c, const char* proof_with_public_inputs_json,
+                             const char* verifier_only_circuit_data_json, uint64_t* out, size_t out_cap_u64);
+/* The solve of groth16.Prove (benchmark.go:249): phase 1 = everything before the range-check commitment challenge,
+ * phase 2 = the log-derivative argument after it. inputs_dev: n_proofs x n_inputs x 4 u64 canonical; wires_dev:
+ * n_proofs x wire_stride Fr (Montgomery). challenges: one canonical Fr per proof (NULL if the circuit has none). */
+int gpw_witness_solve_phase1_dev(gpw_circuit* c, uint64_t inputs_dev, int n_proofs, uint64_t wires_dev, size_t wire_stride);
+int gpw_witness_solve_phase2_dev(gpw_circuit* c, const uint64_t* challenges_canonical, int n_proofs, uint64_t wires_dev,
+                                 size_t wire_stride);
+/* a = L.w, b = R.w, c = O.w (device, >= n_constraints Fr each; pass 0 to only check). GPW_EUNSAT if a*b != c somewhere. */
+int gpw_r1cs_eval_dev(gpw_circuit* c, uint64_t wires_dev, uint64_t a_dev, uint64_t b_dev, uint64_t c_dev, uint64_t* n_unsatisfied);
+int gpw_circuit_supports(const gpw_circuit* c, int side, uint32_t* out, size_t cap, size_t* n);
+/* output wires of every tape instruction of one opcode (1 MulAddHint, 2 ReduceHint, 3 InverseHint, 4 SplitLimbsHint),
+ * in the order the reference's gadget code requests them.                                                       */
+int gpw_circuit_hint_wires(const gpw_circuit* c, int op, uint32_t* out, size_t cap, size_t* n);
+
+/* ---- the whole wrap: JSON inputs -> Groth16 proof (benchmark.go:240-249 on the GPU) --------------------------------
+ * gpw_wrap_key_synthetic = groth16.DummySetup(r1cs) (benchmark.go:214) for a compiled circuit, with known discrete
+ * logs (csrc/wrap.cu). gpw_wrap_prove: inputs on the HOST; out_proof (64 u64): Ar (8) | Bs (16) | Krs (8) |
+ * commitment (8) | commitment PoK (8) | challenge (4, canonical) | n_unsatisfied (1).                             */
+typedef struct gpw_wrap_key gpw_wrap_key;
+int gpw_wrap_key_synthetic(gpw_ctx* ctx, gpw_circuit* circ, uint64_t seed, gpw_wrap_key** out);
+void gpw_wrap_key_free(gpw_wrap_key* k);
+int gpw_wrap_key_info(const gpw_wrap_key* k, uint64_t* info8);
+uint64_t gpw_wrap_key_wires_dev(const gpw_wrap_key* k);
+int gpw_wrap_prove(gpw_wrap_key* k, const uint64_t* inputs, const uint64_t* r_canonical, const uint64_t* s_canonical, int check,
+                   uint64_t* out_proof);
+int gpw_wrap_last_stats(const gpw_wrap_key* k, float* ms6);
+int gpw_hash_to_fr(const uint8_t* msg, size_t len, const char* dst, uint64_t* out_canonical);
+
 /* ---- K3: Poseidon over BN254 Fr (t = 4) ---------------------------------------------------------
  * Replaces poseidon.BN254Chip.Poseidon (poseidon/bn254.go:39-45). states: n x 4 Fr in / out.   */
 int gpw_poseidon_bn254(gpw_ctx* ctx, const uint64_t* states_in, uint64_t* states_out, size_t n, int mont);

@@ -111,6 +111,8 @@ void* ct_compile_small(int kind) {
   }
 }
 
+void ct_schedule_alap(void* h) { ((Circuit*)h)->api.ScheduleALAP(); }
+
 void ct_free(void* h) { delete (Circuit*)h; }
 
 // stats: [wires, public, secret, constraints, tape, levels, commit_level, limb_wires, muladd, reduce, glinv, split,

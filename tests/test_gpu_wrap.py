@@ -1,0 +1,178 @@
+"""GPU witness synthesis + wrap proving, through the C ABI, against the oracle and the test-only host interpreter."""
+import ctypes as C
+import os
+import random
+import subprocess
+
+import numpy as np
+import pytest
+
+import gpw
+from oracle import bn254 as ob
+from oracle import goldilocks as ogl
+from oracle.engine import Api
+from oracle.poseidon import GoldilocksChip, BN254Chip
+from oracle.verifier import verify_testdata
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+R = ob.R
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    c = gpw.Context(0)
+    yield c
+    c.close()
+
+
+def _solve(ctx, circ, inputs, challenge=12345):
+    import torch
+    inp = torch.from_numpy(np.ascontiguousarray(inputs).view(np.int64)).cuda()
+    wires = torch.zeros((circ.n_wires, 4), dtype=torch.int64, device="cuda")
+    torch.cuda.synchronize()
+    circ.solve_phase1_dev(inp.data_ptr(), 1, wires.data_ptr(), circ.n_wires)
+    circ.solve_phase2_dev([challenge] if circ.info["limb_wires"] else None, 1, wires.data_ptr(), circ.n_wires)
+    ctx.sync()
+    return wires
+
+
+def _wire_ints(wires, idx):
+    import torch
+    sel = wires[torch.from_numpy(idx.astype(np.int64)).cuda()].cpu().numpy().view(np.uint64)
+    return gpw.limbs_to_ints(gpw.host_ff_from_mont(0, sel))
+
+
+def test_gadget_circuits_on_gpu(ctx, kats):
+    # Poseidon-GL KAT circuit: satisfied with the right outputs, unsatisfied (-6) with a wrong one
+    circ = gpw.Circuit.compile_gadget(ctx, "poseidon_gl")
+    assert (circ.info["muladd"], circ.info["reduce"], circ.info["split"]) == (130, 630, 890)
+    out = [int(x) for x in kats["poseidon_gl_perm_zero"]]
+    w = _solve(ctx, circ, circ.inputs_from_ints(out, [0] * 12))
+    assert circ.r1cs_eval_dev(w.data_ptr()) == 0
+    # the hint outputs on the GPU == the oracle's hint trace, in order
+    api = Api()
+    GoldilocksChip(api).Poseidon([0] * 12)
+    for kind, op in (("muladd", 1), ("reduce", 2), ("split", 4)):
+        exp = [o for k, _, outs in api.hints if k == kind for o in outs]
+        assert _wire_ints(w, circ.hint_wires(op)) == exp
+    w = _solve(ctx, circ, circ.inputs_from_ints([out[0] ^ 1] + out[1:], [0] * 12))
+    with pytest.raises(gpw.GpwError) as e:
+        circ.r1cs_eval_dev(w.data_ptr())
+    assert e.value.code == -6
+    circ.close()
+    circ = gpw.Circuit.compile_gadget(ctx, "poseidon_bn254")
+    for case in kats["poseidon_bn254"]:
+        w = _solve(ctx, circ, circ.inputs_from_ints([int(x) for x in case["out"]], [int(x) for x in case["in"]]))
+        assert circ.r1cs_eval_dev(w.data_ptr()) == 0
+    circ.close()
+    circ = gpw.Circuit.compile_gadget(ctx, "qe_mul_div")
+    a = tuple(map(int, kats["qe_mul"]["a"]))
+    b = tuple(map(int, kats["qe_mul"]["b"]))
+    ch = ogl.Chip(Api(trace=False))
+    m = ch.MulExtension(a, b)
+    d, _ = ch.DivExtension(a, b)
+    w = _solve(ctx, circ, circ.inputs_from_ints(list(m) + list(d), list(a) + list(b)))
+    assert circ.r1cs_eval_dev(w.data_ptr()) == 0
+    circ.close()
+    # RangeCheck: accepts 0, 1, p-1; the SplitLimbs hint rejects p (goldilocks/base_test.go:26-44)
+    circ = gpw.Circuit.compile_gadget(ctx, "range_check")
+    for x in (0, 1, ogl.P - 1):
+        w = _solve(ctx, circ, circ.inputs_from_ints([], [x]))
+        assert circ.r1cs_eval_dev(w.data_ptr()) == 0
+    with pytest.raises(gpw.GpwError) as e:
+        _solve(ctx, circ, circ.inputs_from_ints([], [ogl.P]))
+    assert e.value.code == -5 and "SplitLimbsHint" in str(e.value)
+    circ.close()
+
+
+@pytest.fixture(scope="module")
+def step(ctx, testdata_dir):
+    d = os.path.join(testdata_dir, "step")
+    rd = lambda f: open(os.path.join(d, f), "rb").read()
+    circ = gpw.Circuit.compile_verifier(ctx, rd("common_circuit_data.json"))
+    inputs = circ.parse_inputs(rd("proof_with_public_inputs.json"), rd("verifier_only_circuit_data.json"))
+    yield circ, inputs, d
+    circ.close()
+
+
+def test_step_witness_on_gpu_matches_oracle_trace_and_satisfies_r1cs(ctx, step):
+    circ, inputs, d = step
+    assert (circ.info["muladd"], circ.info["reduce"], circ.info["split"], circ.info["inverse"]) == (44186, 151410, 251232, 1849)
+    w = _solve(ctx, circ, inputs, challenge=0x1234567890abcdef1234567890abcdef)
+    assert circ.r1cs_eval_dev(w.data_ptr()) == 0          # all ~5.6 M constraints hold on the device
+    api, _ = verify_testdata(d)
+    for kind, op in (("muladd", 1), ("reduce", 2), ("inverse", 3), ("split", 4)):
+        exp = [o for k, _, outs in api.hints if k == kind for o in outs]
+        assert _wire_ints(w, circ.hint_wires(op)) == exp, kind
+
+
+def test_step_witness_equals_host_interpreter(ctx, step):
+    # wire-for-wire equality of the CUDA executor with the sequential test interpreter
+    circ, inputs, d = step
+    hostlib = os.path.join(ROOT, "tests", "hostlib")
+    subprocess.check_call(["make", "-C", hostlib], stdout=subprocess.DEVNULL)
+    lib = C.CDLL(os.path.join(hostlib, "libgpw_circuit_test.so"))
+    lib.ct_compile.restype = C.c_void_p
+    lib.ct_compile.argtypes = [C.c_char_p]
+    lib.ct_solve_inputs.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p]
+    lib.ct_wires_mont.argtypes = [C.c_void_p, C.c_void_p]
+    h = lib.ct_compile(open(os.path.join(d, "common_circuit_data.json"), "rb").read())
+    x = 987654321987654321
+    xl = gpw.ints_to_limbs([x])
+    npub = circ.info["public"]
+    pub, sec = np.ascontiguousarray(inputs[:npub]), np.ascontiguousarray(inputs[npub:])
+    assert lib.ct_solve_inputs(h, pub.ctypes.data, npub, sec.ctypes.data, len(sec), xl.ctypes.data) == 0
+    ref = np.zeros((circ.n_wires, 4), dtype=np.uint64)
+    lib.ct_wires_mont(h, ref.ctypes.data)
+    w = _solve(ctx, circ, inputs, challenge=x).cpu().numpy().view(np.uint64)
+    assert (w == ref).all()
+
+
+def test_tampered_proof_is_rejected_on_gpu(ctx, step):
+    import json
+    circ, inputs, d = step
+    rd = lambda f: open(os.path.join(d, f), "rb").read()
+    p = json.loads(rd("proof_with_public_inputs.json"))
+    p["proof"]["openings"]["plonk_zs"][0][0] ^= 1
+    bad = circ.parse_inputs(json.dumps(p), rd("verifier_only_circuit_data.json"))
+    w = _solve(ctx, circ, bad)
+    with pytest.raises(gpw.GpwError) as e:
+        circ.r1cs_eval_dev(w.data_ptr())
+    assert e.value.code == -6
+    # a structurally wrong proof is refused by the codec
+    del p["proof"]["openings"]["wires"][0]
+    with pytest.raises(gpw.GpwError):
+        circ.parse_inputs(json.dumps(p), rd("verifier_only_circuit_data.json"))
+
+
+def test_wrap_prove_step(ctx, step):
+    # full wrap: witness + commitment + Groth16; proof elements recomputed in the exponent from the witness
+    import torch
+    circ, inputs, d = step
+    key = gpw.WrapKey(ctx, circ, seed=99)
+    r_, s_ = 0x1111222233334444, 0x5555666677778888
+    pr = key.prove(inputs, r_, s_, check=True)
+    assert pr["n_unsatisfied"] == 0
+    pr2 = key.prove(inputs, r_, s_, check=True)
+    assert (pr["raw"] == pr2["raw"]).all()            # deterministic given (r, s)
+    for g, name in ((1, "Ar"), (2, "Bs"), (1, "Krs"), (1, "commitment"), (1, "pok")):
+        assert gpw.host_ec_is_on_curve(g, pr[name]) and pr[name].any()
+    # challenge = hash_to_field(serialised commitment)
+    cx, cy = gpw.points_to_ints(1, pr["commitment"])[0]
+    assert pr["challenge"] == gpw.hash_to_fr(cx.to_bytes(32, "big") + cy.to_bytes(32, "big"))
+    # exponent check of Ar and of the commitment from the device-resident witness
+    info = key.info
+    wires = torch.empty((info["m"], 4), dtype=torch.int64, device="cuda")
+    import ctypes
+    ctypes.cdll.LoadLibrary("libcudart.so").cudaMemcpy(ctypes.c_void_p(wires.data_ptr()), ctypes.c_void_p(key.wires_ptr),
+                                                       ctypes.c_size_t(info["m"] * 32), ctypes.c_int(3))
+    wv = gpw.limbs_to_ints(gpw.host_ff_from_mont(0, wires.cpu().numpy().view(np.uint64)))
+    suppA = circ.supports(0)
+    sA = (99 + 1 + sum(wv[w_] * (1 + j) for j, w_ in enumerate(suppA)) + r_ * (99 + 3)) % R
+    assert gpw.points_to_ints(1, pr["Ar"])[0] == ob.point_key(1, ob.ec_mul(1, ob.G1_GEN, sA))
+    ls, nc = info["limb_start"], info["n_committed"]
+    sD = sum(wv[ls + i] * ((1 << 35) + ls + i) for i in range(nc)) % R
+    assert gpw.points_to_ints(1, pr["commitment"])[0] == ob.point_key(1, ob.ec_mul(1, ob.G1_GEN, sD))
+    print("wrap stats (ms):", key.last_stats(), "key:", info)
+    key.close()
