@@ -2,11 +2,15 @@
 """bench.py - wrap-proofs/sec for the Plonky2 -> Groth16 hot path on B200 (BASELINE.json metric).
 
   python bench.py --gpus N --steps K --warmup W [--impl reference]
-  (N > 1: launched by torch.distributed.run, one rank per GPU; weak scaling = one proof stream per GPU,
-   no data-path collective - independent proofs shard one-per-GPU)
+  (N > 1: launched by torch.distributed.run, one rank per GPU; weak scaling = one proof stream per GPU, no
+   data-path collective - independent proofs shard one-per-GPU)
 
-One "step" = one Groth16 prove of the testdata/step-shaped circuit. Prints ONE JSON line (rank 0).
-See DESIGN.md "Measurement" for what is inside the timed region and how roofline numbers are derived.
+One "step" = one complete wrap of the real testdata/step Plonky2 proof (BASELINE.json configs[1]):
+  parsed proof inputs -> witness synthesis on the GPU (449 k reference hints, 5.6 M constraints, 7.67 M wires) ->
+  range-check commitment (2 MSMs) -> log-derivative argument -> R1CS evaluation -> computeH (7 NTTs of 2^23) ->
+  MSM G1 {A, B1, K, Z} + MSM G2 {B2} -> Groth16 proof (Ar, Bs, Krs) + commitment + PoK on the host.
+Compile (frontend.Compile) and setup (groth16.DummySetup) are one-off per circuit and outside the timed region, as
+in BASELINE.md 5. Prints ONE JSON line (rank 0). See DESIGN.md "Measurement".
 """
 import argparse
 import json
@@ -19,12 +23,7 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "gnark-plonky2-verifier_b200"))
-
-# workload shape of configs[1] (testdata/step under Groth16): wires, public wires, FFT domain
-M_WIRES = int(os.environ.get("GPW_BENCH_WIRES", 7_000_000))
-N_PUB = 37
-LOGN = int(os.environ.get("GPW_BENCH_LOGN", 23))
-R_MOD = 21888242871839275222246405745257275088548364400416034343698204186575808495617
+TESTDATA = os.path.join(ROOT, "tests", "golden", "testdata", os.environ.get("GPW_BENCH_CIRCUIT", "step"))
 
 
 def measured_peak_gbs():
@@ -65,25 +64,20 @@ class ClockSampler(threading.Thread):
                 "sm_max_mhz": int(self.samples[0][1]) if self.samples[0][1].isdigit() else None, "reasons": reasons}
 
 
-def witness_shaped_scalars(torch, n, seed, device):
-    """Montgomery-form Fr scalars with the wire-value mix of a gnark witness: 15% in {0,1},
-    20% < 2^16, 45% < 2^64, 20% full width. Built as canonical ints then converted on the GPU."""
-    g = torch.Generator(device=device).manual_seed(seed)
-    s = torch.randint(0, 1 << 62, (n, 4), dtype=torch.int64, device=device, generator=g)
-    s[:, 3] &= (1 << 59) - 1
-    u = torch.rand(n, device=device, generator=g)
-    s[u < 0.80, 1:] = 0
-    s[u < 0.35, 0] &= 0xffff
-    s[u < 0.15, 0] &= 1
-    return s
+# sizes of the compiled step circuit (printed by the GPU arm; used by the CPU arm, which cannot compile without libgpw)
+STEP_SHAPE = {"wires": 7672120, "constraints": 5597007, "logN": 23, "nA": 7075007, "nB": 3861384, "n_committed": 2528029,
+              "n_k": 5144054}
 
 
-def cpu_baseline(threads=None, budget_s=20.0):
-    """Times the C oracle (oracle/c, OpenMP) on a bounded sample and extrapolates to one step-shaped proof.
-    The only place bench.py executes oracle/ code; reported, not optimised."""
+def cpu_baseline(threads=None):
+    """The reference-equivalent CPU path timed on this box's host cores (oracle port; the only place bench.py runs
+    oracle/ code): (1) the Python oracle replays the verifier dataflow of the real step proof = the witness solve
+    (single thread, like one gnark solver level at a time); (2) the C/OpenMP port of gnark-crypto's Pippenger MSM and
+    radix-2 FFT is timed on a bounded sample and extrapolated linearly to the circuit's real MSM / FFT sizes."""
     import ctypes as C
     import numpy as np
     import gpw
+    from oracle.verifier import verify_testdata
     so = os.path.join(ROOT, "oracle", "c", "libbn254_ref.so")
     if not os.path.exists(so):
         subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle", "c")], stdout=subprocess.DEVNULL)
@@ -93,22 +87,23 @@ def cpu_baseline(threads=None, budget_s=20.0):
     lib.ref_msm_g1.argtypes = [vp, vp, C.c_size_t, C.c_int, C.c_int, C.c_int, vp]
     lib.ref_msm_g2.argtypes = [vp, vp, C.c_size_t, C.c_int, C.c_int, C.c_int, vp]
     lib.ref_ntt_fr.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int]
+    t0 = time.perf_counter()
+    verify_testdata(TESTDATA, trace=False)
+    t_wit = time.perf_counter() - t0
     rng = np.random.default_rng(1)
 
-    def scalars(n):
+    def scalars(n):   # wire-value mix of the real witness: mostly 16/32/64-bit values
         s = rng.integers(0, 1 << 62, size=(n, 4), dtype=np.uint64)
         s[:, 3] &= np.uint64((1 << 59) - 1)
         u = rng.random(n)
-        s[u < 0.80, 1:] = 0
-        s[u < 0.35, 0] &= np.uint64(0xffff)
+        s[u < 0.85, 1:] = 0
+        s[u < 0.45, 0] &= np.uint64(0xffff)
         s[u < 0.15, 0] &= np.uint64(1)
         return s
 
     n1, n2, ln = 1 << 18, 1 << 16, 18
-    p1 = gpw.host_ec_generator_multiples(1, 1, 4096)
-    p1 = np.ascontiguousarray(np.tile(p1, (n1 // 4096, 1)))
-    p2 = gpw.host_ec_generator_multiples(2, 1, 1024)
-    p2 = np.ascontiguousarray(np.tile(p2, (n2 // 1024, 1)))
+    p1 = np.ascontiguousarray(np.tile(gpw.host_ec_generator_multiples(1, 1, 4096), (n1 // 4096, 1)))
+    p2 = np.ascontiguousarray(np.tile(gpw.host_ec_generator_multiples(2, 1, 1024), (n2 // 1024, 1)))
     s1, s2 = scalars(n1), scalars(n2)
     out = np.zeros(16, dtype=np.uint64)
     t0 = time.perf_counter()
@@ -121,22 +116,30 @@ def cpu_baseline(threads=None, budget_s=20.0):
     t0 = time.perf_counter()
     lib.ref_ntt_fr(a.ctypes.data, ln, 0, 1, nthreads)
     t_ntt = time.perf_counter() - t0
-    N = 1 << LOGN
-    # linear extrapolation in the number of points / butterflies (optimistic for the CPU: larger windows help a bit)
-    t_proof = t_g1 * (3 * M_WIRES + N) / n1 + t_g2 * M_WIRES / n2 + 7 * t_ntt * (N * LOGN) / ((1 << ln) * ln)
+    S = STEP_SHAPE
+    N = 1 << S["logN"]
+    g1_points = S["nA"] + S["nB"] + S["n_k"] + (N - 1) + 2 * S["n_committed"]
+    t_proof = t_wit + t_g1 * g1_points / n1 + t_g2 * S["nB"] / n2 + 7 * t_ntt * (N * S["logN"]) / ((1 << ln) * ln)
     return {"value": 1.0 / t_proof, "unit": "proofs/s", "cores": int(nthreads), "kind": "port",
-            "sample": "C/OpenMP port of gnark-crypto Pippenger+FFT (oracle/c): MSM G1 n=2^18 %.2fs, MSM G2 n=2^16 %.2fs, "
-                      "coset NTT 2^18 %.3fs, witness-shaped scalars; extrapolated linearly to 4 G1 MSMs + 1 G2 MSM over "
-                      "%d wires and 7 NTTs of 2^%d; witness solve not included" % (t_g1, t_g2, t_ntt, M_WIRES, LOGN),
+            "sample": "witness: Python oracle replay of the step proof %.1fs (1 thread); prover: C/OpenMP port of gnark-crypto "
+                      "Pippenger+FFT on %d threads: MSM G1 n=2^18 %.2fs, MSM G2 n=2^16 %.2fs, coset NTT 2^18 %.3fs, "
+                      "witness-shaped scalars, extrapolated linearly to %d G1 points, %d G2 points, 7 NTTs of 2^%d"
+                      % (t_wit, nthreads, t_g1, t_g2, t_ntt, g1_points, S["nB"], S["logN"]),
             "t_proof_s": t_proof}
 
 
+def workload_config():
+    return {"workload": "wrap_prove(testdata/%s, Groth16): parsed Plonky2 proof -> GPU witness synthesis (tape) -> range-check "
+                        "commitment -> R1CS eval -> computeH (7 NTT 2^23) -> MSM G1 x6 + MSM G2 x1 -> proof; real proof, "
+                        "synthetic proving key (DummySetup analogue)" % os.path.basename(TESTDATA),
+            "circuit": STEP_SHAPE, "l2_policy": "inputs_exceed_l2 (7.67 M wires + 3 x 2^23 Fr vectors + >2 GB of bases per step)",
+            "witness_synthesis_in_step": True}
+
+
 def run_reference(args):
-    rank = int(os.environ.get("RANK", 0))
-    if rank != 0:
+    if int(os.environ.get("RANK", 0)) != 0:
         return
-    vals = []
-    base = None
+    vals, base = [], None
     for i in range(args.warmup + args.steps):
         base = cpu_baseline()
         if i >= args.warmup:
@@ -144,20 +147,11 @@ def run_reference(args):
     t = sum(vals) / len(vals)
     base["value"] = 1.0 / t
     line = {"metric": "wrap_proofs_per_sec", "value": 1.0 / t, "unit": "proofs/s", "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "u32x8-montgomery", "data": "synthetic", "impl": "reference",
-            "config": workload_config(), "cpu_baseline": {k: v for k, v in base.items() if k != "t_proof_s"},
-            "e2e": {"value": 1.0 / t, "unit": "proofs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-            "gpu_launches": 0}
+            "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u32x8-montgomery", "data": "synthetic", "impl": "reference", "config": workload_config(),
+            "cpu_baseline": {k: v for k, v in base.items() if k != "t_proof_s"},
+            "e2e": {"value": 1.0 / t, "unit": "proofs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
     print(json.dumps(line), flush=True)
-
-
-def workload_config():
-    return {"workload": "groth16_prove(step-shaped R1CS: %d wires, %d public, FFT domain 2^%d; computeH = 7 NTT + "
-                        "pointwise, MSM G1 x4 {A,B1,K,Z} + MSM G2 x1 {B2}); witness-shaped scalars; synthetic proving key "
-                        "with known discrete logs (DummySetup analogue)" % (M_WIRES, N_PUB, LOGN),
-            "wires": M_WIRES, "fft_domain_log2": LOGN, "l2_policy": "inputs_exceed_l2 (>=1.2 GB touched per step)",
-            "witness_synthesis_in_step": False}
 
 
 def main():
@@ -189,36 +183,20 @@ def main():
     torch.cuda.set_stream(side)
     ctx.set_stream(side.cuda_stream)
 
-    N = 1 << LOGN
-    pk = ctx.groth16_pk_synthetic(M_WIRES, N_PUB, LOGN, seed=0x5EED)
-    # synthetic solved witness: wire values + the three evaluation vectors with c = a o b (so h is exact)
-    w = witness_shaped_scalars(torch, M_WIRES, 100 + rank, dev)
-    a0 = witness_shaped_scalars(torch, N, 200 + rank, dev)
-    b0 = witness_shaped_scalars(torch, N, 300 + rank, dev)
-    torch.cuda.synchronize()
-    for t_ in (w, a0, b0):      # gnark keeps wire values in Montgomery form; MSM digits come from the canonical value
-        ctx.fr_convert_dev(t_.data_ptr(), t_.shape[0], to_mont=True)
-    one = gpw.host_ff_to_mont(0, gpw.ints_to_limbs([1]))[0]
-    c0 = a0.clone()
-    zeros = torch.zeros_like(a0)
-    ctx.h_pointwise_dev(c0.data_ptr(), b0.data_ptr(), zeros.data_ptr(), N, one)   # c0 = a0 * b0 (Montgomery)
-    del zeros
-    a, b, c = torch.empty_like(a0), torch.empty_like(a0), torch.empty_like(a0)
-    # pinned host copies for the end-to-end arm
-    hw, ha, hb, hc = (t.cpu().pin_memory() for t in (w, a0, b0, c0))
+    rd = lambda f: open(os.path.join(TESTDATA, f), "rb").read()
+    circ = gpw.Circuit.compile_verifier(ctx, rd("common_circuit_data.json"))           # frontend.Compile (untimed)
+    key = gpw.WrapKey(ctx, circ, seed=0x5EED + rank)                                      # DummySetup (untimed)
+    inputs = circ.parse_inputs(rd("proof_with_public_inputs.json"), rd("verifier_only_circuit_data.json"))
+    host_inputs = torch.from_numpy(inputs.view(np.int64)).pin_memory()
+    dev_inputs = host_inputs.to(dev)
     torch.cuda.synchronize()
     r_int, s_int = 0x1234567 + rank, 0x7654321 + rank
 
     def step_resident():
-        a.copy_(a0), b.copy_(b0), c.copy_(c0)
-        return pk.prove_dev(w.data_ptr(), a.data_ptr(), b.data_ptr(), c.data_ptr(), r_int, s_int)
-
-    dw = torch.empty_like(w)
+        return key.prove_ptr(dev_inputs.data_ptr(), r_int, s_int, check=True, on_device=True)
 
     def step_e2e():
-        dw.copy_(hw, non_blocking=True), a.copy_(ha, non_blocking=True)
-        b.copy_(hb, non_blocking=True), c.copy_(hc, non_blocking=True)
-        return pk.prove_dev(dw.data_ptr(), a.data_ptr(), b.data_ptr(), c.data_ptr(), r_int, s_int)
+        return key.prove_ptr(host_inputs.data_ptr(), r_int, s_int, check=True, on_device=False)
 
     def barrier():
         torch.cuda.synchronize()
@@ -230,14 +208,14 @@ def main():
         for _ in range(warmup):
             fn()
         barrier()
+        key.msm_cumulative_stats(1, reset=True)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         l0 = ctx.launches
-        acc_ms, acc_bytes, proofs = [], [], []
+        proofs, stats = [], []
         e0.record(side)
         for _ in range(steps):
             proofs.append(fn())
-            st = pk.last_stats()
-            acc_ms.append(st)
+            stats.append(key.last_stats())
         e1.record(side)
         barrier()
         ms = e0.elapsed_time(e1)
@@ -245,41 +223,49 @@ def main():
             t = torch.tensor([ms], device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ms = float(t.item())
-        return ms, ctx.launches - l0, acc_ms, proofs
+        return ms, ctx.launches - l0, stats, proofs
 
     sampler = ClockSampler(local)
     sampler.start()
     ms, launches, stats, proofs = timed(step_resident, args.steps, args.warmup)
+    g1 = key.msm_cumulative_stats(1)
+    g2 = key.msm_cumulative_stats(2)
     sampler.stop_flag = True
     sampler.join(timeout=2)
-    ms_e2e, _, _, proofs2 = timed(step_e2e, max(2, args.steps // 2), 1)
     steps_e2e = max(2, args.steps // 2)
-    assert all((p[0] == proofs[0][0]).all() for p in proofs + proofs2), "proof not reproducible across steps"
+    ms_e2e, _, _, proofs2 = timed(step_e2e, steps_e2e, 1)
+    assert all((p["raw"] == proofs[0]["raw"]).all() for p in proofs + proofs2), "proof not reproducible across steps"
+    assert proofs[0]["n_unsatisfied"] == 0
 
-    # dominant kernel: k_msm_accumulate<Fp>; timed by CUDA events on the launching stream inside libgpw. The per-MSM
-    # figure below uses the whole-MSM event time of the G1 MSMs; the accumulate share is reported alongside.
-    g1_ms = [s["msm_ms"][k] for s in stats for k in ("A", "B1", "K", "Z")]
-    g1_pts = [M_WIRES, M_WIRES, M_WIRES - N_PUB, N - 1] * len(stats)
-    alg_bytes = 96.0 * sum(g1_pts) / len(g1_pts)
-    avg_ms = sum(g1_ms) / len(g1_ms)
+    # dominant kernel: k_msm_accumulate<Fp> (bucket accumulation of the G1 MSMs), timed by CUDA events on the launching
+    # stream inside libgpw. achieved = algorithmic bytes (96 B per point) per launch / average launch duration.
     peak, peak_kind = measured_peak_gbs()
-    achieved = alg_bytes / (avg_ms * 1e-3) / 1e9
+    avg_ms = g1["accumulate_ms"] / max(g1["calls"], 1)
+    alg_bytes = 96.0 * g1["points"] / max(g1["calls"], 1)
+    achieved = alg_bytes / (avg_ms * 1e-3) / 1e9 if avg_ms > 0 else 0.0
+    step_ms = ms / args.steps
     last = stats[-1]
     value = world * args.steps / (ms * 1e-3)
     e2e_value = world * steps_e2e / (ms_e2e * 1e-3)
-    h2d = int(hw.numel() + ha.numel() + hb.numel() + hc.numel()) * 8
     line = {
         "metric": "wrap_proofs_per_sec", "value": value, "unit": "proofs/s", "n_gpus": world, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "u32x8-montgomery", "data": "synthetic", "config": workload_config(),
-        "e2e": {"value": e2e_value, "unit": "proofs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 256},
+        "warmup": args.warmup, "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "u32x8-montgomery", "data": "synthetic", "config": workload_config(),
+        "e2e": {"value": e2e_value, "unit": "proofs/s", "h2d_bytes_per_step": int(inputs.nbytes), "d2h_bytes_per_step": 512},
         "gpu_launches": int(launches),
-        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": None, "peak_source": peak_kind, "kernel": "MSM G1 (k_msm_accumulate<Fp> + sort/reduce)",
-                     "note": "BN254 MSM is integer-pipe (IMAD) bound; the HBM fraction is low by construction "
-                             "(BASELINE.md 4). achieved = 96 B x points / whole-MSM time"},
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                     "peak_source": peak_kind, "kernel": "k_msm_accumulate<Fp> (MSM G1 bucket accumulation)",
+                     "launches_per_step": g1["calls"] / args.steps, "avg_launch_ms": avg_ms,
+                     "avg_points_per_launch": g1["points"] / max(g1["calls"], 1),
+                     "nonzero_digits_per_point": g1["digits"] / max(g1["points"], 1),
+                     "kernel_share_of_step": g1["accumulate_ms"] / ms,
+                     "msm_g1_whole_GBps": 96.0 * g1["points"] / (g1["total_ms"] * 1e-3) / 1e9 if g1["total_ms"] else None,
+                     "msm_g2_whole_GBps": 160.0 * g2["points"] / (g2["total_ms"] * 1e-3) / 1e9 if g2["total_ms"] else None,
+                     "note": "BN254 MSM is integer-pipe (IMAD) bound, ~3000 IMADs per 96 B point-digit; the HBM fraction is low "
+                             "by construction (BASELINE.md 4)"},
         "clocks": sampler.summary(),
-        "breakdown_ms": {"compute_h": last["compute_h_ms"], **{"msm_" + k: v for k, v in last["msm_ms"].items()}},
+        "breakdown_ms": last,
+        "circuit": {**circ.info, **key.info},
     }
     if rank == 0:
         if world == 1:

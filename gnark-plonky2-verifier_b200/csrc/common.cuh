@@ -58,6 +58,9 @@ struct gpw_ctx {
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
   float msm_acc_ms = 0.f, msm_total_ms = 0.f;
   uint64_t msm_digits = 0;
+  // cumulative statistics of the G1 bucket-accumulation kernel (bench.py roofline): [0] G1, [1] G2
+  double msm_acc_ms_sum[2] = {0, 0}, msm_total_ms_sum[2] = {0, 0};
+  uint64_t msm_points_sum[2] = {0, 0}, msm_digits_sum[2] = {0, 0}, msm_calls[2] = {0, 0};
   bool poseidon_consts_loaded = false;
 
   int get_scratch(const char* name, size_t bytes, void** out);

@@ -303,6 +303,31 @@ void API::AssertIsEqual(const Variable& a, const Variable& b) {
   add_constraint(a, Const(1), b);
 }
 
+void API::FuseAsMacro(Op op, size_t tape_begin, uint32_t wire_begin, const Variable in[4]) {
+  const uint32_t nout = next_wire_ - wire_begin;
+  if (nout == 0) return;  // everything folded to constants
+  uint32_t expect = wire_begin;
+  for (size_t i = tape_begin; i < tape_.size(); i++) {
+    if (tape_[i].op != OP_MUL || tape_[i].nout != 1 || tape_[i].out != expect)
+      throw std::logic_error("FuseAsMacro: the fused region must consist of multiplications defining consecutive wires");
+    expect++;
+  }
+  if (expect != next_wire_) throw std::logic_error("FuseAsMacro: wires created outside the tape in the fused region");
+  counts_.mul -= (tape_.size() - tape_begin);
+  tape_.resize(tape_begin);
+  uint32_t lvl = 0, le[4];
+  for (int i = 0; i < 4; i++) {
+    lvl = std::max(lvl, level_of(in[i]));
+    le[i] = intern_le(in[i]);
+  }
+  lvl += 1;
+  for (uint32_t w = wire_begin; w < next_wire_; w++) wire_level_[w] = lvl;
+  if (lvl > max_level_) max_level_ = lvl;
+  Instr m{(uint8_t)op, wire_begin, nout, {le[0], le[1], le[2]}, lvl};
+  m.le3 = le[3];
+  tape_.push_back(m);
+}
+
 void API::RangeCheckCollect(const Variable& v, int bits) {
   if (bits % 16 != 0) throw std::logic_error("v.bits is not nbBits aligned");  // goldilocks/base.go:433-435
   rc_.push_back({intern_le(v), bits});
@@ -386,9 +411,10 @@ void API::ScheduleALAP() {
     if (in.op == OP_COMMIT && count_idx >= 0) alap[count_idx] = std::min(alap[count_idx], alap[ii] - 1);
     if (in.op == OP_COUNT) continue;  // its inputs (all DECOMP outputs) are handled below
     if (in.op == OP_DECOMP && count_idx >= 0) alap[ii] = std::min(alap[ii], alap[count_idx] - 1);
-    for (int j = 0; j < 3; j++) {
-      if (in.le[j] == NO_LE) continue;
-      for (uint32_t k = le_off_[in.le[j]]; k < le_off_[in.le[j] + 1]; k++) {
+    for (int j = 0; j < 4; j++) {
+      const uint32_t lej = j < 3 ? in.le[j] : in.le3;
+      if (lej == NO_LE) continue;
+      for (uint32_t k = le_off_[lej]; k < le_off_[lej + 1]; k++) {
         uint32_t p = producer[le_wire_[k]];
         if (p != NO_LE) alap[p] = std::min(alap[p], alap[ii] - 1);
       }
@@ -401,6 +427,76 @@ void API::ScheduleALAP() {
     for (uint32_t k = 0; k < tape_[i].nout; k++) wire_level_[tape_[i].out + k] = alap[i];
     if (tape_[i].op == OP_COMMIT) commit_level_ = alap[i];
   }
+}
+
+void API::ScheduleSpineAndTail() {
+  if (tape_.empty()) return;
+  const size_t n = tape_.size();
+  std::vector<uint32_t> producer(next_wire_, NO_LE);
+  for (uint32_t i = 0; i < n; i++)
+    for (uint32_t k = 0; k < tape_[i].nout; k++) producer[tape_[i].out + k] = i;
+  // 1. height = longest path (in instructions) from an instruction down to a sink of the tape. The spine of the
+  //    verifier (sponge -> FRI) has heights in the tens of thousands; the side branches every hinted operation
+  //    sprouts (SplitLimbs -> IsZero inverse -> select, limb decomposition -> histogram -> commitment -> divisions)
+  //    end within a handful of steps. Everything of small height is "tail".
+  constexpr uint32_t TAIL_HEIGHT = 7;
+  std::vector<uint32_t> height(n, 0);
+  int64_t cnt_i = -1, com_i = -1;
+  for (uint32_t i = 0; i < n; i++) {
+    if (tape_[i].op == OP_COUNT) cnt_i = i;
+    if (tape_[i].op == OP_COMMIT) com_i = i;
+  }
+  for (size_t ii = n; ii-- > 0;) {
+    const Instr& in = tape_[ii];
+    if (in.op == OP_COUNT && com_i >= 0) height[ii] = std::max(height[ii], height[com_i] + 1);   // commitment covers the counts
+    if (in.op == OP_DECOMP && cnt_i >= 0) height[ii] = std::max(height[ii], height[cnt_i] + 1);  // histogram reads the limbs
+    for (int j = 0; j < 4; j++) {
+      const uint32_t lej = j < 3 ? in.le[j] : in.le3;
+      if (lej == NO_LE) continue;
+      for (uint32_t k = le_off_[lej]; k < le_off_[lej + 1]; k++) {
+        uint32_t p = producer[le_wire_[k]];
+        if (p != NO_LE) height[p] = std::max(height[p], height[ii] + 1);
+      }
+    }
+  }
+  std::vector<uint8_t> tail(n, 0);
+  for (size_t i = 0; i < n; i++) tail[i] = height[i] <= TAIL_HEIGHT ? 1 : 0;
+  // 2. levels: spine keeps its ASAP level (parallel branches stay aligned, so the 28 FRI queries execute their
+  //    expensive inversions in the same level); tail instructions are levelled among themselves after the spine.
+  uint32_t spine_max = 0;
+  for (size_t i = 0; i < n; i++)
+    if (!tail[i]) spine_max = std::max(spine_max, tape_[i].level);
+  std::vector<uint32_t> tl(n, 0);
+  uint32_t max_level = spine_max;
+  int64_t count_idx = -1;
+  uint32_t decomp_max = 0;
+  for (size_t i = 0; i < n; i++) {
+    if (!tail[i]) continue;
+    const Instr& in = tape_[i];
+    uint32_t lvl = spine_max + 1;
+    for (int j = 0; j < 4; j++) {
+      const uint32_t lej = j < 3 ? in.le[j] : in.le3;
+      if (lej == NO_LE) continue;
+      for (uint32_t k = le_off_[lej]; k < le_off_[lej + 1]; k++) {
+        uint32_t p = producer[le_wire_[k]];
+        if (p != NO_LE && tail[p]) lvl = std::max(lvl, tl[p] + 1);
+      }
+    }
+    if (in.op == OP_DECOMP) decomp_max = std::max(decomp_max, lvl);
+    if (in.op == OP_COUNT) {
+      lvl = std::max(lvl, decomp_max + 1);
+      count_idx = (int64_t)i;
+    }
+    if (in.op == OP_COMMIT && count_idx >= 0) lvl = std::max(lvl, tl[count_idx] + 1);
+    tl[i] = lvl;
+    max_level = std::max(max_level, lvl);
+  }
+  for (size_t i = 0; i < n; i++) {
+    if (tail[i]) tape_[i].level = tl[i];
+    for (uint32_t k = 0; k < tape_[i].nout; k++) wire_level_[tape_[i].out + k] = tape_[i].level;
+    if (tape_[i].op == OP_COMMIT) commit_level_ = tape_[i].level;
+  }
+  max_level_ = max_level;
 }
 
 }  // namespace fe

@@ -54,6 +54,12 @@ enum Op : uint8_t {
   OP_DECOMP = 8,       // nout 16-bit limbs of <A>, LSB first       gnark std/rangecheck DecomposeHint
   OP_COUNT = 9,        // out[i] = multiplicity of value i among all limb wires (i < 65536)   CountHint
   OP_COMMIT = 10,      // out = challenge derived from the commitment to the committed wires  api.Commit
+  // Macro instruction: one whole Poseidon-BN254 permutation (poseidon/bn254.go:39-45). Inputs: the 4 state
+  // expressions; outputs: the x^2, x^4, x^5 wire of every S-box in the order the gadget code creates them (S-boxes
+  // of round 0 whose input is a constant are folded by the builder and emit nothing). The R1CS is untouched - the
+  // 264 multiplication constraints stay - only the SOLVER computes the permutation natively instead of replaying
+  // 264 separate multiplications whose operands are long linear expressions.
+  OP_POSEIDON_BN254 = 11,
 };
 
 struct Instr {
@@ -62,6 +68,7 @@ struct Instr {
   uint32_t nout;   // number of consecutive output wires
   uint32_t le[3];  // linear-expression ids of the inputs (NO_LE if unused)
   uint32_t level;
+  uint32_t le3 = 0xffffffffu;  // 4th input (macro instructions only)
 };
 constexpr uint32_t NO_LE = 0xffffffffu;
 
@@ -102,6 +109,10 @@ class API {
   std::vector<Variable> NewHint(Op op, uint32_t nout, const Variable* a, const Variable* b = nullptr,
                                 const Variable* c = nullptr);
   // ---- commit-based range checking (gnark std/rangecheck, frontend.Committer) ---------------------------
+  // Replaces the tape instructions created since (tape_begin, wire_begin) - which must all be OP_MULs defining the
+  // consecutive wires [wire_begin, NumWires()) - by ONE macro instruction with the given 4 inputs.
+  size_t TapeSize() const { return tape_.size(); }
+  void FuseAsMacro(Op op, size_t tape_begin, uint32_t wire_begin, const Variable in[4]);
   void RangeCheckCollect(const Variable& v, int bits);  // goldilocks/base.go:411-421, COMMIT_RANGE_CHECKER branch
   // Runs the deferred range-check construction (goldilocks/base.go:423-442 + gnark rangecheck commit):
   // limb decomposition, multiplicity histogram, commitment, log-derivative sums. Call once, at the end.
@@ -111,6 +122,9 @@ class API {
   // instructions that are leaves of the dataflow (range-check splits, IsZero inverses, selects, limb
   // decompositions) sink to a handful of very wide final levels that the GPU runs across all SMs.
   void ScheduleALAP();
+  // The schedule the GPU executor uses: the spine (everything of large dependency height) keeps its ASAP levels so
+  // that parallel branches stay aligned; the short side branches are gathered into a few wide levels at the end.
+  void ScheduleSpineAndTail();
 
   // ---- compiled circuit -----------------------------------------------------------------------------
   uint32_t NumWires() const { return next_wire_; }

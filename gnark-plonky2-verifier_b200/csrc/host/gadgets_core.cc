@@ -352,10 +352,15 @@ PoseidonBn254Chip::PoseidonBn254Chip(fe::API* api) : api(api) {
 
 Bn254State PoseidonBn254Chip::Poseidon(Bn254State state) {
   num_perms++;
+  const Variable in[4] = {state[0], state[1], state[2], state[3]};
+  const size_t tape_begin = api->TapeSize();
+  const uint32_t wire_begin = api->NumWires();
   state = ark(state, 0);
   state = fullRounds(state, true);
   state = partialRounds(state);
   state = fullRounds(state, false);
+  // same constraints, same wires; the solver computes the whole permutation with one macro instruction
+  api->FuseAsMacro(fe::OP_POSEIDON_BN254, tape_begin, wire_begin, in);
   return state;
 }
 

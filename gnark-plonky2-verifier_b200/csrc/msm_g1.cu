@@ -22,3 +22,23 @@ extern "C" int gpw_msm_last_stats(gpw_ctx* ctx, float* accumulate_ms, float* tot
   if (nonzero_digits) *nonzero_digits = ctx->msm_digits;
   return GPW_OK;
 }
+
+// Cumulative per-group MSM statistics since the last reset: out8 = {acc_ms_sum, total_ms_sum, points, digits, calls}
+// for group (1 = G1, 2 = G2). reset != 0 clears both groups afterwards.
+extern "C" int gpw_msm_cumulative_stats(gpw_ctx* ctx, int group, int reset, double* out5) {
+  if (!ctx || group < 1 || group > 2) return GPW_EINVAL;
+  const int g = group - 1;
+  if (out5) {
+    out5[0] = ctx->msm_acc_ms_sum[g];
+    out5[1] = ctx->msm_total_ms_sum[g];
+    out5[2] = (double)ctx->msm_points_sum[g];
+    out5[3] = (double)ctx->msm_digits_sum[g];
+    out5[4] = (double)ctx->msm_calls[g];
+  }
+  if (reset)
+    for (int i = 0; i < 2; i++) {
+      ctx->msm_acc_ms_sum[i] = ctx->msm_total_ms_sum[i] = 0;
+      ctx->msm_points_sum[i] = ctx->msm_digits_sum[i] = ctx->msm_calls[i] = 0;
+    }
+  return GPW_OK;
+}

@@ -458,6 +458,14 @@ static int msm_dev_impl(gpw_ctx* ctx, const Fr* scalars, const Affine<F>* points
   GPW_CUDA(cudaEventElapsedTime(&ctx->msm_acc_ms, ctx->ev[1], ctx->ev[2]));
   GPW_CUDA(cudaEventElapsedTime(&ctx->msm_total_ms, ctx->ev[0], ctx->ev[3]));
   ctx->msm_digits = M;
+  {
+    const int g = sizeof(Affine<F>) == 64 ? 0 : 1;
+    ctx->msm_acc_ms_sum[g] += ctx->msm_acc_ms;
+    ctx->msm_total_ms_sum[g] += ctx->msm_total_ms;
+    ctx->msm_points_sum[g] += n;
+    ctx->msm_digits_sum[g] += M;
+    ctx->msm_calls[g] += 1;
+  }
   // Horner over the window sums on the host: R = sum_w 2^(c (w)) W_w
   XYZZ<F> R = XYZZ<F>::inf();
   for (int w = nw - 1; w >= 0; w--) {

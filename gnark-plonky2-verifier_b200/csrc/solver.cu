@@ -21,6 +21,8 @@
 #include "gl.cuh"
 #include "host/frontend.h"
 #include "host/gadgets.h"
+#include "poseidon_bn254_macro.cuh"
+#include "poseidon_constants.inc"
 
 namespace gpw {
 
@@ -29,7 +31,7 @@ using fe::NO_LE;
 struct DInstr {
   uint32_t op_nout;  // op | nout << 8
   uint32_t out;
-  uint32_t le[3];
+  uint32_t le[4];
 };
 
 struct DevCircuit {
@@ -42,12 +44,20 @@ struct DevCircuit {
   const uint32_t* cons;
   uint32_t n_wires, n_cons, n_levels;
   uint32_t limb_start, n_limbs, count_start, commit_wire;
+  // linear expressions with thousands of terms (the two sides of the log-derivative identity: 65 536 and ~2.5 M
+  // terms) are reduced by a whole CTA each instead of by the single thread that owns their R1CS row
+  uint32_t n_long;
+  uint32_t long_le[8];
+  Fr* long_val;  // per-proof scratch is not needed: evaluated right before use on the stream
+  const Fr* bn_tables;  // Poseidon-BN254 constants: C[88] | S[392] | M[16] | P[16], Montgomery
 };
+constexpr uint32_t LONG_LE_TERMS = 2048;
 
 enum SegKind { SEG_NARROW, SEG_WIDE, SEG_COUNT, SEG_COMMIT };
 struct Segment {
   SegKind kind;
   uint32_t lo, hi;  // level range [lo, hi)
+  uint32_t stream_off = 0, first_words = 0;  // SEG_NARROW: location of its staged chunk stream
 };
 
 constexpr uint32_t WIDE_THRESHOLD = 8192;
@@ -68,18 +78,73 @@ __device__ __forceinline__ void st_w(Fr* p, const Fr& v) {
   d[1] = s[1];
 }
 
-__device__ __forceinline__ Fr eval_le(const DevCircuit& c, const Fr* W, uint32_t le) {
+// A linear expression as (wire, coefficient-id) term list. The terms live either in the global CSR arrays
+// (stride 1, separate arrays) or inline in a staged tape chunk in shared memory (stride 2, interleaved).
+// In the staged stream a term's location is either a wire id (value in HBM) or, with RING_FLAG set, a slot of the
+// CTA's shared-memory ring of recently produced wire values (assigned at compile time, see finish_compile).
+constexpr uint32_t RING_FLAG = 0x80000000u;
+constexpr uint32_t RING_SLOTS = 2048;  // 64 KB of shared memory
+
+struct LeRef {
+  const uint32_t* wires;
+  const uint32_t* cids;
+  uint32_t n, stride;
+  bool present;
+  const Fr* ring;  // nullptr on the CSR path
+};
+
+__device__ __forceinline__ Fr ld_term(const Fr* W, const Fr* ring, uint32_t loc) {
+  return (loc & RING_FLAG) ? ld_w(ring + (loc & (RING_SLOTS - 1))) : ld_w(W + loc);
+}
+
+// sum coeff_k * w_k. The operand loads of a batch are issued together (independent LDGs in flight) before any
+// arithmetic: on the sequential spine of the tape the latency of these loads is the critical path.
+// (A real function call, not inlined: exec_op has ~25 call sites and the body holds the unrolled multiplications.)
+__device__ __noinline__ Fr eval_ref(const DevCircuit& c, const Fr* W, const LeRef& r) {
   Fr acc = Fr::zero();
-  const uint32_t e = c.le_off[le + 1];
-  for (uint32_t k = c.le_off[le]; k < e; k++) {
-    const uint32_t cid = c.le_coeff[k];
-    const Fr v = ld_w(W + c.le_wire[k]);
-    if (cid == 0) acc = add(acc, v);
-    else if (cid == 1) acc = sub(acc, v);
-    else acc = add(acc, mul(ld_w(c.coeffs + cid), v));
+  constexpr int BATCH = 4;
+  for (uint32_t k0 = 0; k0 < r.n; k0 += BATCH) {
+    Fr v[BATCH];
+    uint32_t cid[BATCH];
+    bool is_const[BATCH];
+#pragma unroll
+    for (int j = 0; j < BATCH; j++)
+      if (k0 + j < r.n) {
+        cid[j] = r.cids[(k0 + j) * r.stride];
+        const uint32_t loc = r.wires[(k0 + j) * r.stride];
+        is_const[j] = loc == 0;  // wire 0 is the constant one: the term's value is the coefficient itself
+        v[j] = is_const[j] ? ld_w(c.coeffs + cid[j]) : ld_term(W, r.ring, loc);
+      }
+#pragma unroll
+    for (int j = 0; j < BATCH; j++)
+      if (k0 + j < r.n) {
+        if (cid[j] == 0 || is_const[j]) acc = add(acc, v[j]);
+        else if (cid[j] == 1) acc = sub(acc, v[j]);
+        else acc = add(acc, mul(ld_w(c.coeffs + cid[j]), v[j]));
+      }
   }
   return acc;
 }
+
+__device__ __forceinline__ LeRef csr_ref(const DevCircuit& c, uint32_t le) {
+  if (le == NO_LE) return {nullptr, nullptr, 0, 1, false, nullptr};
+  const uint32_t s = c.le_off[le];
+  return {c.le_wire + s, c.le_coeff + s, c.le_off[le + 1] - s, 1, true, nullptr};
+}
+
+// where an instruction's outputs go: always HBM, plus the ring on the staged path
+struct OutRef {
+  Fr* W;
+  uint32_t out;
+  Fr* ring;
+  uint32_t slot;
+  __device__ __forceinline__ void put(uint32_t k, const Fr& v) const {
+    st_w(W + out + k, v);
+    if (ring) st_w(ring + ((slot + k) & (RING_SLOTS - 1)), v);
+  }
+};
+
+__device__ __forceinline__ Fr eval_le(const DevCircuit& c, const Fr* W, uint32_t le) { return eval_ref(c, W, csr_ref(c, le)); }
 
 __device__ __forceinline__ void to_u64x4(const Fr& mont, uint64_t x[4]) {
   Fr a = from_mont(mont);
@@ -103,88 +168,167 @@ __device__ __forceinline__ Fr from_u64(uint64_t v) {
 // error codes written to err[proof] (first error wins)
 constexpr int ERR_MULADD = 1, ERR_GLINV = 2, ERR_SPLIT = 3, ERR_BITS = 4, ERR_DECOMP = 5, ERR_DIV0 = 6;
 
-__device__ void exec_instr(const DevCircuit& c, Fr* W, const DInstr& in, int* err, uint32_t* hist) {
-  const uint32_t op = in.op_nout & 0xffu, nout = in.op_nout >> 8;
+__device__ __forceinline__ bool ref_is_const(const LeRef& r) { return r.n == 0 || (r.n == 1 && r.wires[0] == 0); }
+
+__device__ void exec_op(const DevCircuit& c, const Fr* W, uint32_t op_nout, const OutRef& O, const LeRef& A, const LeRef& B,
+                        const LeRef& Cc, const LeRef& D, int* err, uint32_t* hist) {
+  const uint32_t op = op_nout & 0xffu, nout = op_nout >> 8;
   switch (op) {
     case fe::OP_MUL: {
-      Fr r = mul(eval_le(c, W, in.le[0]), eval_le(c, W, in.le[1]));
-      if (in.le[2] != NO_LE) r = add(r, eval_le(c, W, in.le[2]));
-      st_w(W + in.out, r);
+      const Fr a = eval_ref(c, W, A);
+      const bool same = B.wires == A.wires && B.n == A.n;  // x * x (S-boxes): evaluate the operand once
+      Fr r = same ? sqr(a) : mul(a, eval_ref(c, W, B));
+      if (Cc.present) r = add(r, eval_ref(c, W, Cc));
+      O.put(0,r);
       break;
     }
     case fe::OP_HINT_MULADD: {
       uint64_t a[4], b[4], d[4];
-      to_u64x4(eval_le(c, W, in.le[0]), a);
-      to_u64x4(eval_le(c, W, in.le[1]), b);
-      to_u64x4(eval_le(c, W, in.le[2]), d);
+      to_u64x4(eval_ref(c, W, A), a);
+      to_u64x4(eval_ref(c, W, B), b);
+      to_u64x4(eval_ref(c, W, Cc), d);
       if ((a[1] | a[2] | a[3] | b[1] | b[2] | b[3] | d[1] | d[2] | d[3]) || a[0] >= gl::P || b[0] >= gl::P || d[0] >= gl::P) {
         atomicCAS(err, 0, ERR_MULADD);  // goldilocks/base.go:228-232 panics
         return;
       }
       uint64_t q, r;
       gl::mul_add_hint(a[0], b[0], d[0], q, r);
-      st_w(W + in.out, from_u64(q));
-      st_w(W + in.out + 1, from_u64(r));
+      O.put(0,from_u64(q));
+      O.put(1,from_u64(r));
       break;
     }
     case fe::OP_HINT_REDUCE: {
       uint64_t x[4], q[4], r;
-      to_u64x4(eval_le(c, W, in.le[0]), x);
+      to_u64x4(eval_ref(c, W, A), x);
       gl::reduce_hint(x, q, r);
-      st_w(W + in.out, from_u64x4(q));
-      st_w(W + in.out + 1, from_u64(r));
+      O.put(0,from_u64x4(q));
+      O.put(1,from_u64(r));
       break;
     }
     case fe::OP_HINT_GLINV: {
       uint64_t x[4];
-      to_u64x4(eval_le(c, W, in.le[0]), x);
+      to_u64x4(eval_ref(c, W, A), x);
       if ((x[1] | x[2] | x[3]) || x[0] >= gl::P) {
         atomicCAS(err, 0, ERR_GLINV);
         return;
       }
-      st_w(W + in.out, from_u64(gl::inverse(x[0])));
+      O.put(0,from_u64(gl::inverse(x[0])));
       break;
     }
     case fe::OP_HINT_SPLIT: {
       uint64_t x[4];
-      to_u64x4(eval_le(c, W, in.le[0]), x);
+      to_u64x4(eval_ref(c, W, A), x);
       if ((x[1] | x[2] | x[3]) || x[0] >= gl::P) {
         atomicCAS(err, 0, ERR_SPLIT);  // goldilocks/base.go:347-349 returns an error
         return;
       }
-      st_w(W + in.out, from_u64(x[0] >> 32));
-      st_w(W + in.out + 1, from_u64(x[0] & 0xffffffffull));
+      O.put(0,from_u64(x[0] >> 32));
+      O.put(1,from_u64(x[0] & 0xffffffffull));
       break;
     }
-    case fe::OP_INVZERO: st_w(W + in.out, inv(eval_le(c, W, in.le[0]))); break;
+    case fe::OP_INVZERO: O.put(0,inv(eval_ref(c, W, A))); break;
     case fe::OP_BITS: {
       uint64_t x[4];
-      to_u64x4(eval_le(c, W, in.le[0]), x);
+      to_u64x4(eval_ref(c, W, A), x);
       const Fr one = Fr::one(), zero = Fr::zero();
-      for (uint32_t i = 0; i < nout; i++) st_w(W + in.out + i, ((x[i >> 6] >> (i & 63)) & 1ull) ? one : zero);
+      for (uint32_t i = 0; i < nout; i++) O.put(i,((x[i >> 6] >> (i & 63)) & 1ull) ? one : zero);
       for (uint32_t i = nout; i < 256; i++)
         if ((x[i >> 6] >> (i & 63)) & 1ull) atomicCAS(err, 0, ERR_BITS);
       break;
     }
     case fe::OP_DIV: {
-      Fr d = eval_le(c, W, in.le[1]);
+      Fr d = eval_ref(c, W, B);
       if (d.is_zero()) atomicCAS(err, 0, ERR_DIV0);
-      st_w(W + in.out, mul(eval_le(c, W, in.le[0]), inv(d)));
+      O.put(0,mul(eval_ref(c, W, A), inv(d)));
       break;
     }
     case fe::OP_DECOMP: {
       uint64_t x[4];
-      to_u64x4(eval_le(c, W, in.le[0]), x);
+      to_u64x4(eval_ref(c, W, A), x);
       for (uint32_t i = 0; i < nout; i++) {
         uint32_t v = (uint32_t)((x[(16 * i) >> 6] >> ((16 * i) & 63)) & 0xffffull);
-        st_w(W + in.out + i, from_u64(v));
+        O.put(i,from_u64(v));
         atomicAdd(&hist[v], 1u);
       }
       for (uint32_t i = 16 * nout; i < 256; i += 16)
         if ((x[i >> 6] >> (i & 63)) & 0xffffull) atomicCAS(err, 0, ERR_DECOMP);  // value exceeds its range: unsatisfiable
       break;
     }
+    case fe::OP_POSEIDON_BN254: {
+      Fr st[4] = {eval_ref(c, W, A), eval_ref(c, W, B), eval_ref(c, W, Cc), eval_ref(c, W, D)};
+      const bool isc[4] = {ref_is_const(A), ref_is_const(B), ref_is_const(Cc), ref_is_const(D)};
+      Bn254PoseidonTables T{c.bn_tables, c.bn_tables + 88, c.bn_tables + 88 + 392, c.bn_tables + 88 + 392 + 16};
+      uint32_t idx = 0;
+      poseidon_bn254_trace(st, isc, T, [&](const Fr& v) { O.put(idx++, v); });
+      break;
+    }
     default: break;
+  }
+}
+
+__device__ __forceinline__ void exec_instr(const DevCircuit& c, Fr* W, const DInstr& in, int* err, uint32_t* hist) {
+  exec_op(c, W, in.op_nout, OutRef{W, in.out, nullptr, 0}, csr_ref(c, in.le[0]), csr_ref(c, in.le[1]), csr_ref(c, in.le[2]),
+          csr_ref(c, in.le[3]), err, hist);
+}
+
+// ---- staged narrow tape ---------------------------------------------------------------------------------------------
+// The narrow levels are re-encoded as a flat stream of CHUNKS (u32 words), each self-contained:
+//   [0] n_instr   [1] words of the NEXT chunk (0 = last)   [2] 1 if a level ends with this chunk   [3] reserved
+//   [4 .. 4+n_instr) word offset of each instruction record inside the chunk
+//   records: op|nout<<8, out, nA, nB, nC, then (wire, coeff-id) pairs of A, B, C
+// so one contiguous copy brings everything an instruction needs except the wire values themselves. The CTA keeps
+// two chunk buffers in shared memory and prefetches chunk i+1 with cp.async while it executes chunk i: the only
+// exposed global-memory latency per level is the load of the operand wires.
+constexpr uint32_t CHUNK_MAX_WORDS = 6144;  // 24 KB per buffer
+constexpr size_t STAGED_SMEM_BYTES = 2 * CHUNK_MAX_WORDS * 4 + RING_SLOTS * sizeof(Fr);  // 48 KB + 64 KB
+
+__device__ __forceinline__ void cp_async_16(void* smem_dst, const void* gmem_src) {
+  uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gmem_src));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+__global__ void __launch_bounds__(NARROW_THREADS)
+    k_tape_staged(DevCircuit c, const uint32_t* __restrict__ stream, uint32_t first_words, Fr* __restrict__ wires, size_t wire_stride,
+                  int* __restrict__ err, uint32_t* __restrict__ hist) {
+  extern __shared__ __align__(16) uint32_t dyn_smem[];
+  uint32_t(*buf)[CHUNK_MAX_WORDS] = reinterpret_cast<uint32_t(*)[CHUNK_MAX_WORDS]>(dyn_smem);
+  Fr* ring = reinterpret_cast<Fr*>(dyn_smem + 2 * CHUNK_MAX_WORDS);
+  Fr* W = wires + (size_t)blockIdx.x * wire_stride;
+  int* e = err + blockIdx.x;
+  uint32_t* h = hist + (size_t)blockIdx.x * 65536;
+  const uint32_t* src = stream;
+  uint32_t words = first_words;
+  for (uint32_t i = threadIdx.x * 4; i < words; i += blockDim.x * 4) cp_async_16(&buf[0][i], src + i);
+  cp_async_commit();
+  int cur = 0;
+  while (words) {
+    cp_async_wait_all();
+    __syncthreads();  // chunk `cur` is resident; wires written by the previous chunk are visible
+    const uint32_t* ch = buf[cur];
+    const uint32_t n_instr = ch[0], next_words = ch[1];
+    const uint32_t* next_src = src + words;
+    for (uint32_t i = threadIdx.x * 4; i < next_words; i += blockDim.x * 4) cp_async_16(&buf[cur ^ 1][i], next_src + i);
+    cp_async_commit();
+    for (uint32_t i = threadIdx.x; i < n_instr; i += blockDim.x) {
+      const uint32_t* rec = ch + ch[4 + i];
+      const uint32_t nA = rec[2], nB = rec[3], nC = rec[4], nD = rec[6];
+      const uint32_t* t = rec + 7;
+      LeRef A{t, t + 1, nA & 0x7fffffffu, 2, (nA >> 31) != 0, ring};
+      t += 2 * (nA & 0x7fffffffu);
+      LeRef B{t, t + 1, nB & 0x3fffffffu, 2, (nB >> 31) != 0, ring};
+      if (nB & 0x40000000u) B = A;  // encoder: B is the same expression as A, its terms are not repeated
+      else t += 2 * (nB & 0x3fffffffu);
+      LeRef Cc{t, t + 1, nC & 0x7fffffffu, 2, (nC >> 31) != 0, ring};
+      t += 2 * (nC & 0x7fffffffu);
+      LeRef D{t, t + 1, nD & 0x7fffffffu, 2, (nD >> 31) != 0, ring};
+      exec_op(c, W, rec[0], OutRef{W, rec[1], ring, rec[5]}, A, B, Cc, D, e, h);
+    }
+    src = next_src;
+    words = next_words;
+    cur ^= 1;
+    __syncthreads();  // everyone is done reading chunk `cur^1`... (now the old buffer) before it is overwritten
   }
 }
 
@@ -230,6 +374,32 @@ __global__ void k_set_inputs(Fr* __restrict__ wires, size_t wire_stride, const u
   st_w(W + 1 + i, from_u64x4(x));
 }
 
+// one CTA per long linear expression: strided partial sums, then a shared-memory tree
+__global__ void __launch_bounds__(1024) k_eval_long_les(DevCircuit c, const Fr* __restrict__ W) {
+  __shared__ uint4 sm_raw[1024 * 2];
+  Fr* sm = reinterpret_cast<Fr*>(sm_raw);
+  const uint32_t le = c.long_le[blockIdx.x];
+  const uint32_t s = c.le_off[le], e = c.le_off[le + 1];
+  Fr acc = Fr::zero();
+  for (uint32_t k = s + threadIdx.x; k < e; k += blockDim.x) {
+    const uint32_t cid = c.le_coeff[k];
+    const Fr v = ld_w(W + c.le_wire[k]);
+    if (cid == 0) acc = add(acc, v);
+    else if (cid == 1) acc = sub(acc, v);
+    else acc = add(acc, mul(ld_w(c.coeffs + cid), v));
+  }
+  st_w(sm + threadIdx.x, acc);
+  __syncthreads();
+  for (uint32_t d = blockDim.x >> 1; d >= 1; d >>= 1) {
+    if (threadIdx.x < d) {
+      acc = add(acc, ld_w(sm + threadIdx.x + d));
+      st_w(sm + threadIdx.x, acc);
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) st_w(c.long_val + blockIdx.x, acc);
+}
+
 // a = L.w, b = R.w, c = O.w for every constraint (zero-padded to the FFT domain by the caller's memset);
 // counts rows with a*b != c.
 __global__ void __launch_bounds__(128)
@@ -237,7 +407,19 @@ __global__ void __launch_bounds__(128)
                 unsigned long long* __restrict__ n_bad, unsigned long long* __restrict__ first_bad) {
   uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= c.n_cons) return;
-  Fr l = eval_le(c, W, c.cons[3 * k]), r = eval_le(c, W, c.cons[3 * k + 1]), o = eval_le(c, W, c.cons[3 * k + 2]);
+  Fr v[3];
+#pragma unroll 1
+  for (int j = 0; j < 3; j++) {
+    const uint32_t le = c.cons[3 * k + j];
+    bool is_long = false;
+    for (uint32_t q = 0; q < c.n_long; q++)
+      if (c.long_le[q] == le) {
+        v[j] = ld_w(c.long_val + q);
+        is_long = true;
+      }
+    if (!is_long) v[j] = eval_le(c, W, le);
+  }
+  const Fr &l = v[0], &r = v[1], &o = v[2];
   if (a) {
     st_w(a + k, l);
     st_w(b + k, r);
@@ -261,6 +443,8 @@ struct gpw_circuit {
   DevCircuit dc{};
   std::vector<Segment> plan;
   std::vector<void*> dev_allocs;
+  const uint32_t* stream_dev = nullptr;
+  double ring_hit_rate = 0;
   uint32_t n_inputs = 0;
   float solve_ms = 0;
 };
@@ -282,7 +466,7 @@ static int upload(gpw_circuit* c, const std::vector<T>& v, const T** out) {
 
 static int finish_compile(gpw_circuit* c) {
   fe::API& api = c->api;
-  api.ScheduleALAP();
+  api.ScheduleSpineAndTail();
   const auto& tape = api.Tape();
   const uint32_t L = api.NumLevels();
   // sort by (level, op)
@@ -306,7 +490,7 @@ static int finish_compile(gpw_circuit* c) {
       commit_level = in.level;
       continue;
     }
-    di.push_back({(uint32_t)in.op | (in.nout << 8), in.out, {in.le[0], in.le[1], in.le[2]}});
+    di.push_back({(uint32_t)in.op | (in.nout << 8), in.out, {in.le[0], in.le[1], in.le[2], in.le3}});
     level_off[in.level + 1]++;
   }
   for (uint32_t l = 0; l < L; l++) level_off[l + 1] += level_off[l];
@@ -328,6 +512,137 @@ static int finish_compile(gpw_circuit* c) {
     }
   }
   flush(L);
+  // staged stream for the narrow segments (see k_tape_staged)
+  {
+    const auto& off = api.LeOffsets();
+    const auto& lw = api.LeWires();
+    const auto& lc = api.LeCoeffIds();
+    std::vector<uint32_t> stream;
+    auto le_words = [&](uint32_t le) -> uint32_t { return le == NO_LE ? 0 : 2 * (off[le + 1] - off[le]); };
+    const bool dbg = getenv("GPW_DEBUG_TAPE") != nullptr;
+    uint64_t dbg_thread[16][3] = {}, dbg_warp[3] = {0, 0, 0}, dbg_warps = 0, dbg_chunks = 0;
+    std::vector<uint8_t> coeff_small(api.Coeffs().size(), 0);
+    for (size_t ci = 0; ci < api.Coeffs().size(); ci++) {
+      uint64_t l4[4];
+      fe::fr_to_limbs(api.Coeffs()[ci], l4);
+      coeff_small[ci] = (l4[1] | l4[2] | l4[3]) == 0;
+    }
+    std::vector<uint64_t> wire_seq(api.NumWires(), 0);
+    std::vector<uint32_t> wire_seg(api.NumWires(), 0xffffffffu);
+    uint64_t ring_seq = 0, ring_hits = 0, ring_total = 0;
+    uint32_t seg_id = 0;
+    for (auto& seg : c->plan) {
+      if (seg.kind != SEG_NARROW) continue;
+      seg_id++;
+      seg.stream_off = (uint32_t)stream.size();
+      seg.first_words = 0;
+      size_t prev_hdr = (size_t)-1;
+      for (uint32_t l = seg.lo; l < seg.hi; l++) {
+        uint32_t i = level_off[l];
+        const uint32_t end = level_off[l + 1];
+        while (i < end) {
+          // greedily take instructions [i, j) that fit one chunk
+          uint32_t j = i, words = 4;
+          while (j < end) {
+            uint32_t rec = 7 + le_words(di[j].le[0]) + le_words(di[j].le[1]) + le_words(di[j].le[2]) + le_words(di[j].le[3]);
+            if ((di[j].op_nout >> 8) >= RING_SLOTS) {
+              set_error("tape instruction with %u outputs exceeds the ring", di[j].op_nout >> 8);
+              return GPW_EINVAL;
+            }
+            if (rec + 5 > CHUNK_MAX_WORDS) {
+              set_error("tape instruction too large for a staged chunk (%u words)", rec);
+              return GPW_EINVAL;
+            }
+            if (words + 1 + rec > CHUNK_MAX_WORDS - 4) break;
+            words += 1 + rec;
+            j++;
+          }
+          const size_t base = stream.size();
+          const uint32_t n = j - i;
+          stream.resize(base + 4 + n, 0);
+          stream[base] = n;
+          stream[base + 2] = (j == end) ? 1u : 0u;
+          // ring bookkeeping: every wire produced on the spine gets the next slot of the shared-memory ring; a later
+          // operand reads the ring instead of HBM if its slot cannot have been overwritten before the END of the
+          // consuming chunk (the chunk's own outputs are written concurrently with its reads)
+          uint64_t seq_end = ring_seq;
+          for (uint32_t k = i; k < j; k++) seq_end += di[k].op_nout >> 8;
+          if (dbg) {  // warp-level cost model: lanes of a warp run in lock step, the slowest lane sets the pace
+            for (uint32_t w0 = i; w0 < j; w0 += 32) {
+              uint32_t worst[3] = {0, 0, 0};
+              for (uint32_t k = w0; k < std::min(j, w0 + 32); k++) {
+                uint32_t cnt[3] = {0, 0, 0};
+                for (int t = 0; t < 4; t++) {
+                  uint32_t le = di[k].le[t];
+                  if (le == NO_LE) continue;
+                  for (uint32_t q = off[le]; q < off[le + 1]; q++) {
+                    if (lc[q] <= 1) continue;
+                    cnt[lw[q] == 0 ? 0 : (coeff_small[lc[q]] ? 1 : 2)]++;
+                  }
+                }
+                for (int t = 0; t < 3; t++) worst[t] = std::max(worst[t], cnt[t]);
+                dbg_thread[di[k].op_nout & 0xff][0] += cnt[0];
+                dbg_thread[di[k].op_nout & 0xff][1] += cnt[1];
+                dbg_thread[di[k].op_nout & 0xff][2] += cnt[2];
+              }
+              for (int t = 0; t < 3; t++) dbg_warp[t] += worst[t];
+              dbg_warps++;
+            }
+            dbg_chunks++;
+          }
+          for (uint32_t k = i; k < j; k++) {
+            stream[base + 4 + (k - i)] = (uint32_t)(stream.size() - base);
+            const DInstr& in = di[k];
+            stream.push_back(in.op_nout);
+            stream.push_back(in.out);
+            const bool same_ab = (in.op_nout & 0xff) == fe::OP_MUL && in.le[1] != NO_LE && in.le[1] == in.le[0];
+            for (int t = 0; t < 3; t++) {
+              uint32_t le = in.le[t];
+              if (t == 1 && same_ab) stream.push_back(0xC0000000u);
+              else stream.push_back(le == NO_LE ? 0u : ((off[le + 1] - off[le]) | 0x80000000u));
+            }
+            stream.push_back((uint32_t)(ring_seq % RING_SLOTS));
+            stream.push_back(in.le[3] == NO_LE ? 0u : ((off[in.le[3] + 1] - off[in.le[3]]) | 0x80000000u));
+            for (uint32_t o = 0; o < (in.op_nout >> 8); o++) {
+              wire_seq[in.out + o] = ring_seq++;
+              wire_seg[in.out + o] = seg_id;
+            }
+            for (int t = 0; t < 4; t++) {
+              uint32_t le = in.le[t];
+              if (le == NO_LE || (t == 1 && same_ab)) continue;
+              for (uint32_t q = off[le]; q < off[le + 1]; q++) {
+                const uint32_t w = lw[q];
+                const bool in_ring = wire_seg[w] == seg_id && seq_end - wire_seq[w] <= RING_SLOTS;
+                stream.push_back(in_ring ? (RING_FLAG | (uint32_t)(wire_seq[w] % RING_SLOTS)) : w);
+                stream.push_back(lc[q]);
+                ring_hits += in_ring;
+                ring_total++;
+              }
+            }
+          }
+          while ((stream.size() - base) % 4) stream.push_back(0);
+          const uint32_t cw = (uint32_t)(stream.size() - base);
+          if (prev_hdr == (size_t)-1) seg.first_words = cw;
+          else stream[prev_hdr + 1] = cw;
+          prev_hdr = base;
+          i = j;
+        }
+      }
+    }
+    stream.resize(stream.size() + 8, 0);
+    c->ring_hit_rate = ring_total ? (double)ring_hits / (double)ring_total : 0.0;
+    if (dbg) {
+      fprintf(stderr, "[gpw tape] narrow stream: %llu chunks, %llu warp-passes, ring hit rate %.3f\n",
+              (unsigned long long)dbg_chunks, (unsigned long long)dbg_warps, c->ring_hit_rate);
+      fprintf(stderr, "[gpw tape] warp-level coefficient muls: const(wire0) %llu, small %llu, full %llu\n",
+              (unsigned long long)dbg_warp[0], (unsigned long long)dbg_warp[1], (unsigned long long)dbg_warp[2]);
+      for (int op = 0; op < 9; op++)
+        fprintf(stderr, "[gpw tape] op %d thread-level coefficient terms: const %llu small %llu full %llu\n", op,
+                (unsigned long long)dbg_thread[op][0], (unsigned long long)dbg_thread[op][1], (unsigned long long)dbg_thread[op][2]);
+    }
+    GPW_TRY(upload(c, stream, &c->stream_dev));
+    GPW_CUDA(cudaFuncSetAttribute(k_tape_staged, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)STAGED_SMEM_BYTES));
+  }
   DevCircuit& dc = c->dc;
   GPW_TRY(upload(c, di, &dc.instr));
   GPW_TRY(upload(c, level_off, &dc.level_off));
@@ -343,6 +658,32 @@ static int finish_compile(gpw_circuit* c) {
   dc.n_limbs = api.NumLimbWires();
   dc.count_start = api.CountWireStart();
   dc.commit_wire = api.CommitWire();
+  {
+    std::vector<Fr> tb(88 + 392 + 16 + 16);
+    memcpy(tb.data(), GPW_BN_C_MONT, 88 * 32);
+    memcpy(tb.data() + 88, GPW_BN_S_MONT, 392 * 32);
+    memcpy(tb.data() + 88 + 392, GPW_BN_M_MONT, 16 * 32);
+    memcpy(tb.data() + 88 + 392 + 16, GPW_BN_P_MONT, 16 * 32);
+    GPW_TRY(upload(c, tb, &dc.bn_tables));
+  }
+  dc.n_long = 0;
+  {
+    std::vector<uint8_t> used(api.LeOffsets().size(), 0);
+    for (uint32_t le : api.Constraints()) used[le] = 1;
+    const auto& off = api.LeOffsets();
+    for (uint32_t le = 0; le + 1 < off.size(); le++)
+      if (used[le] && off[le + 1] - off[le] > LONG_LE_TERMS) {
+        if (dc.n_long >= 8) {
+          set_error("circuit has more than 8 very long linear expressions");
+          return GPW_EINVAL;
+        }
+        dc.long_le[dc.n_long++] = le;
+      }
+    std::vector<Fr> zeros(8, Fr::zero());
+    const Fr* lv;
+    GPW_TRY(upload(c, zeros, &lv));
+    dc.long_val = const_cast<Fr*>(lv);
+  }
   c->n_inputs = api.NumPublic() + api.NumSecret();
   return GPW_OK;
 }
@@ -417,7 +758,13 @@ static int run_segments(gpw_circuit* c, Fr* wires, size_t stride, int n_proofs, 
   for (size_t si = seg_lo; si < seg_hi; si++) {
     const Segment& s = c->plan[si];
     if (s.kind == SEG_NARROW) {
-      k_tape_narrow<<<n_proofs, NARROW_THREADS, 0, st>>>(c->dc, wires, stride, err, hist, s.lo, s.hi);
+      if (!s.first_words) continue;
+      if (getenv("GPW_SOLVER_UNSTAGED")) {  // debugging aid: the simple per-level walker over the CSR arrays
+        k_tape_narrow<<<n_proofs, NARROW_THREADS, 0, st>>>(c->dc, wires, stride, err, hist, s.lo, s.hi);
+      } else {
+        k_tape_staged<<<n_proofs, NARROW_THREADS, STAGED_SMEM_BYTES, st>>>(c->dc, c->stream_dev + s.stream_off, s.first_words, wires, stride, err,
+                                                           hist);
+      }
       GPW_CHECK_LAUNCH();
       ctx->launches++;
     } else if (s.kind == SEG_WIDE) {
@@ -452,7 +799,9 @@ static int check_err(gpw_circuit* c, int* err_dev, int n_proofs) {
   for (int i = 0; i < n_proofs; i++)
     if (e[i]) {
       set_error("witness solve failed for proof %d: %s", i, err_name(e[i]));
-      return GPW_EHINT;
+      // a hint refusing its input mirrors the reference's panic / error return; a value that does not fit its
+      // decomposition means the constraint system is unsatisfiable for this assignment
+      return (e[i] == ERR_BITS || e[i] == ERR_DECOMP || e[i] == ERR_DIV0) ? GPW_EUNSAT : GPW_EHINT;
     }
   return GPW_OK;
 }
@@ -523,6 +872,11 @@ extern "C" int gpw_r1cs_eval_dev(gpw_circuit* c, uint64_t wires_dev, uint64_t a_
   unsigned long long init[2] = {0, ~0ull};
   GPW_CUDA(cudaMemcpyAsync(bad, init, 16, cudaMemcpyHostToDevice, ctx->stream));
   GPW_CUDA(cudaStreamSynchronize(ctx->stream));
+  if (c->dc.n_long) {
+    k_eval_long_les<<<c->dc.n_long, 1024, 0, ctx->stream>>>(c->dc, (const Fr*)wires_dev);
+    GPW_CHECK_LAUNCH();
+    ctx->launches++;
+  }
   k_r1cs_eval<<<div_up(c->dc.n_cons, 128), 128, 0, ctx->stream>>>(c->dc, (const Fr*)wires_dev, (Fr*)a_dev, (Fr*)b_dev, (Fr*)c_dev, bad,
                                                                   bad + 1);
   GPW_CHECK_LAUNCH();

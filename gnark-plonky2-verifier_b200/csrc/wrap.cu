@@ -278,9 +278,24 @@ static void ser_g1_be(const G1Affine& p, uint8_t out[64]) {
 // out_proof (u64 x 64): Ar (8) | Bs (16) | Krs (8) | commitment D (8) | commitment PoK (8) | challenge (4, canonical) |
 //                       n_unsatisfied (1) | reserved.  If check != 0 the R1CS is verified on the device (a*b == c on every
 // row) and GPW_EUNSAT is returned on failure.
+extern "C" int gpw_wrap_prove_dev(gpw_wrap_key* k, uint64_t inputs_dev, const uint64_t* r_canon, const uint64_t* s_canon, int check,
+                                  uint64_t* out_proof);
+
 extern "C" int gpw_wrap_prove(gpw_wrap_key* k, const uint64_t* inputs, const uint64_t* r_canon, const uint64_t* s_canon, int check,
                               uint64_t* out_proof) {
-  if (!k || !inputs || !r_canon || !s_canon || !out_proof) {
+  if (!k || !inputs) {
+    set_error("wrap_prove: null argument");
+    return GPW_EINVAL;
+  }
+  GPW_CUDA(cudaSetDevice(k->ctx->device));
+  GPW_CUDA(cudaMemcpyAsync(k->inputs_dev, inputs, (size_t)k->n_inputs * 32, cudaMemcpyHostToDevice, k->ctx->stream));
+  return gpw_wrap_prove_dev(k, (uint64_t)k->inputs_dev, r_canon, s_canon, check, out_proof);
+}
+
+// Same with the parsed inputs already resident on the device (n_inputs x 4 u64 canonical).
+extern "C" int gpw_wrap_prove_dev(gpw_wrap_key* k, uint64_t inputs_dev, const uint64_t* r_canon, const uint64_t* s_canon, int check,
+                                  uint64_t* out_proof) {
+  if (!k || !inputs_dev || !r_canon || !s_canon || !out_proof) {
     set_error("wrap_prove: null argument");
     return GPW_EINVAL;
   }
@@ -292,8 +307,7 @@ extern "C" int gpw_wrap_prove(gpw_wrap_key* k, const uint64_t* inputs, const uin
   for (auto& e : ev) GPW_CUDA(cudaEventCreate(&e));
   memset(out_proof, 0, 64 * 8);
   GPW_CUDA(cudaEventRecord(ev[0], st));
-  GPW_CUDA(cudaMemcpyAsync(k->inputs_dev, inputs, (size_t)k->n_inputs * 32, cudaMemcpyHostToDevice, st));
-  GPW_TRY(gpw_witness_solve_phase1_dev(k->circ, (uint64_t)k->inputs_dev, 1, (uint64_t)k->wires, k->m));
+  GPW_TRY(gpw_witness_solve_phase1_dev(k->circ, inputs_dev, 1, (uint64_t)k->wires, k->m));
   GPW_CUDA(cudaEventRecord(ev[1], st));
   // commitment to the committed wires (range-check limbs + multiplicities) and its proof of knowledge
   G1Affine D{Fp::zero(), Fp::zero()}, PoK{Fp::zero(), Fp::zero()};

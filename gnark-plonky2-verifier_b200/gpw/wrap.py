@@ -29,6 +29,8 @@ _NEW = {
     "gpw_wrap_key_info": (C.c_int, [_vp, _vp]),
     "gpw_wrap_key_wires_dev": (C.c_uint64, [_vp]),
     "gpw_wrap_prove": (C.c_int, [_vp, _vp, _vp, _vp, C.c_int, _vp]),
+    "gpw_wrap_prove_dev": (C.c_int, [_vp, C.c_uint64, _vp, _vp, C.c_int, _vp]),
+    "gpw_msm_cumulative_stats": (C.c_int, [_vp, C.c_int, C.c_int, _vp]),
     "gpw_wrap_last_stats": (C.c_int, [_vp, _vp]),
     "gpw_hash_to_fr": (C.c_int, [C.c_char_p, C.c_size_t, C.c_char_p, _vp]),
 }
@@ -149,6 +151,28 @@ class WrapKey:
         return {"Ar": out[0:8].copy(), "Bs": out[8:24].copy(), "Krs": out[24:32].copy(), "commitment": out[32:40].copy(),
                 "pok": out[40:48].copy(), "challenge": sum(int(out[48 + i]) << (64 * i) for i in range(4)),
                 "n_unsatisfied": int(out[52]), "raw": out}
+
+    def _unpack(self, out):
+        return {"Ar": out[0:8].copy(), "Bs": out[8:24].copy(), "Krs": out[24:32].copy(), "commitment": out[32:40].copy(),
+                "pok": out[40:48].copy(), "challenge": sum(int(out[48 + i]) << (64 * i) for i in range(4)),
+                "n_unsatisfied": int(out[52]), "raw": out}
+
+    def prove_ptr(self, inputs_ptr, r_int, s_int, check=True, on_device=False):
+        """inputs_ptr: address of the (n_inputs, 4) u64 canonical input block - pinned host memory, or device memory
+        when on_device=True."""
+        r = ints_to_limbs([r_int])[0]
+        s = ints_to_limbs([s_int])[0]
+        out = np.zeros(64, dtype=np.uint64)
+        if on_device:
+            _check(_lib.gpw_wrap_prove_dev(self._h, inputs_ptr, _p(r), _p(s), int(check), _p(out)))
+        else:
+            _check(_lib.gpw_wrap_prove(self._h, _vp(inputs_ptr), _p(r), _p(s), int(check), _p(out)))
+        return self._unpack(out)
+
+    def msm_cumulative_stats(self, group, reset=False):
+        out = np.zeros(5, dtype=np.float64)
+        _check(_lib.gpw_msm_cumulative_stats(self.ctx._h, group, int(reset), _p(out)))
+        return dict(zip(("accumulate_ms", "total_ms", "points", "digits", "calls"), map(float, out)))
 
     def last_stats(self):
         ms = (C.c_float * 6)()

@@ -86,6 +86,9 @@ int gpw_msm_g2_dev(gpw_ctx* ctx, uint64_t scalars_dev, uint64_t points_dev, size
 /* Time (ms, CUDA events on the ctx stream) spent in the bucket-accumulation kernel of the most
  * recent MSM on this ctx, and the number of non-zero digits it processed. */
 int gpw_msm_last_stats(gpw_ctx* ctx, float* accumulate_ms, float* total_ms, uint64_t* nonzero_digits);
+/* Cumulative per-group (1 = G1, 2 = G2) statistics since the last reset: {accumulate ms, whole-MSM ms, points,
+ * non-zero digits, calls}; the figures bench.py derives roofline.achieved from. */
+int gpw_msm_cumulative_stats(gpw_ctx* ctx, int group, int reset, double* out5);
 
 /* ---- K8: radix-2 NTT over BN254 Fr ------------------------------------------------------------
  * Replaces gnark-crypto fr/fft Domain.FFT / FFTInverse (+ OnCoset) as used by groth16 computeH.
@@ -165,6 +168,9 @@ int gpw_wrap_key_info(const gpw_wrap_key* k, uint64_t* info8);
 uint64_t gpw_wrap_key_wires_dev(const gpw_wrap_key* k);
 int gpw_wrap_prove(gpw_wrap_key* k, const uint64_t* inputs, const uint64_t* r_canonical, const uint64_t* s_canonical, int check,
                    uint64_t* out_proof);
+/* same, with the parsed inputs already resident on the device (n_inputs x 4 u64 canonical) */
+int gpw_wrap_prove_dev(gpw_wrap_key* k, uint64_t inputs_dev, const uint64_t* r_canonical, const uint64_t* s_canonical, int check,
+                       uint64_t* out_proof);
 int gpw_wrap_last_stats(const gpw_wrap_key* k, float* ms6);
 int gpw_hash_to_fr(const uint8_t* msg, size_t len, const char* dst, uint64_t* out_canonical);
 

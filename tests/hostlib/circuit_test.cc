@@ -12,6 +12,8 @@
 #include "../../gnark-plonky2-verifier_b200/csrc/gl.cuh"
 #include "../../gnark-plonky2-verifier_b200/csrc/host/frontend.h"
 #include "../../gnark-plonky2-verifier_b200/csrc/host/gadgets.h"
+#include "../../gnark-plonky2-verifier_b200/csrc/poseidon_bn254_macro.cuh"
+#include "../../gnark-plonky2-verifier_b200/csrc/poseidon_constants.inc"
 
 using namespace gpw;
 using namespace gpw::fe;
@@ -112,6 +114,7 @@ void* ct_compile_small(int kind) {
 }
 
 void ct_schedule_alap(void* h) { ((Circuit*)h)->api.ScheduleALAP(); }
+void ct_schedule_spine_tail(void* h) { ((Circuit*)h)->api.ScheduleSpineAndTail(); }
 
 void ct_free(void* h) { delete (Circuit*)h; }
 
@@ -231,6 +234,24 @@ int ct_solve_inputs(void* h, const uint64_t* pub, size_t npub, const uint64_t* s
         break;
       }
       case OP_COMMIT: c->w[in.out] = fr_from_limbs(x_commit); break;
+      case OP_POSEIDON_BN254: {
+        const uint32_t les[4] = {in.le[0], in.le[1], in.le[2], in.le3};
+        const auto& off = api.LeOffsets();
+        const auto& wi = api.LeWires();
+        Fr st[4];
+        bool isc[4];
+        for (int k = 0; k < 4; k++) {
+          st[k] = eval_le(*c, les[k]);
+          uint32_t n = off[les[k] + 1] - off[les[k]];
+          isc[k] = n == 0 || (n == 1 && wi[off[les[k]]] == 0);
+        }
+        Bn254PoseidonTables T{reinterpret_cast<const Fr*>(GPW_BN_C_MONT), reinterpret_cast<const Fr*>(GPW_BN_S_MONT),
+                              reinterpret_cast<const Fr*>(GPW_BN_M_MONT), reinterpret_cast<const Fr*>(GPW_BN_P_MONT)};
+        uint32_t idx = 0;
+        poseidon_bn254_trace(st, isc, T, [&](const Fr& v) { c->w[in.out + idx++] = v; });
+        if (idx != in.nout) { g_err = "poseidon macro emitted a different number of wires than the builder created"; return -1; }
+        break;
+      }
       default: g_err = "unknown opcode"; return -1;
     }
   }
