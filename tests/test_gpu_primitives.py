@@ -318,3 +318,16 @@ def test_ntt_large_roundtrip_and_linearity(ctx):
     ks = [0, 1, 2, 12345, n // 2, n - 1]
     got = gpw.limbs_to_ints(gpw.host_ff_from_mont(0, spec[ks]))
     assert got == [pow(w, k, ob.R) for k in ks]
+
+
+def test_sharded_msm_nccl_two_gpus():
+    # multi-GPU window split over NCCL (needs >= 2 GPUs on the box; the CPU logic is covered by the gloo test)
+    import subprocess, sys, torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                          "--master-addr", "127.0.0.1", "--master-port", "29517", os.path.join(root, "tools", "sharded_msm_check.py"), "16"],
+                         capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert out.stdout.count("bit-identical") == 2
