@@ -445,6 +445,11 @@ struct gpw_circuit {
   std::vector<void*> dev_allocs;
   const uint32_t* stream_dev = nullptr;
   double ring_hit_rate = 0;
+  // pipelined proving: solves may be issued on a second stream with their own scratch slot (see wrap.cu)
+  cudaStream_t stream_override = nullptr;
+  int slot = 0;
+  cudaStream_t stream() const { return stream_override ? stream_override : ctx->stream; }
+  std::string scratch_name(const char* base) const { return std::string(base) + "." + std::to_string(slot); }
   uint32_t n_inputs = 0;
   float solve_ms = 0;
 };
@@ -754,7 +759,7 @@ static const char* err_name(int e) {
 static int run_segments(gpw_circuit* c, Fr* wires, size_t stride, int n_proofs, int* err, uint32_t* hist, size_t seg_lo,
                         size_t seg_hi) {
   gpw_ctx* ctx = c->ctx;
-  cudaStream_t st = ctx->stream;
+  cudaStream_t st = c->stream();
   for (size_t si = seg_lo; si < seg_hi; si++) {
     const Segment& s = c->plan[si];
     if (s.kind == SEG_NARROW) {
@@ -794,8 +799,8 @@ static size_t commit_segment(const gpw_circuit* c) {
 
 static int check_err(gpw_circuit* c, int* err_dev, int n_proofs) {
   std::vector<int> e(n_proofs);
-  GPW_CUDA(cudaMemcpyAsync(e.data(), err_dev, n_proofs * sizeof(int), cudaMemcpyDeviceToHost, c->ctx->stream));
-  GPW_CUDA(cudaStreamSynchronize(c->ctx->stream));
+  GPW_CUDA(cudaMemcpyAsync(e.data(), err_dev, n_proofs * sizeof(int), cudaMemcpyDeviceToHost, c->stream()));
+  GPW_CUDA(cudaStreamSynchronize(c->stream()));
   for (int i = 0; i < n_proofs; i++)
     if (e[i]) {
       set_error("witness solve failed for proof %d: %s", i, err_name(e[i]));
@@ -808,7 +813,9 @@ static int check_err(gpw_circuit* c, int* err_dev, int n_proofs) {
 
 // Phase 1: everything up to (not including) the commitment challenge. inputs_dev: n_proofs x n_inputs x 4 u64
 // canonical (public then secret). wires_dev: n_proofs x wire_stride Fr.
-extern "C" int gpw_witness_solve_phase1_dev(gpw_circuit* c, uint64_t inputs_dev, int n_proofs, uint64_t wires_dev, size_t wire_stride) {
+// launch part (asynchronous on the circuit's current stream); gpw_witness_solve_phase1_finish collects the status
+extern "C" int gpw_witness_solve_phase1_launch_dev(gpw_circuit* c, uint64_t inputs_dev, int n_proofs, uint64_t wires_dev,
+                                                   size_t wire_stride) {
   if (!c || !inputs_dev || !wires_dev || n_proofs < 1 || wire_stride < c->dc.n_wires) {
     set_error("witness_solve: bad argument");
     return GPW_EINVAL;
@@ -817,16 +824,35 @@ extern "C" int gpw_witness_solve_phase1_dev(gpw_circuit* c, uint64_t inputs_dev,
   GPW_CUDA(cudaSetDevice(ctx->device));
   int* err;
   uint32_t* hist;
-  GPW_TRY(ctx->get_scratch("solve.err", (size_t)n_proofs * sizeof(int), (void**)&err));
-  GPW_TRY(ctx->get_scratch("solve.hist", (size_t)n_proofs * 65536 * 4, (void**)&hist));
-  GPW_CUDA(cudaMemsetAsync(err, 0, (size_t)n_proofs * sizeof(int), ctx->stream));
-  GPW_CUDA(cudaMemsetAsync(hist, 0, (size_t)n_proofs * 65536 * 4, ctx->stream));
+  GPW_TRY(ctx->get_scratch(c->scratch_name("solve.err").c_str(), (size_t)n_proofs * sizeof(int), (void**)&err));
+  GPW_TRY(ctx->get_scratch(c->scratch_name("solve.hist").c_str(), (size_t)n_proofs * 65536 * 4, (void**)&hist));
+  GPW_CUDA(cudaMemsetAsync(err, 0, (size_t)n_proofs * sizeof(int), c->stream()));
+  GPW_CUDA(cudaMemsetAsync(hist, 0, (size_t)n_proofs * 65536 * 4, c->stream()));
   dim3 grid(div_up(std::max<uint32_t>(c->n_inputs, 1), 256), n_proofs);
-  k_set_inputs<<<grid, 256, 0, ctx->stream>>>((Fr*)wires_dev, wire_stride, (const uint64_t*)inputs_dev, c->n_inputs);
+  k_set_inputs<<<grid, 256, 0, c->stream()>>>((Fr*)wires_dev, wire_stride, (const uint64_t*)inputs_dev, c->n_inputs);
   GPW_CHECK_LAUNCH();
   ctx->launches++;
-  GPW_TRY(run_segments(c, (Fr*)wires_dev, wire_stride, n_proofs, err, hist, 0, commit_segment(c)));
+  return run_segments(c, (Fr*)wires_dev, wire_stride, n_proofs, err, hist, 0, commit_segment(c));
+}
+
+extern "C" int gpw_witness_solve_phase1_finish(gpw_circuit* c, int n_proofs) {
+  if (!c || n_proofs < 1) return GPW_EINVAL;
+  int* err;
+  GPW_TRY(c->ctx->get_scratch(c->scratch_name("solve.err").c_str(), (size_t)n_proofs * sizeof(int), (void**)&err));
   return check_err(c, err, n_proofs);
+}
+
+extern "C" int gpw_witness_solve_phase1_dev(gpw_circuit* c, uint64_t inputs_dev, int n_proofs, uint64_t wires_dev, size_t wire_stride) {
+  GPW_TRY(gpw_witness_solve_phase1_launch_dev(c, inputs_dev, n_proofs, wires_dev, wire_stride));
+  return gpw_witness_solve_phase1_finish(c, n_proofs);
+}
+
+// Selects the stream (0 = the context's) and scratch slot used by subsequent solve calls on this circuit.
+extern "C" int gpw_circuit_set_stream_slot(gpw_circuit* c, void* cuda_stream, int slot) {
+  if (!c || slot < 0 || slot > 7) return GPW_EINVAL;
+  c->stream_override = (cudaStream_t)cuda_stream;
+  c->slot = slot;
+  return GPW_OK;
 }
 
 // Phase 2: sets the commitment challenge (one canonical Fr per proof) and runs the rest of the tape.
@@ -846,13 +872,13 @@ extern "C" int gpw_witness_solve_phase2_dev(gpw_circuit* c, const uint64_t* chal
   }
   int* err;
   uint32_t* hist;
-  GPW_TRY(ctx->get_scratch("solve.err", (size_t)n_proofs * sizeof(int), (void**)&err));
-  GPW_TRY(ctx->get_scratch("solve.hist", (size_t)n_proofs * 65536 * 4, (void**)&hist));
+  GPW_TRY(ctx->get_scratch(c->scratch_name("solve.err").c_str(), (size_t)n_proofs * sizeof(int), (void**)&err));
+  GPW_TRY(ctx->get_scratch(c->scratch_name("solve.hist").c_str(), (size_t)n_proofs * 65536 * 4, (void**)&hist));
   for (int p = 0; p < n_proofs; p++) {
     Fr x = fe::fr_from_limbs(challenges_canonical + 4 * p);
     GPW_CUDA(cudaMemcpyAsync((Fr*)wires_dev + (size_t)p * wire_stride + c->dc.commit_wire, &x, sizeof(Fr), cudaMemcpyHostToDevice,
-                             ctx->stream));
-    GPW_CUDA(cudaStreamSynchronize(ctx->stream));  // x lives on the host stack
+                             c->stream()));
+    GPW_CUDA(cudaStreamSynchronize(c->stream()));  // x lives on the host stack
   }
   GPW_TRY(run_segments(c, (Fr*)wires_dev, wire_stride, n_proofs, err, hist, cs + 1, c->plan.size()));
   return check_err(c, err, n_proofs);

@@ -20,6 +20,9 @@ int gpw_witness_solve_phase1_dev(gpw_circuit* c, uint64_t inputs_dev, int n_proo
 int gpw_witness_solve_phase2_dev(gpw_circuit* c, const uint64_t* ch, int n_proofs, uint64_t wires_dev, size_t wire_stride);
 int gpw_r1cs_eval_dev(gpw_circuit* c, uint64_t wires_dev, uint64_t a_dev, uint64_t b_dev, uint64_t c_dev, uint64_t* n_unsat);
 int gpw_circuit_supports(const gpw_circuit* c, int side, uint32_t* out, size_t cap, size_t* n);
+int gpw_witness_solve_phase1_launch_dev(gpw_circuit* c, uint64_t inputs_dev, int n_proofs, uint64_t wires_dev, size_t wire_stride);
+int gpw_witness_solve_phase1_finish(gpw_circuit* c, int n_proofs);
+int gpw_circuit_set_stream_slot(gpw_circuit* c, void* cuda_stream, int slot);
 }
 
 namespace gpw {
@@ -165,6 +168,10 @@ struct gpw_wrap_key {
   Fr *wires = nullptr, *va = nullptr, *vb = nullptr, *vc = nullptr, *gathA = nullptr, *gathB = nullptr;
   uint64_t* inputs_dev = nullptr;
   uint32_t n_inputs = 0;
+  // second proof slot + side stream for pipelined proving (gpw_wrap_prove_many)
+  Fr* wires2 = nullptr;
+  uint64_t* inputs_dev2 = nullptr;
+  cudaStream_t side = nullptr;
   uint64_t seed = 0;
   float t_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 };
@@ -184,6 +191,9 @@ extern "C" void gpw_wrap_key_free(gpw_wrap_key* k) {
   void* ps[] = {k->suppA, k->suppB, k->A, k->B1, k->K, k->Z, k->CK, k->CKs, k->B2, k->wires, k->va, k->vb, k->vc, k->gathA, k->gathB,
                 k->inputs_dev};
   for (void* p : ps) cudaFree(p);
+  cudaFree(k->wires2);
+  cudaFree(k->inputs_dev2);
+  if (k->side) cudaStreamDestroy(k->side);
   delete k;
 }
 
@@ -280,6 +290,7 @@ static void ser_g1_be(const G1Affine& p, uint8_t out[64]) {
 // row) and GPW_EUNSAT is returned on failure.
 extern "C" int gpw_wrap_prove_dev(gpw_wrap_key* k, uint64_t inputs_dev, const uint64_t* r_canon, const uint64_t* s_canon, int check,
                                   uint64_t* out_proof);
+static int wrap_stage2(gpw_wrap_key* k, Fr* wires, const uint64_t* r_canon, const uint64_t* s_canon, int check, uint64_t* out_proof);
 
 extern "C" int gpw_wrap_prove(gpw_wrap_key* k, const uint64_t* inputs, const uint64_t* r_canon, const uint64_t* s_canon, int check,
                               uint64_t* out_proof) {
@@ -303,17 +314,39 @@ extern "C" int gpw_wrap_prove_dev(gpw_wrap_key* k, uint64_t inputs_dev, const ui
   GPW_CUDA(cudaSetDevice(ctx->device));
   cudaStream_t st = ctx->stream;
   const size_t N = (size_t)1 << k->logN;
+  cudaEvent_t e0, e1;
+  GPW_CUDA(cudaEventCreate(&e0));
+  GPW_CUDA(cudaEventCreate(&e1));
+  GPW_CUDA(cudaEventRecord(e0, st));
+  GPW_TRY(gpw_witness_solve_phase1_dev(k->circ, inputs_dev, 1, (uint64_t)k->wires, k->m));
+  GPW_CUDA(cudaEventRecord(e1, st));
+  GPW_CUDA(cudaEventSynchronize(e1));
+  float t1 = 0;
+  GPW_CUDA(cudaEventElapsedTime(&t1, e0, e1));
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  int rc = wrap_stage2(k, k->wires, r_canon, s_canon, check, out_proof);
+  k->t_ms[0] = t1;
+  (void)N;
+  return rc;
+}
+
+// Everything after the first solve phase, on the context's stream: commitment, second solve phase, R1CS evaluation,
+// computeH, MSMs, assembly. `wires` = the proof's wire vector (phase 1 complete).
+static int wrap_stage2(gpw_wrap_key* k, Fr* wires, const uint64_t* r_canon, const uint64_t* s_canon, int check, uint64_t* out_proof) {
+  gpw_ctx* ctx = k->ctx;
+  cudaStream_t st = ctx->stream;
+  const size_t N = (size_t)1 << k->logN;
   cudaEvent_t ev[7];
   for (auto& e : ev) GPW_CUDA(cudaEventCreate(&e));
   memset(out_proof, 0, 64 * 8);
   GPW_CUDA(cudaEventRecord(ev[0], st));
-  GPW_TRY(gpw_witness_solve_phase1_dev(k->circ, inputs_dev, 1, (uint64_t)k->wires, k->m));
   GPW_CUDA(cudaEventRecord(ev[1], st));
   // commitment to the committed wires (range-check limbs + multiplicities) and its proof of knowledge
   G1Affine D{Fp::zero(), Fp::zero()}, PoK{Fp::zero(), Fp::zero()};
   uint64_t X[4] = {0, 0, 0, 0};
   if (k->n_committed) {
-    uint64_t sc = (uint64_t)(k->wires + k->limb_start);
+    uint64_t sc = (uint64_t)(wires + k->limb_start);
     GPW_TRY(gpw_msm_g1_dev(ctx, sc, (uint64_t)k->CK, k->n_committed, 1, 0, 0, 0, (uint64_t*)&D));
     GPW_TRY(gpw_msm_g1_dev(ctx, sc, (uint64_t)k->CKs, k->n_committed, 1, 0, 0, 0, (uint64_t*)&PoK));
     uint8_t ser[64];
@@ -321,22 +354,22 @@ extern "C" int gpw_wrap_prove_dev(gpw_wrap_key* k, uint64_t inputs_dev, const ui
     hash_to_fr(ser, 64, "bsb22-commitment", X);
   }
   GPW_CUDA(cudaEventRecord(ev[2], st));
-  GPW_TRY(gpw_witness_solve_phase2_dev(k->circ, X, 1, (uint64_t)k->wires, k->m));
+  GPW_TRY(gpw_witness_solve_phase2_dev(k->circ, X, 1, (uint64_t)wires, k->m));
   GPW_CUDA(cudaEventRecord(ev[3], st));
   // R1CS evaluation vectors, zero padded to the FFT domain
   GPW_CUDA(cudaMemsetAsync(k->va, 0, N * sizeof(Fr), st));
   GPW_CUDA(cudaMemsetAsync(k->vb, 0, N * sizeof(Fr), st));
   GPW_CUDA(cudaMemsetAsync(k->vc, 0, N * sizeof(Fr), st));
   uint64_t n_bad = 0;
-  int rc = gpw_r1cs_eval_dev(k->circ, (uint64_t)k->wires, (uint64_t)k->va, (uint64_t)k->vb, (uint64_t)k->vc, &n_bad);
+  int rc = gpw_r1cs_eval_dev(k->circ, (uint64_t)wires, (uint64_t)k->va, (uint64_t)k->vb, (uint64_t)k->vc, &n_bad);
   if (rc != GPW_OK && (check || rc != GPW_EUNSAT)) return rc;
   GPW_CUDA(cudaEventRecord(ev[4], st));
   GPW_TRY(gpw_groth16_compute_h_dev(ctx, (uint64_t)k->va, (uint64_t)k->vb, (uint64_t)k->vc, k->logN));
   GPW_CUDA(cudaEventRecord(ev[5], st));
   // gather the scalars of the A / B supports
-  k_gather_fr<<<div_up(k->nA, 256), 256, 0, st>>>(k->wires, k->suppA, k->nA, k->gathA);
+  k_gather_fr<<<div_up(k->nA, 256), 256, 0, st>>>(wires, k->suppA, k->nA, k->gathA);
   GPW_CHECK_LAUNCH();
-  k_gather_fr<<<div_up(k->nB, 256), 256, 0, st>>>(k->wires, k->suppB, k->nB, k->gathB);
+  k_gather_fr<<<div_up(k->nB, 256), 256, 0, st>>>(wires, k->suppB, k->nB, k->gathB);
   GPW_CHECK_LAUNCH();
   ctx->launches += 2;
   G1Affine mA, mB1, mK1, mK2, mZ;
@@ -347,10 +380,10 @@ extern "C" int gpw_wrap_prove_dev(gpw_wrap_key* k, uint64_t inputs_dev, const ui
   // K: private wires that are not committed = [1 + n_pub, limb_start) U [limb_start + n_committed, m), minus the challenge wire
   const uint32_t k_lo = 1 + k->n_pub;
   const uint32_t c_lo = k->n_committed ? k->limb_start : k->m, c_hi = c_lo + k->n_committed;
-  GPW_TRY(gpw_msm_g1_dev(ctx, (uint64_t)(k->wires + k_lo), (uint64_t)(k->K + k_lo), c_lo - k_lo, 1, 0, 0, 0, (uint64_t*)&mK1));
+  GPW_TRY(gpw_msm_g1_dev(ctx, (uint64_t)(wires + k_lo), (uint64_t)(k->K + k_lo), c_lo - k_lo, 1, 0, 0, 0, (uint64_t*)&mK1));
   mK2 = G1Affine{Fp::zero(), Fp::zero()};
   if (c_hi < k->m)
-    GPW_TRY(gpw_msm_g1_dev(ctx, (uint64_t)(k->wires + c_hi), (uint64_t)(k->K + c_hi), k->m - c_hi, 1, 0, 0, 0, (uint64_t*)&mK2));
+    GPW_TRY(gpw_msm_g1_dev(ctx, (uint64_t)(wires + c_hi), (uint64_t)(k->K + c_hi), k->m - c_hi, 1, 0, 0, 0, (uint64_t*)&mK2));
   GPW_TRY(gpw_msm_g1_dev(ctx, (uint64_t)k->va, (uint64_t)k->Z, N - 1, 1, 0, 0, 0, (uint64_t*)&mZ));
   GPW_CUDA(cudaEventRecord(ev[6], st));
   GPW_CUDA(cudaStreamSynchronize(st));
@@ -400,6 +433,47 @@ extern "C" int gpw_wrap_last_stats(const gpw_wrap_key* k, float* ms6) {
   if (!k || !ms6) return GPW_EINVAL;
   for (int i = 0; i < 6; i++) ms6[i] = k->t_ms[i];
   return GPW_OK;
+}
+
+// A stream of n proofs with software pipelining: the sequential first solve phase of proof i+1 (one persistent CTA on
+// one SM, plus a few wide launches) runs on a side stream while the GPU-filling part of proof i (commitment MSMs,
+// log-derivative divisions, R1CS evaluation, NTTs, MSMs) runs on the context's stream. Two wire-vector slots.
+// inputs: n x n_inputs x 4 u64 canonical (host); r, s: n x 4 u64 each; out: n x 64 u64.
+extern "C" int gpw_wrap_prove_many(gpw_wrap_key* k, const uint64_t* inputs, int n, const uint64_t* r_canon, const uint64_t* s_canon,
+                                   int check, uint64_t* out_proofs) {
+  if (!k || !inputs || n < 1 || !r_canon || !s_canon || !out_proofs) {
+    set_error("wrap_prove_many: bad argument");
+    return GPW_EINVAL;
+  }
+  gpw_ctx* ctx = k->ctx;
+  GPW_CUDA(cudaSetDevice(ctx->device));
+  if (!k->side) {
+    GPW_CUDA(cudaStreamCreateWithFlags(&k->side, cudaStreamNonBlocking));
+    GPW_TRY(wk_alloc((void**)&k->wires2, (size_t)k->m * sizeof(Fr)));
+    GPW_TRY(wk_alloc((void**)&k->inputs_dev2, (size_t)k->n_inputs * 32));
+  }
+  Fr* wires[2] = {k->wires, k->wires2};
+  uint64_t* inp[2] = {k->inputs_dev, k->inputs_dev2};
+  const size_t in_words = (size_t)k->n_inputs * 4;
+  auto launch1 = [&](int i) -> int {
+    const int sl = i & 1;
+    GPW_TRY(gpw_circuit_set_stream_slot(k->circ, k->side, sl));
+    GPW_CUDA(cudaMemcpyAsync(inp[sl], inputs + (size_t)i * in_words, in_words * 8, cudaMemcpyHostToDevice, k->side));
+    return gpw_witness_solve_phase1_launch_dev(k->circ, (uint64_t)inp[sl], 1, (uint64_t)wires[sl], k->m);
+  };
+  int rc = launch1(0);
+  for (int i = 0; i < n && rc == GPW_OK; i++) {
+    const int sl = i & 1;
+    rc = gpw_circuit_set_stream_slot(k->circ, k->side, sl);
+    if (rc == GPW_OK) rc = gpw_witness_solve_phase1_finish(k->circ, 1);  // waits for the side stream: phase 1 of proof i is done
+    if (rc == GPW_OK && i + 1 < n) rc = launch1(i + 1);                  // overlaps with stage 2 of proof i below
+    if (rc != GPW_OK) break;
+    gpw_circuit_set_stream_slot(k->circ, nullptr, sl);
+    rc = wrap_stage2(k, wires[sl], r_canon + 4 * i, s_canon + 4 * i, check, out_proofs + 64 * (size_t)i);
+  }
+  cudaStreamSynchronize(k->side);
+  gpw_circuit_set_stream_slot(k->circ, nullptr, 0);
+  return rc;
 }
 
 extern "C" int gpw_hash_to_fr(const uint8_t* msg, size_t len, const char* dst, uint64_t* out_canonical) {

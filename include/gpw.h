@@ -150,6 +150,11 @@ int gpw_circuit_parse_inputs(const gpw_circuit* c, const char* proof_with_public
 int gpw_witness_solve_phase1_dev(gpw_circuit* c, uint64_t inputs_dev, int n_proofs, uint64_t wires_dev, size_t wire_stride);
 int gpw_witness_solve_phase2_dev(gpw_circuit* c, const uint64_t* challenges_canonical, int n_proofs, uint64_t wires_dev,
                                  size_t wire_stride);
+/* phase 1 split into an asynchronous launch and a status-collecting finish; gpw_circuit_set_stream_slot selects the
+ * stream (0 = the context's) and scratch slot (0..7) that subsequent solve calls on the circuit use.               */
+int gpw_witness_solve_phase1_launch_dev(gpw_circuit* c, uint64_t inputs_dev, int n_proofs, uint64_t wires_dev, size_t wire_stride);
+int gpw_witness_solve_phase1_finish(gpw_circuit* c, int n_proofs);
+int gpw_circuit_set_stream_slot(gpw_circuit* c, void* cuda_stream, int slot);
 /* a = L.w, b = R.w, c = O.w (device, >= n_constraints Fr each; pass 0 to only check). GPW_EUNSAT if a*b != c somewhere. */
 int gpw_r1cs_eval_dev(gpw_circuit* c, uint64_t wires_dev, uint64_t a_dev, uint64_t b_dev, uint64_t c_dev, uint64_t* n_unsatisfied);
 int gpw_circuit_supports(const gpw_circuit* c, int side, uint32_t* out, size_t cap, size_t* n);
@@ -171,6 +176,10 @@ int gpw_wrap_prove(gpw_wrap_key* k, const uint64_t* inputs, const uint64_t* r_ca
 /* same, with the parsed inputs already resident on the device (n_inputs x 4 u64 canonical) */
 int gpw_wrap_prove_dev(gpw_wrap_key* k, uint64_t inputs_dev, const uint64_t* r_canonical, const uint64_t* s_canonical, int check,
                        uint64_t* out_proof);
+/* A stream of n proofs, software-pipelined: the sequential first solve phase of proof i+1 (one SM) overlaps the
+ * GPU-filling remainder of proof i. inputs: n x n_inputs x 4 u64 (host); r, s: n x 4 u64; out: n x 64 u64.        */
+int gpw_wrap_prove_many(gpw_wrap_key* k, const uint64_t* inputs, int n, const uint64_t* r_canonical, const uint64_t* s_canonical,
+                        int check, uint64_t* out_proofs);
 int gpw_wrap_last_stats(const gpw_wrap_key* k, float* ms6);
 int gpw_hash_to_fr(const uint8_t* msg, size_t len, const char* dst, uint64_t* out_canonical);
 
