@@ -237,16 +237,6 @@ __global__ void __launch_bounds__(128)
   }
 }
 
-template <class F>
-__device__ __forceinline__ XYZZ<F> shfl_down_point(const XYZZ<F>& v, int delta) {
-  XYZZ<F> r;
-  const uint32_t* s = reinterpret_cast<const uint32_t*>(&v);
-  uint32_t* d = reinterpret_cast<uint32_t*>(&r);
-#pragma unroll
-  for (int i = 0; i < (int)(sizeof(XYZZ<F>) / 4); i++) d[i] = __shfl_down_sync(0xffffffffu, s[i], delta);
-  return r;
-}
-
 constexpr uint32_t FIXUP_SERIAL_MAX = 24;  // spans up to this many tasks are summed by one thread
 
 // Buckets that span several tasks: tail[t0] + head[t0+1] + head[t0+2] + ...  One thread per bucket; the
@@ -276,32 +266,38 @@ __global__ void __launch_bounds__(128)
   }
 }
 
-// one warp per long-span bucket
+// one CTA per long-span bucket (the hot buckets of a skewed scalar distribution: thousands of partials): strided
+// serial sums per thread, then a shared-memory tree
 template <class F>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(256)
     k_msm_fixup_big(const XYZZ<F>* __restrict__ head, const XYZZ<F>* __restrict__ tail,
                     const uint32_t* __restrict__ head_key, const uint32_t* __restrict__ tail_key,
                     const uint32_t* __restrict__ big_list, const uint32_t* __restrict__ nbig, uint32_t ntasks,
                     XYZZ<F>* __restrict__ buckets) {
-  const uint32_t lane = threadIdx.x & 31u;
-  const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
+  extern __shared__ uint4 fix_smem[];
+  XYZZ<F>* sm = reinterpret_cast<XYZZ<F>*>(fix_smem);
   const uint32_t nt = *nbig;
-  for (uint32_t i = warp; i < nt; i += nwarps) {
+  for (uint32_t i = blockIdx.x; i < nt; i += gridDim.x) {
     const uint32_t t0 = big_list[i];
     const uint32_t key = tail_key[t0];
     XYZZ<F> acc = XYZZ<F>::inf();
-    if (lane == 0) acc = tail[t0];
-    for (uint64_t t = (uint64_t)t0 + 1 + lane; t < ntasks && head_key[t] == key; t += 32) {
-      XYZZ<F> h = head[t];
+    if (threadIdx.x == 0) acc = ld_struct(tail + t0);
+    for (uint64_t t = (uint64_t)t0 + 1 + threadIdx.x; t < ntasks && head_key[t] == key; t += blockDim.x) {
+      XYZZ<F> h = ld_struct(head + t);
       add_full(acc, h);
     }
-#pragma unroll 1
-    for (int d = 16; d >= 1; d >>= 1) {
-      XYZZ<F> o = shfl_down_point(acc, d);
-      if ((int)lane < d) add_full(acc, o);
+    st_struct(sm + threadIdx.x, acc);
+    __syncthreads();
+    for (uint32_t d = blockDim.x >> 1; d >= 1; d >>= 1) {
+      if (threadIdx.x < d) {
+        XYZZ<F> o = sm[threadIdx.x + d];
+        add_full(acc, o);
+        sm[threadIdx.x] = acc;
+      }
+      __syncthreads();
     }
-    if (lane == 0) st_struct(buckets + key, acc);
+    if (threadIdx.x == 0) st_struct(buckets + key, acc);
+    __syncthreads();
   }
 }
 
@@ -442,7 +438,11 @@ static int msm_dev_impl(gpw_ctx* ctx, const Fr* scalars, const Affine<F>* points
   k_msm_fixup<F><<<ctx->sm_count * 8, 128, 0, st>>>(head, tail, head_key, tail_key, tail_list, ntail, ntasks, big_list,
                                                     nbig, buckets);
   GPW_CHECK_LAUNCH();
-  k_msm_fixup_big<F><<<ctx->sm_count * 4, 128, 0, st>>>(head, tail, head_key, tail_key, big_list, nbig, ntasks, buckets);
+  {
+    const int fb_threads = sizeof(XYZZ<F>) > 128 ? 128 : 256;
+    k_msm_fixup_big<F><<<ctx->sm_count * 2, fb_threads, fb_threads * sizeof(XYZZ<F>), st>>>(head, tail, head_key, tail_key, big_list,
+                                                                                          nbig, ntasks, buckets);
+  }
   GPW_CHECK_LAUNCH();
   k_msm_window_partial<F><<<div_up((size_t)nw * nchunks, 128), 128, 0, st>>>(buckets, half, chunk, (uint32_t)nw, partials);
   GPW_CHECK_LAUNCH();

@@ -874,6 +874,7 @@ extern "C" int gpw_witness_solve_phase2_dev(gpw_circuit* c, const uint64_t* chal
   uint32_t* hist;
   GPW_TRY(ctx->get_scratch(c->scratch_name("solve.err").c_str(), (size_t)n_proofs * sizeof(int), (void**)&err));
   GPW_TRY(ctx->get_scratch(c->scratch_name("solve.hist").c_str(), (size_t)n_proofs * 65536 * 4, (void**)&hist));
+  GPW_CUDA(cudaMemsetAsync(err, 0, (size_t)n_proofs * sizeof(int), c->stream()));  // phase 1 reported its own status
   for (int p = 0; p < n_proofs; p++) {
     Fr x = fe::fr_from_limbs(challenges_canonical + 4 * p);
     GPW_CUDA(cudaMemcpyAsync((Fr*)wires_dev + (size_t)p * wire_stride + c->dc.commit_wire, &x, sizeof(Fr), cudaMemcpyHostToDevice,

@@ -153,6 +153,9 @@ int gpw_groth16_compute_h_dev(gpw_ctx* ctx, uint64_t a_dev, uint64_t b_dev, uint
 // groth16.DummySetup - but have exactly the shapes a real key has for THIS circuit: A / B bases only for wires that
 // occur in some L / R row (gnark's pk.InfinityA / InfinityB filtering), K bases for private non-committed wires, a
 // Pedersen commitment basis (+ its sigma-twin for the proof of knowledge) for the committed wires, Z for h.
+// proofs whose sequential first solve phase runs side by side (one SM each) in the pipelined stream
+constexpr int PIPE_GROUP = 2;
+
 struct gpw_wrap_key {
   gpw_ctx* ctx = nullptr;
   gpw_circuit* circ = nullptr;
@@ -168,7 +171,7 @@ struct gpw_wrap_key {
   Fr *wires = nullptr, *va = nullptr, *vb = nullptr, *vc = nullptr, *gathA = nullptr, *gathB = nullptr;
   uint64_t* inputs_dev = nullptr;
   uint32_t n_inputs = 0;
-  // second proof slot + side stream for pipelined proving (gpw_wrap_prove_many)
+  // wire-vector slots (2 groups of PIPE_GROUP proofs) + side stream for pipelined proving (gpw_wrap_prove_many)
   Fr* wires2 = nullptr;
   uint64_t* inputs_dev2 = nullptr;
   cudaStream_t side = nullptr;
@@ -340,6 +343,12 @@ static int wrap_stage2(gpw_wrap_key* k, Fr* wires, const uint64_t* r_canon, cons
   cudaEvent_t ev[7];
   for (auto& e : ev) GPW_CUDA(cudaEventCreate(&e));
   memset(out_proof, 0, 64 * 8);
+  const bool dbg = getenv("GPW_DEBUG_WRAP") != nullptr;
+  auto report = [&](const char* what, size_t n) {
+    if (dbg)
+      fprintf(stderr, "[gpw wrap] MSM %-4s n=%8zu total %7.2f ms accumulate %7.2f ms digits %llu\n", what, n, ctx->msm_total_ms,
+              ctx->msm_acc_ms, (unsigned long long)ctx->msm_digits);
+  };
   GPW_CUDA(cudaEventRecord(ev[0], st));
   GPW_CUDA(cudaEventRecord(ev[1], st));
   // commitment to the committed wires (range-check limbs + multiplicities) and its proof of knowledge
@@ -348,7 +357,9 @@ static int wrap_stage2(gpw_wrap_key* k, Fr* wires, const uint64_t* r_canon, cons
   if (k->n_committed) {
     uint64_t sc = (uint64_t)(wires + k->limb_start);
     GPW_TRY(gpw_msm_g1_dev(ctx, sc, (uint64_t)k->CK, k->n_committed, 1, 0, 0, 0, (uint64_t*)&D));
+    report("CK", k->n_committed);
     GPW_TRY(gpw_msm_g1_dev(ctx, sc, (uint64_t)k->CKs, k->n_committed, 1, 0, 0, 0, (uint64_t*)&PoK));
+    report("CKs", k->n_committed);
     uint8_t ser[64];
     ser_g1_be(D, ser);
     hash_to_fr(ser, 64, "bsb22-commitment", X);
@@ -375,16 +386,22 @@ static int wrap_stage2(gpw_wrap_key* k, Fr* wires, const uint64_t* r_canon, cons
   G1Affine mA, mB1, mK1, mK2, mZ;
   G2Affine mB2;
   GPW_TRY(gpw_msm_g1_dev(ctx, (uint64_t)k->gathA, (uint64_t)k->A, k->nA, 1, 0, 0, 0, (uint64_t*)&mA));
+  report("A", k->nA);
   GPW_TRY(gpw_msm_g1_dev(ctx, (uint64_t)k->gathB, (uint64_t)k->B1, k->nB, 1, 0, 0, 0, (uint64_t*)&mB1));
+  report("B1", k->nB);
   GPW_TRY(gpw_msm_g2_dev(ctx, (uint64_t)k->gathB, (uint64_t)k->B2, k->nB, 1, 0, 0, 0, (uint64_t*)&mB2));
+  report("B2", k->nB);
   // K: private wires that are not committed = [1 + n_pub, limb_start) U [limb_start + n_committed, m), minus the challenge wire
   const uint32_t k_lo = 1 + k->n_pub;
   const uint32_t c_lo = k->n_committed ? k->limb_start : k->m, c_hi = c_lo + k->n_committed;
   GPW_TRY(gpw_msm_g1_dev(ctx, (uint64_t)(wires + k_lo), (uint64_t)(k->K + k_lo), c_lo - k_lo, 1, 0, 0, 0, (uint64_t*)&mK1));
+  report("K1", c_lo - k_lo);
   mK2 = G1Affine{Fp::zero(), Fp::zero()};
   if (c_hi < k->m)
     GPW_TRY(gpw_msm_g1_dev(ctx, (uint64_t)(wires + c_hi), (uint64_t)(k->K + c_hi), k->m - c_hi, 1, 0, 0, 0, (uint64_t*)&mK2));
+  if (c_hi < k->m) report("K2", k->m - c_hi);
   GPW_TRY(gpw_msm_g1_dev(ctx, (uint64_t)k->va, (uint64_t)k->Z, N - 1, 1, 0, 0, 0, (uint64_t*)&mZ));
+  report("Z", N - 1);
   GPW_CUDA(cudaEventRecord(ev[6], st));
   GPW_CUDA(cudaStreamSynchronize(st));
   for (int i = 0; i < 6; i++) GPW_CUDA(cudaEventElapsedTime(&k->t_ms[i], ev[i], ev[i + 1]));
@@ -447,29 +464,36 @@ extern "C" int gpw_wrap_prove_many(gpw_wrap_key* k, const uint64_t* inputs, int 
   }
   gpw_ctx* ctx = k->ctx;
   GPW_CUDA(cudaSetDevice(ctx->device));
+  // Proofs are solved in GROUPS of G: one launch runs the spines of G proofs on G SMs (they take as long as one),
+  // while the G proofs of the previous group go through stage 2 one after the other. Two groups of wire slots.
+  constexpr int G = PIPE_GROUP;
   if (!k->side) {
     GPW_CUDA(cudaStreamCreateWithFlags(&k->side, cudaStreamNonBlocking));
-    GPW_TRY(wk_alloc((void**)&k->wires2, (size_t)k->m * sizeof(Fr)));
-    GPW_TRY(wk_alloc((void**)&k->inputs_dev2, (size_t)k->n_inputs * 32));
+    GPW_TRY(wk_alloc((void**)&k->wires2, (size_t)k->m * sizeof(Fr) * (2 * G)));
+    GPW_TRY(wk_alloc((void**)&k->inputs_dev2, (size_t)k->n_inputs * 32 * (2 * G)));
   }
-  Fr* wires[2] = {k->wires, k->wires2};
-  uint64_t* inp[2] = {k->inputs_dev, k->inputs_dev2};
   const size_t in_words = (size_t)k->n_inputs * 4;
-  auto launch1 = [&](int i) -> int {
-    const int sl = i & 1;
-    GPW_TRY(gpw_circuit_set_stream_slot(k->circ, k->side, sl));
-    GPW_CUDA(cudaMemcpyAsync(inp[sl], inputs + (size_t)i * in_words, in_words * 8, cudaMemcpyHostToDevice, k->side));
-    return gpw_witness_solve_phase1_launch_dev(k->circ, (uint64_t)inp[sl], 1, (uint64_t)wires[sl], k->m);
+  auto group_wires = [&](int g) { return k->wires2 + (size_t)(g & 1) * G * k->m; };
+  auto group_inputs = [&](int g) { return k->inputs_dev2 + (size_t)(g & 1) * G * in_words; };
+  const int n_groups = (n + G - 1) / G;
+  auto group_size = [&](int g) { return std::min(G, n - g * G); };
+  auto launch1 = [&](int g) -> int {
+    GPW_TRY(gpw_circuit_set_stream_slot(k->circ, k->side, g & 1));
+    GPW_CUDA(cudaMemcpyAsync(group_inputs(g), inputs + (size_t)g * G * in_words, in_words * 8 * group_size(g), cudaMemcpyHostToDevice,
+                             k->side));
+    return gpw_witness_solve_phase1_launch_dev(k->circ, (uint64_t)group_inputs(g), group_size(g), (uint64_t)group_wires(g), k->m);
   };
   int rc = launch1(0);
-  for (int i = 0; i < n && rc == GPW_OK; i++) {
-    const int sl = i & 1;
-    rc = gpw_circuit_set_stream_slot(k->circ, k->side, sl);
-    if (rc == GPW_OK) rc = gpw_witness_solve_phase1_finish(k->circ, 1);  // waits for the side stream: phase 1 of proof i is done
-    if (rc == GPW_OK && i + 1 < n) rc = launch1(i + 1);                  // overlaps with stage 2 of proof i below
+  for (int g = 0; g < n_groups && rc == GPW_OK; g++) {
+    rc = gpw_circuit_set_stream_slot(k->circ, k->side, g & 1);
+    if (rc == GPW_OK) rc = gpw_witness_solve_phase1_finish(k->circ, group_size(g));  // waits for the side stream
+    if (rc == GPW_OK && g + 1 < n_groups) rc = launch1(g + 1);                         // overlaps with stage 2 below
     if (rc != GPW_OK) break;
-    gpw_circuit_set_stream_slot(k->circ, nullptr, sl);
-    rc = wrap_stage2(k, wires[sl], r_canon + 4 * i, s_canon + 4 * i, check, out_proofs + 64 * (size_t)i);
+    gpw_circuit_set_stream_slot(k->circ, nullptr, 2 + (g & 1));
+    for (int j = 0; j < group_size(g) && rc == GPW_OK; j++) {
+      const int i = g * G + j;
+      rc = wrap_stage2(k, group_wires(g) + (size_t)j * k->m, r_canon + 4 * i, s_canon + 4 * i, check, out_proofs + 64 * (size_t)i);
+    }
   }
   cudaStreamSynchronize(k->side);
   gpw_circuit_set_stream_slot(k->circ, nullptr, 0);
