@@ -182,19 +182,73 @@ static __global__ void k_msm_scatter(const Fr* __restrict__ scalars, size_t n, i
   });
 }
 
+// select helpers: branch-free so that the lanes of a warp stay converged through the accumulate loop
+template <class P>
+__device__ __forceinline__ Fe<P> fsel(bool c, const Fe<P>& a, const Fe<P>& b) {
+  Fe<P> r;
+#pragma unroll
+  for (int i = 0; i < 8; i++) r.l[i] = c ? a.l[i] : b.l[i];
+  return r;
+}
+__device__ __forceinline__ Fp2 fsel(bool c, const Fp2& a, const Fp2& b) { return {fsel(c, a.c0, b.c0), fsel(c, a.c1, b.c1)}; }
+
+// acc += (q.x, negate ? -q.y : q.y), written for SIMT: the common cases (ordinary addition, first point of a run,
+// base at infinity) run the same instruction stream and are resolved by selects; only the doubling / cancellation
+// case (acc == +-q, never hit by honest keys but reachable from tests) leaves the straight-line path.
 template <class F>
-__global__ void __launch_bounds__(128)
+__device__ __forceinline__ void add_mixed_flat(XYZZ<F>& acc, const Affine<F>& q, bool negate) {
+  const bool q_inf = q.is_inf();
+  const bool a_inf = acc.is_inf();
+  const F y2 = fsel(negate, neg(q.y), q.y);
+  const F U2 = mul(q.x, acc.ZZ);
+  const F S2 = mul(y2, acc.ZZZ);
+  const F Pv = sub(U2, acc.X);
+  const F R = sub(S2, acc.Y);
+  if (!q_inf && !a_inf && Pv.is_zero()) {
+    if (R.is_zero()) acc = dbl_affine(Affine<F>{q.x, y2});
+    else acc = XYZZ<F>::inf();
+    return;
+  }
+  const F PP = sqr(Pv);
+  const F PPP = mul(Pv, PP);
+  const F Q = mul(acc.X, PP);
+  const F X3 = sub(sub(sqr(R), PPP), dbl(Q));
+  const F Y3 = sub(mul(R, sub(Q, X3)), mul(acc.Y, PPP));
+  const F Z2 = mul(acc.ZZ, PP);
+  const F Z3 = mul(acc.ZZZ, PPP);
+  // a_inf: the sum is q itself; q_inf: acc unchanged
+  const F one = F::one();
+  acc.X = fsel(q_inf, acc.X, fsel(a_inf, q.x, X3));
+  acc.Y = fsel(q_inf, acc.Y, fsel(a_inf, y2, Y3));
+  acc.ZZ = fsel(q_inf, acc.ZZ, fsel(a_inf, one, Z2));
+  acc.ZZZ = fsel(q_inf, acc.ZZZ, fsel(a_inf, one, Z3));
+}
+
+constexpr int MSM_ACC_THREADS = 128;
+
+// One thread per task of MSM_TASK consecutive sorted entries, walked by ONE flat loop so that all lanes of a warp
+// execute the same mixed addition in lock step (the earlier nested per-run loops left ~55 % of the lanes idle:
+// smsp__thread_inst_executed_per_inst_executed 14.4, profiles/r01_msm_accumulate_ncu.md). A run that ends inside
+// the task is flushed by a short divergent store. CTAs whose 8192 entries all belong to one (hot) bucket - bit
+// wires make bucket (window 0, digit 1) millions of entries long - merge their 128 partials in shared memory, so
+// the fix-up pass sees one partial per CTA instead of one per thread.
+template <class F>
+__global__ void __launch_bounds__(MSM_ACC_THREADS)
     k_msm_accumulate(const Affine<F>* __restrict__ points, const uint32_t* __restrict__ sorted,
                      const uint32_t* __restrict__ offsets, uint32_t B, XYZZ<F>* __restrict__ buckets,
                      XYZZ<F>* __restrict__ head, XYZZ<F>* __restrict__ tail, uint32_t* __restrict__ head_key,
                      uint32_t* __restrict__ tail_key, uint32_t* __restrict__ tail_list,
                      uint32_t* __restrict__ ntail) {
+  extern __shared__ uint4 acc_smem[];
   const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
   const uint32_t M = offsets[B];
+  const uint64_t cta_p0 = (uint64_t)blockIdx.x * blockDim.x * MSM_TASK;
+  if (cta_p0 >= M) return;  // whole CTA past the end
+  const uint64_t cta_p1 = cta_p0 + (uint64_t)blockDim.x * MSM_TASK;
   const uint64_t p0 = (uint64_t)t * MSM_TASK;
-  if (p0 >= M) return;
-  const uint32_t pos0 = (uint32_t)p0;
-  const uint32_t pos1 = min(pos0 + (uint32_t)MSM_TASK, M);
+  const bool active = p0 < M;
+  const uint32_t pos0 = active ? (uint32_t)p0 : M - 1;
+  const uint32_t pos1 = active ? min(pos0 + (uint32_t)MSM_TASK, M) : M - 1;
   // bucket containing pos0: largest b with offsets[b] <= pos0 (skips empty buckets sharing the offset)
   uint32_t lo = 0, hi = B;
   while (hi - lo > 1) {
@@ -202,38 +256,79 @@ __global__ void __launch_bounds__(128)
     if (offsets[mid] <= pos0) lo = mid; else hi = mid;
   }
   uint32_t b = lo;
+  uint32_t bstart = offsets[b], bend = offsets[b + 1];
+  // the same value in every thread: if one thread's bucket covers the CTA's whole range, all threads are in it
+  const bool cta_uniform = cta_p1 <= M && bstart <= cta_p0 && bend >= cta_p1;
+
+  XYZZ<F> acc = XYZZ<F>::inf();
   uint32_t pos = pos0;
-  uint32_t e_next = sorted[pos];
+  uint32_t e_next = sorted[pos0];
   Affine<F> p_next = ld_struct(points + (e_next & 0x7fffffffu));
+#pragma unroll 1
   while (pos < pos1) {
-    const uint32_t bstart = offsets[b];
-    const uint32_t bend = offsets[b + 1];
-    const uint32_t run_end = min(bend, pos1);
-    XYZZ<F> acc = XYZZ<F>::inf();
-    while (pos < run_end) {
-      const uint32_t e = e_next;
-      const Affine<F> p = p_next;
-      pos++;
-      if (pos < pos1) {  // prefetch the next point while this add runs
-        e_next = sorted[pos];
-        p_next = ld_struct(points + (e_next & 0x7fffffffu));
+    if (pos == bend) {  // the previous entry closed bucket b (never taken in a uniform CTA)
+      if (bstart < pos0) {
+        st_struct(head + t, acc);
+        head_key[t] = b;
+      } else {
+        st_struct(buckets + b, acc);
       }
-      add_mixed(acc, p, (e >> 31) != 0);
+      acc = XYZZ<F>::inf();
+      b++;
+      while (offsets[b + 1] <= pos) b++;
+      bstart = pos;
+      bend = offsets[b + 1];
     }
-    if (bstart < pos0) {  // bucket began in an earlier task
-      st_struct(head + t, acc);
-      head_key[t] = b;
-    } else if (bend > pos1) {  // bucket continues into later tasks
+    const uint32_t e = e_next;
+    const Affine<F> p = p_next;
+    pos++;
+    if (pos < pos1) {  // prefetch the next point while this add runs
+      e_next = sorted[pos];
+      p_next = ld_struct(points + (e_next & 0x7fffffffu));
+    }
+    add_mixed_flat(acc, p, (e >> 31) != 0);
+  }
+
+  if (cta_uniform) {
+    XYZZ<F>* sm = reinterpret_cast<XYZZ<F>*>(acc_smem);
+    const uint32_t tid = threadIdx.x;
+    sm[tid] = acc;
+    __syncthreads();
+    for (uint32_t d = blockDim.x >> 1; d >= 1; d >>= 1) {
+      if (tid < d) {
+        XYZZ<F> o = sm[tid + d];
+        add_full(acc, o);
+        sm[tid] = acc;
+      }
+      __syncthreads();
+    }
+    // thread 0 carries the CTA's sum; the other threads publish "same bucket, nothing to add" so that the
+    // fix-up's scan over head_key sees one unbroken span
+    if (tid != 0) acc = XYZZ<F>::inf();
+    const bool starts_here = bstart == (uint32_t)cta_p0, ends_here = bend == (uint32_t)cta_p1;
+    if (starts_here && ends_here) {  // the bucket is exactly this CTA
+      if (tid == 0) st_struct(buckets + b, acc);
+    } else if (starts_here && tid == 0) {
       st_struct(tail + t, acc);
       tail_key[t] = b;
       tail_list[atomicAdd(ntail, 1u)] = t;
     } else {
-      st_struct(buckets + b, acc);
+      st_struct(head + t, acc);
+      head_key[t] = b;
     }
-    if (pos < pos1) {
-      b++;
-      while (offsets[b + 1] <= pos) b++;
-    }
+    return;
+  }
+  if (!active) return;
+  // last run of the task (ends at pos1 or beyond)
+  if (bstart < pos0) {  // bucket began in an earlier task
+    st_struct(head + t, acc);
+    head_key[t] = b;
+  } else if (bend > pos1) {  // bucket continues into later tasks
+    st_struct(tail + t, acc);
+    tail_key[t] = b;
+    tail_list[atomicAdd(ntail, 1u)] = t;
+  } else {
+    st_struct(buckets + b, acc);
   }
 }
 
@@ -431,8 +526,8 @@ static int msm_dev_impl(gpw_ctx* ctx, const Fr* scalars, const Affine<F>* points
   k_msm_scatter<<<div_up(n, TPB), TPB, 0, st>>>(scalars, n, mont, c, nwin, win_lo, win_hi, cursor, sorted);
   GPW_CHECK_LAUNCH();
   GPW_CUDA(cudaEventRecord(ctx->ev[1], st));
-  k_msm_accumulate<F><<<div_up(ntasks, 128), 128, 0, st>>>(points, sorted, offsets, B, buckets, head, tail, head_key,
-                                                          tail_key, tail_list, ntail);
+  k_msm_accumulate<F><<<div_up(ntasks, MSM_ACC_THREADS), MSM_ACC_THREADS, MSM_ACC_THREADS * sizeof(XYZZ<F>), st>>>(
+      points, sorted, offsets, B, buckets, head, tail, head_key, tail_key, tail_list, ntail);
   GPW_CHECK_LAUNCH();
   GPW_CUDA(cudaEventRecord(ctx->ev[2], st));
   k_msm_fixup<F><<<ctx->sm_count * 8, 128, 0, st>>>(head, tail, head_key, tail_key, tail_list, ntail, ntasks, big_list,

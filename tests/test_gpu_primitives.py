@@ -249,6 +249,19 @@ def test_msm_hot_bucket(ctx):
     _msm_case(ctx, 1, [3] * (n // 2) + [ob.R - 3] * (n // 2), list(range(1, n + 1)))
 
 
+@pytest.mark.parametrize("group,n", [(1, 8192), (1, 16384), (1, 8192 * 3 + 77), (2, 8192 * 2 + 5)])
+def test_msm_hot_bucket_whole_ctas(ctx, group, n):
+    # a bucket that fills whole accumulate CTAs (128 threads x 64 entries): the in-CTA merge of the 128 partials,
+    # for a bucket that is exactly one CTA, exactly two, and one that starts and ends inside neighbouring CTAs;
+    # a few other scalars before and after it so the hot bucket is neither the first nor the last one
+    ks = list(range(1, n + 1))
+    _msm_case(ctx, group, [7] * n, ks, window_bits=16)
+    lead, trail = [1, 2, 3, 5, 6], [9, 11, 0xffff, 1 << 40]
+    _msm_case(ctx, group, lead + [7] * n + trail, list(range(1, n + len(lead) + len(trail) + 1)), window_bits=16)
+    # the same base repeated inside the hot bucket: doubling / cancellation leave the straight-line path
+    _msm_case(ctx, group, [7] * n, [1 + (i % 5) for i in range(n)], window_bits=16)
+
+
 def test_msm_window_split_matches_full(ctx):
     # multi-GPU window split: partial results over disjoint window ranges must add up to the full MSM
     import torch
