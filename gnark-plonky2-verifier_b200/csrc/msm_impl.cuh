@@ -6,9 +6,9 @@
 // with any correct implementation is exact.
 //
 // Pipeline (all on one stream, no host round trips until the final 16 window sums):
-//   1. k_msm_count     signed c-bit digits of every scalar -> histogram over (window, |digit|) buckets
+//   1. k_msm_digits<0> signed c-bit digits of every scalar -> histogram over (window, |digit|) buckets
 //   2. k_msm_scan      exclusive prefix sum of the histogram (bucket start offsets)
-//   3. k_msm_scatter   counting-sort scatter of (point index | sign) by bucket
+//   3. k_msm_digits<1> counting-sort scatter of (point index | sign) by bucket (both passes warp-aggregate their atomics)
 //   4. k_msm_accumulate  THE hot kernel: the sorted entry array is cut into uniform tasks of
 //                      MSM_TASK entries; one thread walks one task doing XYZZ += affine mixed adds
 //                      (8M + 2S each, ~3000 IMADs) with 64 B / 128 B gathers of the affine points.
@@ -25,7 +25,6 @@
 namespace gpw {
 
 constexpr int MSM_TASK = 64;         // sorted entries per accumulate thread
-constexpr uint32_t KEY_NONE = 0xffffffffu;
 
 template <class T>
 __device__ __forceinline__ T ld_struct(const T* p) {
@@ -54,29 +53,47 @@ __device__ __forceinline__ uint32_t get_bits(const uint32_t* s, int lo, int c) {
   return (uint32_t)(v >> off) & ((1u << c) - 1u);
 }
 
-// Calls f(window, bucket_index, negative) for every non-zero signed digit in [win_lo, win_hi).
-template <class Fn>
-__device__ __forceinline__ void for_each_digit(const Fr& s, int c, int nwin, int win_lo, int win_hi, Fn f) {
-  const uint32_t half = 1u << (c - 1);
-  uint32_t carry = 0;
-  for (int w = 0; w < win_hi && w < nwin; w++) {
-    uint32_t raw = get_bits(s.l, w * c, c) + carry;
-    bool negv = raw > half;
-    uint32_t mag = negv ? ((1u << c) - raw) : raw;
-    carry = negv ? 1u : 0u;
-    if (mag != 0 && w >= win_lo) f(w, mag - 1u, negv);
+// Signed-digit extraction shared by the histogram and the scatter pass. Every lane walks every window (uniform trip
+// count) so that the warp can aggregate its atomics: lanes that hit the same bucket - bit wires and small constants make
+// (window 0, digit 1) and its neighbours receive millions of entries - are found with match.any and served by ONE
+// atomic of the group's size instead of a same-address atomic per lane (which the L2 serialises).
+template <bool SCATTER>
+static __global__ void __launch_bounds__(256) k_msm_digits(const Fr* __restrict__ scalars, size_t n, int mont, int c, int nwin,
+                                                           int win_lo, int win_hi, uint32_t* __restrict__ counters,
+                                                           uint32_t* __restrict__ sorted) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t lane = threadIdx.x & 31u;
+  Fr s = Fr::zero();
+  if (i < n) {
+    s = ld_struct(scalars + i);
+    if (mont) s = from_mont(s);
   }
-}
-
-static __global__ void k_msm_count(const Fr* __restrict__ scalars, size_t n, int mont, int c, int nwin, int win_lo,
-                            int win_hi, uint32_t* __restrict__ counts) {
-  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  Fr s = ld_struct(scalars + i);
-  if (mont) s = from_mont(s);
   const uint32_t half = 1u << (c - 1);
-  for_each_digit(s, c, nwin, win_lo, win_hi,
-                 [&](int w, uint32_t b, bool) { atomicAdd(&counts[(uint32_t)(w - win_lo) * half + b], 1u); });
+  const int wend = win_hi < nwin ? win_hi : nwin;
+  uint32_t carry = 0;
+  for (int w = 0; w < wend; w++) {
+    const uint32_t raw = get_bits(s.l, w * c, c) + carry;
+    const bool negv = raw > half;
+    const uint32_t mag = negv ? ((1u << c) - raw) : raw;
+    carry = negv ? 1u : 0u;
+    const bool has = mag != 0 && w >= win_lo;
+    if (!__any_sync(0xffffffffu, has)) continue;
+    const uint32_t key = has ? (uint32_t)(w - win_lo) * half + (mag - 1u) : (0xffffffffu - lane);
+    const uint32_t peers = __match_any_sync(0xffffffffu, key);
+    if (has) {
+      const uint32_t leader = (uint32_t)__ffs(peers) - 1u;
+      const uint32_t cnt = (uint32_t)__popc(peers);
+      if (!SCATTER) {
+        if (lane == leader) atomicAdd(&counters[key], cnt);
+      } else {
+        uint32_t base = 0;
+        if (lane == leader) base = atomicAdd(&counters[key], cnt);
+        base = __shfl_sync(peers, base, leader);
+        const uint32_t rank = (uint32_t)__popc(peers & ((1u << lane) - 1u));
+        sorted[base + rank] = (uint32_t)i | (negv ? 0x80000000u : 0u);
+      }
+    }
+  }
 }
 
 // exclusive scan of B counters -> offsets[0..B], cursor[0..B): per-block sums, scan of the block sums,
@@ -169,19 +186,6 @@ static __global__ void __launch_bounds__(SCAN_THREADS) k_msm_scan_final(const ui
   }
 }
 
-static __global__ void k_msm_scatter(const Fr* __restrict__ scalars, size_t n, int mont, int c, int nwin, int win_lo,
-                              int win_hi, uint32_t* __restrict__ cursor, uint32_t* __restrict__ sorted) {
-  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  Fr s = ld_struct(scalars + i);
-  if (mont) s = from_mont(s);
-  const uint32_t half = 1u << (c - 1);
-  for_each_digit(s, c, nwin, win_lo, win_hi, [&](int w, uint32_t b, bool negv) {
-    uint32_t pos = atomicAdd(&cursor[(uint32_t)(w - win_lo) * half + b], 1u);
-    sorted[pos] = (uint32_t)i | (negv ? 0x80000000u : 0u);
-  });
-}
-
 // select helpers: branch-free so that the lanes of a warp stay converged through the accumulate loop
 template <class P>
 __device__ __forceinline__ Fe<P> fsel(bool c, const Fe<P>& a, const Fe<P>& b) {
@@ -236,9 +240,8 @@ template <class F>
 __global__ void __launch_bounds__(MSM_ACC_THREADS)
     k_msm_accumulate(const Affine<F>* __restrict__ points, const uint32_t* __restrict__ sorted,
                      const uint32_t* __restrict__ offsets, uint32_t B, XYZZ<F>* __restrict__ buckets,
-                     XYZZ<F>* __restrict__ head, XYZZ<F>* __restrict__ tail, uint32_t* __restrict__ head_key,
-                     uint32_t* __restrict__ tail_key, uint32_t* __restrict__ tail_list,
-                     uint32_t* __restrict__ ntail) {
+                     XYZZ<F>* __restrict__ head, XYZZ<F>* __restrict__ tail, uint32_t* __restrict__ tail_key,
+                     uint32_t* __restrict__ tail_list, uint32_t* __restrict__ ntail) {
   extern __shared__ uint4 acc_smem[];
   const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
   const uint32_t M = offsets[B];
@@ -267,12 +270,7 @@ __global__ void __launch_bounds__(MSM_ACC_THREADS)
 #pragma unroll 1
   while (pos < pos1) {
     if (pos == bend) {  // the previous entry closed bucket b (never taken in a uniform CTA)
-      if (bstart < pos0) {
-        st_struct(head + t, acc);
-        head_key[t] = b;
-      } else {
-        st_struct(buckets + b, acc);
-      }
+      st_struct(bstart < pos0 ? head + t : buckets + b, acc);
       acc = XYZZ<F>::inf();
       b++;
       while (offsets[b + 1] <= pos) b++;
@@ -302,19 +300,18 @@ __global__ void __launch_bounds__(MSM_ACC_THREADS)
       }
       __syncthreads();
     }
-    // thread 0 carries the CTA's sum; the other threads publish "same bucket, nothing to add" so that the
-    // fix-up's scan over head_key sees one unbroken span
-    if (tid != 0) acc = XYZZ<F>::inf();
+    // thread 0 carries the CTA's sum: the fix-up pass knows from the bucket's offsets which CTAs merged (those lying
+    // wholly inside the bucket) and reads one partial per such CTA - slot of its thread 0 - skipping the other 127
+    if (tid != 0) return;
     const bool starts_here = bstart == (uint32_t)cta_p0, ends_here = bend == (uint32_t)cta_p1;
     if (starts_here && ends_here) {  // the bucket is exactly this CTA
-      if (tid == 0) st_struct(buckets + b, acc);
-    } else if (starts_here && tid == 0) {
+      st_struct(buckets + b, acc);
+    } else if (starts_here) {
       st_struct(tail + t, acc);
       tail_key[t] = b;
       tail_list[atomicAdd(ntail, 1u)] = t;
     } else {
       st_struct(head + t, acc);
-      head_key[t] = b;
     }
     return;
   }
@@ -322,7 +319,6 @@ __global__ void __launch_bounds__(MSM_ACC_THREADS)
   // last run of the task (ends at pos1 or beyond)
   if (bstart < pos0) {  // bucket began in an earlier task
     st_struct(head + t, acc);
-    head_key[t] = b;
   } else if (bend > pos1) {  // bucket continues into later tasks
     st_struct(tail + t, acc);
     tail_key[t] = b;
@@ -332,53 +328,88 @@ __global__ void __launch_bounds__(MSM_ACC_THREADS)
   }
 }
 
+// The partial sums of a bucket that spans several tasks: tail[t0] (the task the bucket starts in) plus one "item" per
+// later task up to the task holding the bucket's last entry - except that CTAs lying wholly inside the bucket merged
+// their 128 partials into the slot of their first thread. Everything follows from the bucket's offsets, so the
+// accumulate kernel does not have to publish per-task keys.
+struct SpanItems {
+  uint32_t t0, pre, mid, first_u, qb, total;
+  __device__ __forceinline__ SpanItems(uint32_t t0_, uint32_t bstart, uint32_t bend) : t0(t0_) {
+    constexpr uint32_t CTA_E = (uint32_t)MSM_ACC_THREADS * MSM_TASK;
+    const uint32_t t_last = (bend - 1u) / MSM_TASK;
+    const uint32_t qa = (bstart + CTA_E - 1u) / CTA_E;
+    qb = bend / CTA_E;
+    if (qa < qb) {
+      first_u = qa;
+      if (t0 == qa * MSM_ACC_THREADS) {  // the bucket starts exactly at CTA qa: its merged sum IS tail[t0]
+        first_u = qa + 1u;
+        pre = 0;
+      } else {
+        pre = qa * MSM_ACC_THREADS - (t0 + 1u);
+      }
+      mid = qb - first_u;
+      const uint32_t post = t_last + 1u - qb * MSM_ACC_THREADS;  // t_last >= qb * 128 - 1 always
+      total = pre + mid + post;
+    } else {
+      first_u = qb = 0;
+      pre = t_last - t0;
+      mid = 0;
+      total = pre;
+    }
+  }
+  // task slot (index into head[]) of item j
+  __device__ __forceinline__ uint32_t slot(uint32_t j) const {
+    if (j < pre) return t0 + 1u + j;
+    if (j < pre + mid) return (first_u + (j - pre)) * MSM_ACC_THREADS;
+    return qb * MSM_ACC_THREADS + (j - pre - mid);
+  }
+};
+
 constexpr uint32_t FIXUP_SERIAL_MAX = 24;  // spans up to this many tasks are summed by one thread
 
-// Buckets that span several tasks: tail[t0] + head[t0+1] + head[t0+2] + ...  One thread per bucket; the
-// rare long spans (hot buckets of a skewed scalar distribution) are deferred to the warp kernel below.
+// Buckets that span several tasks. One thread per bucket; the rare long spans (hot buckets of a skewed scalar
+// distribution) are deferred to the CTA kernel below.
 template <class F>
 __global__ void __launch_bounds__(128)
-    k_msm_fixup(const XYZZ<F>* __restrict__ head, const XYZZ<F>* __restrict__ tail,
-                const uint32_t* __restrict__ head_key, const uint32_t* __restrict__ tail_key,
-                const uint32_t* __restrict__ tail_list, const uint32_t* __restrict__ ntail, uint32_t ntasks,
-                uint32_t* __restrict__ big_list, uint32_t* __restrict__ nbig, XYZZ<F>* __restrict__ buckets) {
+    k_msm_fixup(const XYZZ<F>* __restrict__ head, const XYZZ<F>* __restrict__ tail, const uint32_t* __restrict__ offsets,
+                const uint32_t* __restrict__ tail_key, const uint32_t* __restrict__ tail_list,
+                const uint32_t* __restrict__ ntail, uint32_t* __restrict__ big_list, uint32_t* __restrict__ nbig,
+                XYZZ<F>* __restrict__ buckets) {
   const uint32_t nt = *ntail;
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < nt; i += gridDim.x * blockDim.x) {
     const uint32_t t0 = tail_list[i];
     const uint32_t key = tail_key[t0];
-    uint32_t span = 0;
-    while (span <= FIXUP_SERIAL_MAX && (uint64_t)t0 + 1 + span < ntasks && head_key[t0 + 1 + span] == key) span++;
-    if (span > FIXUP_SERIAL_MAX) {
+    const SpanItems it(t0, offsets[key], offsets[key + 1]);
+    if (it.total > FIXUP_SERIAL_MAX) {
       big_list[atomicAdd(nbig, 1u)] = t0;
       continue;
     }
     XYZZ<F> acc = ld_struct(tail + t0);
-    for (uint32_t k = 0; k < span; k++) {
-      XYZZ<F> h = ld_struct(head + t0 + 1 + k);
+    for (uint32_t j = 0; j < it.total; j++) {
+      XYZZ<F> h = ld_struct(head + it.slot(j));
       add_full(acc, h);
     }
     st_struct(buckets + key, acc);
   }
 }
 
-// one CTA per long-span bucket (the hot buckets of a skewed scalar distribution: thousands of partials): strided
-// serial sums per thread, then a shared-memory tree
+// one CTA per long-span bucket: strided serial sums per thread, then a shared-memory tree
 template <class F>
 __global__ void __launch_bounds__(256)
-    k_msm_fixup_big(const XYZZ<F>* __restrict__ head, const XYZZ<F>* __restrict__ tail,
-                    const uint32_t* __restrict__ head_key, const uint32_t* __restrict__ tail_key,
-                    const uint32_t* __restrict__ big_list, const uint32_t* __restrict__ nbig, uint32_t ntasks,
-                    XYZZ<F>* __restrict__ buckets) {
+    k_msm_fixup_big(const XYZZ<F>* __restrict__ head, const XYZZ<F>* __restrict__ tail, const uint32_t* __restrict__ offsets,
+                    const uint32_t* __restrict__ tail_key, const uint32_t* __restrict__ big_list,
+                    const uint32_t* __restrict__ nbig, XYZZ<F>* __restrict__ buckets) {
   extern __shared__ uint4 fix_smem[];
   XYZZ<F>* sm = reinterpret_cast<XYZZ<F>*>(fix_smem);
   const uint32_t nt = *nbig;
   for (uint32_t i = blockIdx.x; i < nt; i += gridDim.x) {
     const uint32_t t0 = big_list[i];
     const uint32_t key = tail_key[t0];
+    const SpanItems it(t0, offsets[key], offsets[key + 1]);
     XYZZ<F> acc = XYZZ<F>::inf();
     if (threadIdx.x == 0) acc = ld_struct(tail + t0);
-    for (uint64_t t = (uint64_t)t0 + 1 + threadIdx.x; t < ntasks && head_key[t] == key; t += blockDim.x) {
-      XYZZ<F> h = ld_struct(head + t);
+    for (uint32_t j = threadIdx.x; j < it.total; j += blockDim.x) {
+      XYZZ<F> h = ld_struct(head + it.slot(j));
       add_full(acc, h);
     }
     st_struct(sm + threadIdx.x, acc);
@@ -399,14 +430,19 @@ __global__ void __launch_bounds__(256)
 // sum_{b in chunk} (b+1) * B[w][b]   (running-sum trick + one small scalar mul per chunk)
 template <class F>
 __global__ void __launch_bounds__(128)
-    k_msm_window_partial(const XYZZ<F>* __restrict__ buckets, uint32_t half, uint32_t chunk, uint32_t nwin,
-                         XYZZ<F>* __restrict__ partials) {
+    k_msm_window_partial(const XYZZ<F>* __restrict__ buckets, const uint32_t* __restrict__ offsets, uint32_t half,
+                         uint32_t chunk, uint32_t nwin, XYZZ<F>* __restrict__ partials) {
   const uint32_t gid = blockIdx.x * blockDim.x + threadIdx.x;
   const uint32_t nchunks = half / chunk;
   const uint32_t w = gid / nchunks, ci = gid % nchunks;
   if (w >= nwin) return;
   const uint32_t lo = ci * chunk;
   XYZZ<F> acc = XYZZ<F>::inf(), sum = XYZZ<F>::inf();
+  // chunks without a single entry (the upper windows of an MSM over 16-bit limbs or 64-bit values) cost nothing
+  if (offsets[w * half + lo] == offsets[w * half + lo + chunk]) {
+    st_struct(partials + gid, sum);
+    return;
+  }
   for (int b = (int)(lo + chunk) - 1; b >= (int)lo; b--) {
     XYZZ<F> bk = buckets[(size_t)w * half + b];
     add_full(acc, bk);
@@ -489,7 +525,7 @@ static int msm_dev_impl(gpw_ctx* ctx, const Fr* scalars, const Affine<F>* points
   const uint32_t chunk = half < 16u ? half : 16u;
   const uint32_t nchunks = half / chunk;
 
-  uint32_t *counts, *offsets, *cursor, *sorted, *head_key, *tail_key, *tail_list, *ntail, *nbig, *big_list, *block_sums;
+  uint32_t *counts, *offsets, *cursor, *sorted, *tail_key, *tail_list, *ntail, *nbig, *big_list, *block_sums;
   XYZZ<F>*buckets, *head, *tail, *partials, *wsums;
   std::string T(tag);
   GPW_TRY(ctx->get_scratch((T + ".counts").c_str(), (size_t)(B + 1) * 4 * 3 + 64, (void**)&counts));
@@ -500,8 +536,7 @@ static int msm_dev_impl(gpw_ctx* ctx, const Fr* scalars, const Affine<F>* points
   const uint32_t nscan_blocks = (B + SCAN_BLOCK - 1) / SCAN_BLOCK;
   GPW_TRY(ctx->get_scratch((T + ".scanblk").c_str(), (size_t)nscan_blocks * 4 + 16, (void**)&block_sums));
   GPW_TRY(ctx->get_scratch((T + ".sorted").c_str(), (size_t)max_entries * 4 + 16, (void**)&sorted));
-  GPW_TRY(ctx->get_scratch((T + ".keys").c_str(), (size_t)ntasks * 4 * 4, (void**)&head_key));
-  tail_key = head_key + ntasks;
+  GPW_TRY(ctx->get_scratch((T + ".keys").c_str(), (size_t)ntasks * 4 * 3, (void**)&tail_key));
   tail_list = tail_key + ntasks;
   big_list = tail_list + ntasks;
   GPW_TRY(ctx->get_scratch((T + ".buckets").c_str(), (size_t)B * sizeof(XYZZ<F>), (void**)&buckets));
@@ -512,10 +547,9 @@ static int msm_dev_impl(gpw_ctx* ctx, const Fr* scalars, const Affine<F>* points
 
   GPW_CUDA(cudaEventRecord(ctx->ev[0], st));
   GPW_CUDA(cudaMemsetAsync(counts, 0, (size_t)(B + 1) * 4 * 3 + 64, st));
-  GPW_CUDA(cudaMemsetAsync(head_key, 0xff, (size_t)ntasks * 4 * 2, st));
   GPW_CUDA(cudaMemsetAsync(buckets, 0, (size_t)B * sizeof(XYZZ<F>), st));
   const int TPB = 256;
-  k_msm_count<<<div_up(n, TPB), TPB, 0, st>>>(scalars, n, mont, c, nwin, win_lo, win_hi, counts);
+  k_msm_digits<false><<<div_up(n, TPB), TPB, 0, st>>>(scalars, n, mont, c, nwin, win_lo, win_hi, counts, nullptr);
   GPW_CHECK_LAUNCH();
   k_msm_scan_sums<<<nscan_blocks, SCAN_THREADS, 0, st>>>(counts, B, block_sums);
   GPW_CHECK_LAUNCH();
@@ -523,23 +557,22 @@ static int msm_dev_impl(gpw_ctx* ctx, const Fr* scalars, const Affine<F>* points
   GPW_CHECK_LAUNCH();
   k_msm_scan_final<<<nscan_blocks, SCAN_THREADS, 0, st>>>(counts, B, block_sums, offsets, cursor);
   GPW_CHECK_LAUNCH();
-  k_msm_scatter<<<div_up(n, TPB), TPB, 0, st>>>(scalars, n, mont, c, nwin, win_lo, win_hi, cursor, sorted);
+  k_msm_digits<true><<<div_up(n, TPB), TPB, 0, st>>>(scalars, n, mont, c, nwin, win_lo, win_hi, cursor, sorted);
   GPW_CHECK_LAUNCH();
   GPW_CUDA(cudaEventRecord(ctx->ev[1], st));
   k_msm_accumulate<F><<<div_up(ntasks, MSM_ACC_THREADS), MSM_ACC_THREADS, MSM_ACC_THREADS * sizeof(XYZZ<F>), st>>>(
-      points, sorted, offsets, B, buckets, head, tail, head_key, tail_key, tail_list, ntail);
+      points, sorted, offsets, B, buckets, head, tail, tail_key, tail_list, ntail);
   GPW_CHECK_LAUNCH();
   GPW_CUDA(cudaEventRecord(ctx->ev[2], st));
-  k_msm_fixup<F><<<ctx->sm_count * 8, 128, 0, st>>>(head, tail, head_key, tail_key, tail_list, ntail, ntasks, big_list,
-                                                    nbig, buckets);
+  k_msm_fixup<F><<<ctx->sm_count * 8, 128, 0, st>>>(head, tail, offsets, tail_key, tail_list, ntail, big_list, nbig, buckets);
   GPW_CHECK_LAUNCH();
   {
     const int fb_threads = sizeof(XYZZ<F>) > 128 ? 128 : 256;
-    k_msm_fixup_big<F><<<ctx->sm_count * 2, fb_threads, fb_threads * sizeof(XYZZ<F>), st>>>(head, tail, head_key, tail_key, big_list,
-                                                                                          nbig, ntasks, buckets);
+    k_msm_fixup_big<F><<<ctx->sm_count * 2, fb_threads, fb_threads * sizeof(XYZZ<F>), st>>>(head, tail, offsets, tail_key, big_list,
+                                                                                          nbig, buckets);
   }
   GPW_CHECK_LAUNCH();
-  k_msm_window_partial<F><<<div_up((size_t)nw * nchunks, 128), 128, 0, st>>>(buckets, half, chunk, (uint32_t)nw, partials);
+  k_msm_window_partial<F><<<div_up((size_t)nw * nchunks, 128), 128, 0, st>>>(buckets, offsets, half, chunk, (uint32_t)nw, partials);
   GPW_CHECK_LAUNCH();
   k_msm_window_final<F><<<nw, 128, 128 * sizeof(XYZZ<F>), st>>>(partials, nchunks, wsums);
   GPW_CHECK_LAUNCH();

@@ -58,6 +58,12 @@ struct Segment {
   SegKind kind;
   uint32_t lo, hi;  // level range [lo, hi)
   uint32_t stream_off = 0, first_words = 0;  // SEG_NARROW: location of its staged chunk stream
+  // SEG_WIDE: the level's instruction range cut into runs of (batched Fr inversions | everything else)
+  struct Part {
+    uint32_t s, t;
+    bool inv;
+  };
+  std::vector<Part> parts;
 };
 
 constexpr uint32_t WIDE_THRESHOLD = 8192;
@@ -346,14 +352,59 @@ __global__ void __launch_bounds__(NARROW_THREADS)
   }
 }
 
-// grid.y = proof
+// grid.y = proof; instructions [s, t) of one level
 __global__ void __launch_bounds__(128)
     k_tape_wide(DevCircuit c, Fr* __restrict__ wires, size_t wire_stride, int* __restrict__ err, uint32_t* __restrict__ hist,
-                uint32_t lvl) {
+                uint32_t s, uint32_t t) {
   Fr* W = wires + (size_t)blockIdx.y * wire_stride;
-  const uint32_t s = c.level_off[lvl], t = c.level_off[lvl + 1];
   for (uint32_t i = s + blockIdx.x * blockDim.x + threadIdx.x; i < t; i += gridDim.x * blockDim.x)
     exec_instr(c, W, c.instr[i], err + blockIdx.y, hist + (size_t)blockIdx.y * 65536);
+}
+
+// The Fr inversions of a wide level - gnark's IsZero hint (one per range check) and the 2.5 M divisions of the
+// log-derivative argument - with Montgomery's trick: a thread owns INV_G instructions (strided by the grid so that
+// neighbouring lanes touch neighbouring wires), multiplies their denominators up, inverts the product once (Fermat,
+// ~380 multiplies) and peels the individual inverses off on the way back: ~27 multiplies per inversion instead of ~380.
+// Zero denominators (IsZero of 0 -> 0; a division by zero is reported and yields 0 like inv(0) = 0 did) sit out.
+constexpr int INV_G = 16;
+__global__ void __launch_bounds__(128)
+    k_tape_wide_inv(DevCircuit c, Fr* __restrict__ wires, size_t wire_stride, int* __restrict__ err, uint32_t s, uint32_t t) {
+  Fr* W = wires + (size_t)blockIdx.y * wire_stride;
+  const uint32_t nthreads = gridDim.x * blockDim.x;
+  const uint32_t first = s + blockIdx.x * blockDim.x + threadIdx.x;
+  Fr pre[INV_G], den[INV_G];
+  uint32_t zero_mask = 0;
+  int cnt = 0;
+  Fr run = Fr::one();
+#pragma unroll 1
+  for (int j = 0; j < INV_G; j++) {
+    const uint64_t i = (uint64_t)first + (uint64_t)j * nthreads;
+    if (i >= t) break;
+    const DInstr in = c.instr[i];
+    const bool is_div = (in.op_nout & 0xffu) == fe::OP_DIV;
+    Fr d = eval_le(c, W, is_div ? in.le[1] : in.le[0]);
+    if (d.is_zero()) {
+      if (is_div) atomicCAS(err + blockIdx.y, 0, ERR_DIV0);
+      zero_mask |= 1u << j;
+      d = Fr::one();
+    }
+    den[j] = d;
+    run = mul(run, d);
+    pre[j] = run;
+    cnt = j + 1;
+  }
+  if (cnt == 0) return;
+  Fr iv = inv(run);
+#pragma unroll 1
+  for (int j = cnt - 1; j >= 0; j--) {
+    const uint32_t i = first + (uint32_t)j * nthreads;
+    const DInstr in = c.instr[i];
+    Fr r = j ? mul(iv, pre[j - 1]) : iv;
+    iv = mul(iv, den[j]);
+    if ((in.op_nout & 0xffu) == fe::OP_DIV) r = mul(eval_le(c, W, in.le[0]), r);
+    if ((zero_mask >> j) & 1u) r = Fr::zero();
+    st_w(W + in.out, r);
+  }
 }
 
 __global__ void k_counts_to_wires(DevCircuit c, Fr* __restrict__ wires, size_t wire_stride, const uint32_t* __restrict__ hist) {
@@ -510,7 +561,30 @@ static int finish_compile(gpw_circuit* c) {
     const bool special = (l == count_level || l == commit_level);
     if (cnt >= WIDE_THRESHOLD || special) {
       flush(l);
-      if (cnt) c->plan.push_back({SEG_WIDE, l, l + 1});
+      if (cnt) {
+        Segment w{SEG_WIDE, l, l + 1};
+        // instructions of a level are sorted by op: runs of Fr inversions go to the batched-inverse kernel
+        auto is_inv = [&](uint32_t i) {
+          const uint32_t op = di[i].op_nout & 0xffu;
+          return op == fe::OP_INVZERO || op == fe::OP_DIV;
+        };
+        uint32_t i = level_off[l];
+        while (i < level_off[l + 1]) {
+          uint32_t j = i;
+          const bool iv = is_inv(i);
+          while (j < level_off[l + 1] && is_inv(j) == iv) j++;
+          w.parts.push_back({i, j, iv && (j - i) >= 1024});
+          i = j;
+        }
+        // merge neighbouring generic parts (short inversion runs stay on the generic path)
+        std::vector<Segment::Part> merged;
+        for (const auto& p : w.parts) {
+          if (!merged.empty() && !merged.back().inv && !p.inv) merged.back().t = p.t;
+          else merged.push_back(p);
+        }
+        w.parts = merged;
+        c->plan.push_back(w);
+      }
       if (l == count_level) c->plan.push_back({SEG_COUNT, l, l + 1});
       if (l == commit_level) c->plan.push_back({SEG_COMMIT, l, l + 1});
       run_lo = l + 1;
@@ -773,14 +847,17 @@ static int run_segments(gpw_circuit* c, Fr* wires, size_t stride, int n_proofs, 
       GPW_CHECK_LAUNCH();
       ctx->launches++;
     } else if (s.kind == SEG_WIDE) {
-      uint32_t cnt = 0;
-      // level width is known on the host from the plan construction; recompute cheaply from the API tape size bound
-      cnt = 0;
-      (void)cnt;
-      dim3 grid(ctx->sm_count * 8, n_proofs);
-      k_tape_wide<<<grid, 128, 0, st>>>(c->dc, wires, stride, err, hist, s.lo);
-      GPW_CHECK_LAUNCH();
-      ctx->launches++;
+      for (const Segment::Part& p : s.parts) {
+        if (p.inv) {
+          dim3 grid(div_up(p.t - p.s, 128 * INV_G), n_proofs);
+          k_tape_wide_inv<<<grid, 128, 0, st>>>(c->dc, wires, stride, err, p.s, p.t);
+        } else {
+          dim3 grid(std::min<int>(ctx->sm_count * 8, div_up(p.t - p.s, 128)), n_proofs);
+          k_tape_wide<<<grid, 128, 0, st>>>(c->dc, wires, stride, err, hist, p.s, p.t);
+        }
+        GPW_CHECK_LAUNCH();
+        ctx->launches++;
+      }
     } else if (s.kind == SEG_COUNT) {
       dim3 grid(65536 / 256, n_proofs);
       k_counts_to_wires<<<grid, 256, 0, st>>>(c->dc, wires, stride, hist);
