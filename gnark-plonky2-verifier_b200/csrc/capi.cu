@@ -77,6 +77,7 @@ extern "C" int gpw_ctx_create(int device, gpw_ctx** out) {
   GPW_CUDA(cudaGetDeviceProperties(&prop, device));
   c->sm_count = prop.multiProcessorCount;
   for (int i = 0; i < 4; i++) GPW_CUDA(cudaEventCreate(&c->ev[i]));
+  GPW_CUDA(cudaHostAlloc((void**)&c->pin, gpw_ctx::PIN_CAP, cudaHostAllocDefault));
   *out = c;
   return GPW_OK;
 }
@@ -88,6 +89,7 @@ extern "C" void gpw_ctx_destroy(gpw_ctx* ctx) {
   for (auto& kv : ctx->scratch)
     if (kv.second.p) cudaFree(kv.second.p);
   for (auto& kv : ctx->ntt) {
+    if (kv.second.shared) continue;
     cudaFree(kv.second.tw);
     cudaFree(kv.second.coset);
     cudaFree(kv.second.coset_inv);
@@ -95,6 +97,7 @@ extern "C" void gpw_ctx_destroy(gpw_ctx* ctx) {
   for (int i = 0; i < 4; i++)
     if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
   if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
+  if (ctx->pin) cudaFreeHost(ctx->pin);
   delete ctx;
 }
 

@@ -43,6 +43,7 @@ struct NttTables {
   void* tw = nullptr;         // w^e, e < N/2
   void* coset = nullptr;      // g^j, j < N
   void* coset_inv = nullptr;  // g^-j / N, j < N
+  bool shared = false;        // borrowed from another context of the same device (gpw_ntt_share_tables): not freed here
 };
 
 }  // namespace gpw
@@ -62,6 +63,23 @@ struct gpw_ctx {
   double msm_acc_ms_sum[2] = {0, 0}, msm_total_ms_sum[2] = {0, 0};
   uint64_t msm_points_sum[2] = {0, 0}, msm_digits_sum[2] = {0, 0}, msm_calls[2] = {0, 0};
   bool poseidon_consts_loaded = false;
+  // Pinned host staging for the small host<->device transfers of the proving path (window sums, status words,
+  // challenges). A cudaMemcpyAsync to or from PAGEABLE memory blocks inside the driver until the stream has drained -
+  // behind a 190 ms solve spine that stalls every other host thread's launches - so these go through pinned memory
+  // and wait with cudaStreamSynchronize instead.
+  uint8_t* pin = nullptr;
+  size_t pin_off = 0;
+  static constexpr size_t PIN_CAP = 1 << 16;
+  void* pin_take(size_t bytes) {
+    bytes = (bytes + 15) & ~(size_t)15;
+    if (pin_off + bytes > PIN_CAP) {  // wrap around: everything staged so far must have been consumed
+      cudaStreamSynchronize(stream);
+      pin_off = 0;
+    }
+    void* p = pin + pin_off;
+    pin_off += bytes;
+    return p;
+  }
 
   int get_scratch(const char* name, size_t bytes, void** out);
 };

@@ -577,14 +577,15 @@ static int msm_dev_impl(gpw_ctx* ctx, const Fr* scalars, const Affine<F>* points
   k_msm_window_final<F><<<nw, 128, 128 * sizeof(XYZZ<F>), st>>>(partials, nchunks, wsums);
   GPW_CHECK_LAUNCH();
   ctx->launches += 10;
-  std::vector<XYZZ<F>> hw(nw);
-  uint32_t M = 0;
-  GPW_CUDA(cudaMemcpyAsync(hw.data(), wsums, (size_t)nw * sizeof(XYZZ<F>), cudaMemcpyDeviceToHost, st));
-  GPW_CUDA(cudaMemcpyAsync(&M, offsets + B, 4, cudaMemcpyDeviceToHost, st));
+  const XYZZ<F>* hw = (const XYZZ<F>*)ctx->pin_take((size_t)nw * sizeof(XYZZ<F>));
+  const uint32_t* Mp = (const uint32_t*)ctx->pin_take(4);
+  GPW_CUDA(cudaMemcpyAsync((void*)hw, wsums, (size_t)nw * sizeof(XYZZ<F>), cudaMemcpyDeviceToHost, st));
+  GPW_CUDA(cudaMemcpyAsync((void*)Mp, offsets + B, 4, cudaMemcpyDeviceToHost, st));
   GPW_CUDA(cudaEventRecord(ctx->ev[3], st));
   GPW_CUDA(cudaStreamSynchronize(st));
   GPW_CUDA(cudaEventElapsedTime(&ctx->msm_acc_ms, ctx->ev[1], ctx->ev[2]));
   GPW_CUDA(cudaEventElapsedTime(&ctx->msm_total_ms, ctx->ev[0], ctx->ev[3]));
+  const uint32_t M = *Mp;
   ctx->msm_digits = M;
   {
     const int g = sizeof(Affine<F>) == 64 ? 0 : 1;

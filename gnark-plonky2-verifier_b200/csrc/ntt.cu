@@ -335,6 +335,24 @@ static int ntt_dev_impl(gpw_ctx* ctx, Fr* data, int L, int inverse, int coset, i
 
 using namespace gpw;
 
+// Lets `to` (another context of the same device, e.g. a proving lane) use `from`'s twiddle / coset tables for 2^logn
+// instead of building its own 0.6 GB copy. `from` must outlive `to`.
+extern "C" int gpw_ntt_share_tables(gpw_ctx* from, gpw_ctx* to, int logn) {
+  if (!from || !to || from->device != to->device || logn < 0 || logn > 27) {
+    set_error("ntt_share_tables: bad argument");
+    return GPW_EINVAL;
+  }
+  if (from == to || to->ntt.count(logn)) return GPW_OK;
+  GPW_CUDA(cudaSetDevice(from->device));
+  NttTables* tb;
+  GPW_TRY(ensure_tables(from, logn, &tb));
+  GPW_CUDA(cudaStreamSynchronize(from->stream));
+  NttTables copy = *tb;
+  copy.shared = true;
+  to->ntt[logn] = copy;
+  return GPW_OK;
+}
+
 extern "C" int gpw_ntt_fr_dev(gpw_ctx* ctx, uint64_t data_dev, int logn, int inverse, int coset, int in_bitrev,
                               int out_bitrev) {
   if (!ctx || !data_dev) {

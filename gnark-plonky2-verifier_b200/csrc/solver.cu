@@ -287,6 +287,14 @@ __device__ __forceinline__ void exec_instr(const DevCircuit& c, Fr* W, const DIn
 // exposed global-memory latency per level is the load of the operand wires.
 constexpr uint32_t CHUNK_MAX_WORDS = 6144;  // 24 KB per buffer
 constexpr size_t STAGED_SMEM_BYTES = 2 * CHUNK_MAX_WORDS * 4 + RING_SLOTS * sizeof(Fr);  // 48 KB + 64 KB
+// The spine CTA is latency bound and shares nothing: when other proofs' MSM / NTT kernels run next to it (several
+// proofs in flight, wrap.cu) their warps would saturate the SM's IMAD pipe and stretch every level of the spine. It
+// therefore asks for the SM's whole shared memory, which keeps every kernel that uses shared memory off its SM.
+constexpr size_t SPINE_EXCLUSIVE_SMEM_BYTES = 227 * 1024;
+static size_t spine_smem_bytes() {
+  static const size_t v = getenv("GPW_SPINE_SHARED_SM") ? STAGED_SMEM_BYTES : SPINE_EXCLUSIVE_SMEM_BYTES;
+  return v;
+}
 
 __device__ __forceinline__ void cp_async_16(void* smem_dst, const void* gmem_src) {
   uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
@@ -496,11 +504,6 @@ struct gpw_circuit {
   std::vector<void*> dev_allocs;
   const uint32_t* stream_dev = nullptr;
   double ring_hit_rate = 0;
-  // pipelined proving: solves may be issued on a second stream with their own scratch slot (see wrap.cu)
-  cudaStream_t stream_override = nullptr;
-  int slot = 0;
-  cudaStream_t stream() const { return stream_override ? stream_override : ctx->stream; }
-  std::string scratch_name(const char* base) const { return std::string(base) + "." + std::to_string(slot); }
   uint32_t n_inputs = 0;
   float solve_ms = 0;
 };
@@ -720,7 +723,7 @@ static int finish_compile(gpw_circuit* c) {
                 (unsigned long long)dbg_thread[op][0], (unsigned long long)dbg_thread[op][1], (unsigned long long)dbg_thread[op][2]);
     }
     GPW_TRY(upload(c, stream, &c->stream_dev));
-    GPW_CUDA(cudaFuncSetAttribute(k_tape_staged, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)STAGED_SMEM_BYTES));
+    GPW_CUDA(cudaFuncSetAttribute(k_tape_staged, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SPINE_EXCLUSIVE_SMEM_BYTES));
   }
   DevCircuit& dc = c->dc;
   GPW_TRY(upload(c, di, &dc.instr));
@@ -830,10 +833,9 @@ static const char* err_name(int e) {
 }
 
 // Runs plan segments [seg_lo, seg_hi) for n_proofs proofs.
-static int run_segments(gpw_circuit* c, Fr* wires, size_t stride, int n_proofs, int* err, uint32_t* hist, size_t seg_lo,
-                        size_t seg_hi) {
-  gpw_ctx* ctx = c->ctx;
-  cudaStream_t st = c->stream();
+static int run_segments(gpw_circuit* c, gpw_ctx* ctx, Fr* wires, size_t stride, int n_proofs, int* err, uint32_t* hist,
+                        size_t seg_lo, size_t seg_hi) {
+  cudaStream_t st = ctx->stream;
   for (size_t si = seg_lo; si < seg_hi; si++) {
     const Segment& s = c->plan[si];
     if (s.kind == SEG_NARROW) {
@@ -841,7 +843,7 @@ static int run_segments(gpw_circuit* c, Fr* wires, size_t stride, int n_proofs, 
       if (getenv("GPW_SOLVER_UNSTAGED")) {  // debugging aid: the simple per-level walker over the CSR arrays
         k_tape_narrow<<<n_proofs, NARROW_THREADS, 0, st>>>(c->dc, wires, stride, err, hist, s.lo, s.hi);
       } else {
-        k_tape_staged<<<n_proofs, NARROW_THREADS, STAGED_SMEM_BYTES, st>>>(c->dc, c->stream_dev + s.stream_off, s.first_words, wires, stride, err,
+        k_tape_staged<<<n_proofs, NARROW_THREADS, spine_smem_bytes(), st>>>(c->dc, c->stream_dev + s.stream_off, s.first_words, wires, stride, err,
                                                            hist);
       }
       GPW_CHECK_LAUNCH();
@@ -874,10 +876,14 @@ static size_t commit_segment(const gpw_circuit* c) {
   return c->plan.size();
 }
 
-static int check_err(gpw_circuit* c, int* err_dev, int n_proofs) {
-  std::vector<int> e(n_proofs);
-  GPW_CUDA(cudaMemcpyAsync(e.data(), err_dev, n_proofs * sizeof(int), cudaMemcpyDeviceToHost, c->stream()));
-  GPW_CUDA(cudaStreamSynchronize(c->stream()));
+static int check_err(gpw_ctx* ctx, int* err_dev, int n_proofs) {
+  if ((size_t)n_proofs * sizeof(int) > gpw_ctx::PIN_CAP) {
+    set_error("witness_solve: too many proofs in one call");
+    return GPW_EINVAL;
+  }
+  const int* e = (const int*)ctx->pin_take(n_proofs * sizeof(int));
+  GPW_CUDA(cudaMemcpyAsync((void*)e, err_dev, n_proofs * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  GPW_CUDA(cudaStreamSynchronize(ctx->stream));
   for (int i = 0; i < n_proofs; i++)
     if (e[i]) {
       set_error("witness solve failed for proof %d: %s", i, err_name(e[i]));
@@ -888,58 +894,46 @@ static int check_err(gpw_circuit* c, int* err_dev, int n_proofs) {
   return GPW_OK;
 }
 
+// The *_on variants run on `lane`, any context of the circuit's device: a context is a stream plus its scratch
+// memory, so several proofs of one compiled circuit can be in flight side by side (wrap.cu runs one lane per host
+// thread). The circuit itself is read-only after compilation.
+//
 // Phase 1: everything up to (not including) the commitment challenge. inputs_dev: n_proofs x n_inputs x 4 u64
 // canonical (public then secret). wires_dev: n_proofs x wire_stride Fr.
-// launch part (asynchronous on the circuit's current stream); gpw_witness_solve_phase1_finish collects the status
-extern "C" int gpw_witness_solve_phase1_launch_dev(gpw_circuit* c, uint64_t inputs_dev, int n_proofs, uint64_t wires_dev,
-                                                   size_t wire_stride) {
-  if (!c || !inputs_dev || !wires_dev || n_proofs < 1 || wire_stride < c->dc.n_wires) {
+extern "C" int gpw_witness_solve_phase1_on(gpw_circuit* c, gpw_ctx* lane, uint64_t inputs_dev, int n_proofs, uint64_t wires_dev,
+                                           size_t wire_stride) {
+  if (!c || !lane || !inputs_dev || !wires_dev || n_proofs < 1 || wire_stride < c->dc.n_wires || lane->device != c->ctx->device) {
     set_error("witness_solve: bad argument");
     return GPW_EINVAL;
   }
-  gpw_ctx* ctx = c->ctx;
+  gpw_ctx* ctx = lane;
   GPW_CUDA(cudaSetDevice(ctx->device));
   int* err;
   uint32_t* hist;
-  GPW_TRY(ctx->get_scratch(c->scratch_name("solve.err").c_str(), (size_t)n_proofs * sizeof(int), (void**)&err));
-  GPW_TRY(ctx->get_scratch(c->scratch_name("solve.hist").c_str(), (size_t)n_proofs * 65536 * 4, (void**)&hist));
-  GPW_CUDA(cudaMemsetAsync(err, 0, (size_t)n_proofs * sizeof(int), c->stream()));
-  GPW_CUDA(cudaMemsetAsync(hist, 0, (size_t)n_proofs * 65536 * 4, c->stream()));
+  GPW_TRY(ctx->get_scratch("solve.err", (size_t)n_proofs * sizeof(int), (void**)&err));
+  GPW_TRY(ctx->get_scratch("solve.hist", (size_t)n_proofs * 65536 * 4, (void**)&hist));
+  GPW_CUDA(cudaMemsetAsync(err, 0, (size_t)n_proofs * sizeof(int), ctx->stream));
+  GPW_CUDA(cudaMemsetAsync(hist, 0, (size_t)n_proofs * 65536 * 4, ctx->stream));
   dim3 grid(div_up(std::max<uint32_t>(c->n_inputs, 1), 256), n_proofs);
-  k_set_inputs<<<grid, 256, 0, c->stream()>>>((Fr*)wires_dev, wire_stride, (const uint64_t*)inputs_dev, c->n_inputs);
+  k_set_inputs<<<grid, 256, 0, ctx->stream>>>((Fr*)wires_dev, wire_stride, (const uint64_t*)inputs_dev, c->n_inputs);
   GPW_CHECK_LAUNCH();
   ctx->launches++;
-  return run_segments(c, (Fr*)wires_dev, wire_stride, n_proofs, err, hist, 0, commit_segment(c));
-}
-
-extern "C" int gpw_witness_solve_phase1_finish(gpw_circuit* c, int n_proofs) {
-  if (!c || n_proofs < 1) return GPW_EINVAL;
-  int* err;
-  GPW_TRY(c->ctx->get_scratch(c->scratch_name("solve.err").c_str(), (size_t)n_proofs * sizeof(int), (void**)&err));
-  return check_err(c, err, n_proofs);
+  GPW_TRY(run_segments(c, ctx, (Fr*)wires_dev, wire_stride, n_proofs, err, hist, 0, commit_segment(c)));
+  return check_err(ctx, err, n_proofs);
 }
 
 extern "C" int gpw_witness_solve_phase1_dev(gpw_circuit* c, uint64_t inputs_dev, int n_proofs, uint64_t wires_dev, size_t wire_stride) {
-  GPW_TRY(gpw_witness_solve_phase1_launch_dev(c, inputs_dev, n_proofs, wires_dev, wire_stride));
-  return gpw_witness_solve_phase1_finish(c, n_proofs);
-}
-
-// Selects the stream (0 = the context's) and scratch slot used by subsequent solve calls on this circuit.
-extern "C" int gpw_circuit_set_stream_slot(gpw_circuit* c, void* cuda_stream, int slot) {
-  if (!c || slot < 0 || slot > 7) return GPW_EINVAL;
-  c->stream_override = (cudaStream_t)cuda_stream;
-  c->slot = slot;
-  return GPW_OK;
+  return gpw_witness_solve_phase1_on(c, c ? c->ctx : nullptr, inputs_dev, n_proofs, wires_dev, wire_stride);
 }
 
 // Phase 2: sets the commitment challenge (one canonical Fr per proof) and runs the rest of the tape.
-extern "C" int gpw_witness_solve_phase2_dev(gpw_circuit* c, const uint64_t* challenges_canonical, int n_proofs, uint64_t wires_dev,
-                                            size_t wire_stride) {
-  if (!c || !wires_dev || n_proofs < 1) {
+extern "C" int gpw_witness_solve_phase2_on(gpw_circuit* c, gpw_ctx* lane, const uint64_t* challenges_canonical, int n_proofs,
+                                           uint64_t wires_dev, size_t wire_stride) {
+  if (!c || !lane || !wires_dev || n_proofs < 1 || lane->device != c->ctx->device) {
     set_error("witness_solve: bad argument");
     return GPW_EINVAL;
   }
-  gpw_ctx* ctx = c->ctx;
+  gpw_ctx* ctx = lane;
   GPW_CUDA(cudaSetDevice(ctx->device));
   size_t cs = commit_segment(c);
   if (cs == c->plan.size()) return GPW_OK;  // circuit has no commitment
@@ -949,44 +943,52 @@ extern "C" int gpw_witness_solve_phase2_dev(gpw_circuit* c, const uint64_t* chal
   }
   int* err;
   uint32_t* hist;
-  GPW_TRY(ctx->get_scratch(c->scratch_name("solve.err").c_str(), (size_t)n_proofs * sizeof(int), (void**)&err));
-  GPW_TRY(ctx->get_scratch(c->scratch_name("solve.hist").c_str(), (size_t)n_proofs * 65536 * 4, (void**)&hist));
-  GPW_CUDA(cudaMemsetAsync(err, 0, (size_t)n_proofs * sizeof(int), c->stream()));  // phase 1 reported its own status
+  GPW_TRY(ctx->get_scratch("solve.err", (size_t)n_proofs * sizeof(int), (void**)&err));
+  GPW_TRY(ctx->get_scratch("solve.hist", (size_t)n_proofs * 65536 * 4, (void**)&hist));
+  GPW_CUDA(cudaMemsetAsync(err, 0, (size_t)n_proofs * sizeof(int), ctx->stream));  // phase 1 reported its own status
   for (int p = 0; p < n_proofs; p++) {
-    Fr x = fe::fr_from_limbs(challenges_canonical + 4 * p);
-    GPW_CUDA(cudaMemcpyAsync((Fr*)wires_dev + (size_t)p * wire_stride + c->dc.commit_wire, &x, sizeof(Fr), cudaMemcpyHostToDevice,
-                             c->stream()));
-    GPW_CUDA(cudaStreamSynchronize(c->stream()));  // x lives on the host stack
+    Fr* x = (Fr*)ctx->pin_take(sizeof(Fr));
+    *x = fe::fr_from_limbs(challenges_canonical + 4 * p);
+    GPW_CUDA(cudaMemcpyAsync((Fr*)wires_dev + (size_t)p * wire_stride + c->dc.commit_wire, x, sizeof(Fr), cudaMemcpyHostToDevice,
+                             ctx->stream));
   }
-  GPW_TRY(run_segments(c, (Fr*)wires_dev, wire_stride, n_proofs, err, hist, cs + 1, c->plan.size()));
-  return check_err(c, err, n_proofs);
+  GPW_TRY(run_segments(c, ctx, (Fr*)wires_dev, wire_stride, n_proofs, err, hist, cs + 1, c->plan.size()));
+  return check_err(ctx, err, n_proofs);
+}
+
+extern "C" int gpw_witness_solve_phase2_dev(gpw_circuit* c, const uint64_t* challenges_canonical, int n_proofs, uint64_t wires_dev,
+                                            size_t wire_stride) {
+  return gpw_witness_solve_phase2_on(c, c ? c->ctx : nullptr, challenges_canonical, n_proofs, wires_dev, wire_stride);
 }
 
 // a, b, c evaluation vectors of one proof (may be 0 to only check). Returns GPW_EUNSAT if a constraint fails.
-extern "C" int gpw_r1cs_eval_dev(gpw_circuit* c, uint64_t wires_dev, uint64_t a_dev, uint64_t b_dev, uint64_t c_dev,
-                                 uint64_t* n_unsatisfied) {
-  if (!c || !wires_dev) {
-    set_error("r1cs_eval: null argument");
+extern "C" int gpw_r1cs_eval_on(gpw_circuit* c, gpw_ctx* lane, uint64_t wires_dev, uint64_t a_dev, uint64_t b_dev, uint64_t c_dev,
+                                uint64_t* n_unsatisfied) {
+  if (!c || !lane || !wires_dev || lane->device != c->ctx->device) {
+    set_error("r1cs_eval: bad argument");
     return GPW_EINVAL;
   }
-  gpw_ctx* ctx = c->ctx;
+  gpw_ctx* ctx = lane;
   GPW_CUDA(cudaSetDevice(ctx->device));
+  // [0..1]: unsatisfied count / first bad row; then the lane's values of the circuit's long linear expressions
   unsigned long long* bad;
-  GPW_TRY(ctx->get_scratch("solve.bad", 16, (void**)&bad));
-  unsigned long long init[2] = {0, ~0ull};
+  GPW_TRY(ctx->get_scratch("solve.bad", 64 + 8 * sizeof(Fr), (void**)&bad));
+  DevCircuit dc = c->dc;
+  dc.long_val = reinterpret_cast<Fr*>(bad + 8);
+  unsigned long long* init = (unsigned long long*)ctx->pin_take(16);
+  init[0] = 0;
+  init[1] = ~0ull;
   GPW_CUDA(cudaMemcpyAsync(bad, init, 16, cudaMemcpyHostToDevice, ctx->stream));
-  GPW_CUDA(cudaStreamSynchronize(ctx->stream));
-  if (c->dc.n_long) {
-    k_eval_long_les<<<c->dc.n_long, 1024, 0, ctx->stream>>>(c->dc, (const Fr*)wires_dev);
+  if (dc.n_long) {
+    k_eval_long_les<<<dc.n_long, 1024, 0, ctx->stream>>>(dc, (const Fr*)wires_dev);
     GPW_CHECK_LAUNCH();
     ctx->launches++;
   }
-  k_r1cs_eval<<<div_up(c->dc.n_cons, 128), 128, 0, ctx->stream>>>(c->dc, (const Fr*)wires_dev, (Fr*)a_dev, (Fr*)b_dev, (Fr*)c_dev, bad,
-                                                                  bad + 1);
+  k_r1cs_eval<<<div_up(dc.n_cons, 128), 128, 0, ctx->stream>>>(dc, (const Fr*)wires_dev, (Fr*)a_dev, (Fr*)b_dev, (Fr*)c_dev, bad, bad + 1);
   GPW_CHECK_LAUNCH();
   ctx->launches++;
-  unsigned long long res[2];
-  GPW_CUDA(cudaMemcpyAsync(res, bad, 16, cudaMemcpyDeviceToHost, ctx->stream));
+  const unsigned long long* res = (const unsigned long long*)ctx->pin_take(16);
+  GPW_CUDA(cudaMemcpyAsync((void*)res, bad, 16, cudaMemcpyDeviceToHost, ctx->stream));
   GPW_CUDA(cudaStreamSynchronize(ctx->stream));
   if (n_unsatisfied) *n_unsatisfied = res[0];
   if (res[0]) {
@@ -994,6 +996,11 @@ extern "C" int gpw_r1cs_eval_dev(gpw_circuit* c, uint64_t wires_dev, uint64_t a_
     return GPW_EUNSAT;
   }
   return GPW_OK;
+}
+
+extern "C" int gpw_r1cs_eval_dev(gpw_circuit* c, uint64_t wires_dev, uint64_t a_dev, uint64_t b_dev, uint64_t c_dev,
+                                 uint64_t* n_unsatisfied) {
+  return gpw_r1cs_eval_on(c, c ? c->ctx : nullptr, wires_dev, a_dev, b_dev, c_dev, n_unsatisfied);
 }
 
 // variables.DeserializeProofWithPublicInputs + DeserializeVerifierOnlyCircuitData (variables/deserialize.go:114-156):

@@ -5,7 +5,10 @@
 //     proof, _   := groth16.Prove(r1cs, pk, witness)            (benchmark.go:240-249)
 // with the circuit from gpw_circuit_compile_verifier standing in for frontend.Compile (benchmark.go:55) and
 // gpw_wrap_key_synthetic for groth16.DummySetup (benchmark.go:214).
+#include <atomic>
 #include <cstring>
+#include <mutex>
+#include <thread>
 
 #include "common.cuh"
 #include "ec.cuh"
@@ -16,13 +19,11 @@ struct gpw_circuit;
 extern "C" {
 int gpw_circuit_info(const gpw_circuit* c, uint64_t* info16);
 int gpw_circuit_parse_inputs(const gpw_circuit* c, const char* p, const char* v, uint64_t* out, size_t cap);
-int gpw_witness_solve_phase1_dev(gpw_circuit* c, uint64_t inputs_dev, int n_proofs, uint64_t wires_dev, size_t wire_stride);
-int gpw_witness_solve_phase2_dev(gpw_circuit* c, const uint64_t* ch, int n_proofs, uint64_t wires_dev, size_t wire_stride);
-int gpw_r1cs_eval_dev(gpw_circuit* c, uint64_t wires_dev, uint64_t a_dev, uint64_t b_dev, uint64_t c_dev, uint64_t* n_unsat);
+int gpw_witness_solve_phase1_on(gpw_circuit* c, gpw_ctx* lane, uint64_t inputs_dev, int n_proofs, uint64_t wires_dev, size_t wire_stride);
+int gpw_witness_solve_phase2_on(gpw_circuit* c, gpw_ctx* lane, const uint64_t* ch, int n_proofs, uint64_t wires_dev, size_t wire_stride);
+int gpw_r1cs_eval_on(gpw_circuit* c, gpw_ctx* lane, uint64_t wires_dev, uint64_t a_dev, uint64_t b_dev, uint64_t c_dev, uint64_t* n_unsat);
 int gpw_circuit_supports(const gpw_circuit* c, int side, uint32_t* out, size_t cap, size_t* n);
-int gpw_witness_solve_phase1_launch_dev(gpw_circuit* c, uint64_t inputs_dev, int n_proofs, uint64_t wires_dev, size_t wire_stride);
-int gpw_witness_solve_phase1_finish(gpw_circuit* c, int n_proofs);
-int gpw_circuit_set_stream_slot(gpw_circuit* c, void* cuda_stream, int slot);
+int gpw_ntt_share_tables(gpw_ctx* from, gpw_ctx* to, int logn);
 }
 
 namespace gpw {
@@ -153,8 +154,19 @@ int gpw_groth16_compute_h_dev(gpw_ctx* ctx, uint64_t a_dev, uint64_t b_dev, uint
 // groth16.DummySetup - but have exactly the shapes a real key has for THIS circuit: A / B bases only for wires that
 // occur in some L / R row (gnark's pk.InfinityA / InfinityB filtering), K bases for private non-committed wires, a
 // Pedersen commitment basis (+ its sigma-twin for the proof of knowledge) for the committed wires, Z for h.
-// proofs whose sequential first solve phase runs side by side (one SM each) in the pipelined stream
-constexpr int PIPE_GROUP = 2;
+// A proving LANE = one proof in flight: its own context (stream + scratch memory), wire vector, evaluation vectors
+// and gathered scalars. Lane 0 lives on the key's context and serves the single-proof entry points; gpw_wrap_prove_many
+// runs one host thread per lane, so that the sequential solve spine of one proof (one SM), the host-side glue of another
+// (Horner over window sums, proof assembly) and the MSMs / NTTs of the others overlap on the device.
+struct WrapLane {
+  gpw_ctx* ctx = nullptr;
+  bool own_ctx = false;
+  Fr *wires = nullptr, *va = nullptr, *vb = nullptr, *vc = nullptr, *gathA = nullptr, *gathB = nullptr;
+  uint64_t* inputs_dev = nullptr;
+  cudaEvent_t done = nullptr;
+  float t_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+};
+constexpr int WRAP_DEFAULT_LANES = 4, WRAP_MAX_LANES = 16;
 
 struct gpw_wrap_key {
   gpw_ctx* ctx = nullptr;
@@ -168,15 +180,10 @@ struct gpw_wrap_key {
   G2Affine* B2 = nullptr;
   G1Affine alpha1, beta1, delta1;
   G2Affine beta2, delta2;
-  Fr *wires = nullptr, *va = nullptr, *vb = nullptr, *vc = nullptr, *gathA = nullptr, *gathB = nullptr;
-  uint64_t* inputs_dev = nullptr;
   uint32_t n_inputs = 0;
-  // wire-vector slots (2 groups of PIPE_GROUP proofs) + side stream for pipelined proving (gpw_wrap_prove_many)
-  Fr* wires2 = nullptr;
-  uint64_t* inputs_dev2 = nullptr;
-  cudaStream_t side = nullptr;
+  std::vector<WrapLane*> lanes;
+  int want_lanes = WRAP_DEFAULT_LANES;
   uint64_t seed = 0;
-  float t_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 };
 
 static int wk_alloc(void** p, size_t bytes) {
@@ -188,15 +195,57 @@ static int wk_alloc(void** p, size_t bytes) {
   return GPW_OK;
 }
 
+static void lane_free(WrapLane* l) {
+  if (!l) return;
+  void* ps[] = {l->wires, l->va, l->vb, l->vc, l->gathA, l->gathB, l->inputs_dev};
+  for (void* p : ps) cudaFree(p);
+  if (l->done) cudaEventDestroy(l->done);
+  if (l->own_ctx) gpw_ctx_destroy(l->ctx);
+  delete l;
+}
+
+// ctx == nullptr: the lane gets a context of its own
+static int lane_create(gpw_wrap_key* k, gpw_ctx* ctx, WrapLane** out) {
+  WrapLane* l = new WrapLane();
+  if (ctx) {
+    l->ctx = ctx;
+  } else {
+    int rc = gpw_ctx_create(k->ctx->device, &l->ctx);
+    if (rc != GPW_OK) {
+      delete l;
+      return rc;
+    }
+    l->own_ctx = true;
+    rc = gpw_ntt_share_tables(k->ctx, l->ctx, k->logN);
+    if (rc != GPW_OK) {
+      lane_free(l);
+      return rc;
+    }
+  }
+  const size_t N = (size_t)1 << k->logN;
+  int rc = 0;
+  if ((rc = wk_alloc((void**)&l->wires, (size_t)k->m * sizeof(Fr))) || (rc = wk_alloc((void**)&l->va, N * sizeof(Fr))) ||
+      (rc = wk_alloc((void**)&l->vb, N * sizeof(Fr))) || (rc = wk_alloc((void**)&l->vc, N * sizeof(Fr))) ||
+      (rc = wk_alloc((void**)&l->gathA, (size_t)k->nA * sizeof(Fr))) || (rc = wk_alloc((void**)&l->gathB, (size_t)k->nB * sizeof(Fr))) ||
+      (rc = wk_alloc((void**)&l->inputs_dev, (size_t)k->n_inputs * 32))) {
+    lane_free(l);
+    return rc;
+  }
+  if (cudaEventCreateWithFlags(&l->done, cudaEventDisableTiming) != cudaSuccess) {
+    set_error("cudaEventCreate failed");
+    lane_free(l);
+    return GPW_ECUDA;
+  }
+  *out = l;
+  return GPW_OK;
+}
+
 extern "C" void gpw_wrap_key_free(gpw_wrap_key* k) {
   if (!k) return;
   cudaSetDevice(k->ctx->device);
-  void* ps[] = {k->suppA, k->suppB, k->A, k->B1, k->K, k->Z, k->CK, k->CKs, k->B2, k->wires, k->va, k->vb, k->vc, k->gathA, k->gathB,
-                k->inputs_dev};
+  for (WrapLane* l : k->lanes) lane_free(l);
+  void* ps[] = {k->suppA, k->suppB, k->A, k->B1, k->K, k->Z, k->CK, k->CKs, k->B2};
   for (void* p : ps) cudaFree(p);
-  cudaFree(k->wires2);
-  cudaFree(k->inputs_dev2);
-  if (k->side) cudaStreamDestroy(k->side);
   delete k;
 }
 
@@ -242,13 +291,19 @@ extern "C" int gpw_wrap_key_synthetic(gpw_ctx* ctx, gpw_circuit* circ, uint64_t 
       (rc = wk_alloc((void**)&k->A, na * sizeof(G1Affine))) || (rc = wk_alloc((void**)&k->B1, nb * sizeof(G1Affine))) ||
       (rc = wk_alloc((void**)&k->B2, nb * sizeof(G2Affine))) || (rc = wk_alloc((void**)&k->K, (size_t)k->m * sizeof(G1Affine))) ||
       (rc = wk_alloc((void**)&k->Z, N * sizeof(G1Affine))) || (rc = wk_alloc((void**)&k->CK, (size_t)k->n_committed * sizeof(G1Affine))) ||
-      (rc = wk_alloc((void**)&k->CKs, (size_t)k->n_committed * sizeof(G1Affine))) || (rc = wk_alloc((void**)&k->wires, (size_t)k->m * sizeof(Fr))) ||
-      (rc = wk_alloc((void**)&k->va, N * sizeof(Fr))) || (rc = wk_alloc((void**)&k->vb, N * sizeof(Fr))) ||
-      (rc = wk_alloc((void**)&k->vc, N * sizeof(Fr))) || (rc = wk_alloc((void**)&k->gathA, na * sizeof(Fr))) ||
-      (rc = wk_alloc((void**)&k->gathB, nb * sizeof(Fr))) || (rc = wk_alloc((void**)&k->inputs_dev, (size_t)k->n_inputs * 32))) {
+      (rc = wk_alloc((void**)&k->CKs, (size_t)k->n_committed * sizeof(G1Affine)))) {
     gpw_wrap_key_free(k);
     return rc;
   }
+  {
+    WrapLane* l0 = nullptr;
+    if ((rc = lane_create(k, ctx, &l0))) {
+      gpw_wrap_key_free(k);
+      return rc;
+    }
+    k->lanes.push_back(l0);
+  }
+  if (const char* e = getenv("GPW_WRAP_LANES")) k->want_lanes = std::max(1, std::min(WRAP_MAX_LANES, atoi(e)));
   GPW_CUDA(cudaMemcpy(k->suppA, sa.data(), na * 4, cudaMemcpyHostToDevice));
   GPW_CUDA(cudaMemcpy(k->suppB, sb.data(), nb * 4, cudaMemcpyHostToDevice));
   GPW_TRY(gpw_ec_generator_multiples_dev(ctx, 1, 1, na, (uint64_t)k->A));
@@ -276,7 +331,17 @@ extern "C" int gpw_wrap_key_info(const gpw_wrap_key* k, uint64_t* info8) {
   return GPW_OK;
 }
 
-extern "C" uint64_t gpw_wrap_key_wires_dev(const gpw_wrap_key* k) { return k ? (uint64_t)k->wires : 0; }
+extern "C" uint64_t gpw_wrap_key_wires_dev(const gpw_wrap_key* k) { return k ? (uint64_t)k->lanes[0]->wires : 0; }
+
+// Number of proofs gpw_wrap_prove_many keeps in flight (default 4; each lane holds ~1.5 GB of vectors plus its MSM scratch).
+extern "C" int gpw_wrap_set_lanes(gpw_wrap_key* k, int n) {
+  if (!k || n < 1 || n > WRAP_MAX_LANES) {
+    set_error("wrap_set_lanes: n must be in [1, %d]", WRAP_MAX_LANES);
+    return GPW_EINVAL;
+  }
+  k->want_lanes = n;
+  return GPW_OK;
+}
 
 static void ser_g1_be(const G1Affine& p, uint8_t out[64]) {
   Fp x = from_mont(p.x), y = from_mont(p.y);
@@ -291,9 +356,33 @@ static void ser_g1_be(const G1Affine& p, uint8_t out[64]) {
 // out_proof (u64 x 64): Ar (8) | Bs (16) | Krs (8) | commitment D (8) | commitment PoK (8) | challenge (4, canonical) |
 //                       n_unsatisfied (1) | reserved.  If check != 0 the R1CS is verified on the device (a*b == c on every
 // row) and GPW_EUNSAT is returned on failure.
+static int wrap_stage2(gpw_wrap_key* k, WrapLane* L, const uint64_t* r_canon, const uint64_t* s_canon, int check, uint64_t* out_proof);
+
+// solve phase 1 + everything after it for one proof on lane L (inputs already on the device)
+static int wrap_one(gpw_wrap_key* k, WrapLane* L, uint64_t inputs_dev, const uint64_t* r_canon, const uint64_t* s_canon, int check,
+                    uint64_t* out_proof) {
+  cudaStream_t st = L->ctx->stream;
+  cudaEvent_t e0, e1;
+  GPW_CUDA(cudaEventCreate(&e0));
+  GPW_CUDA(cudaEventCreate(&e1));
+  GPW_CUDA(cudaEventRecord(e0, st));
+  int rc = gpw_witness_solve_phase1_on(k->circ, L->ctx, inputs_dev, 1, (uint64_t)L->wires, k->m);
+  float t1 = 0;
+  if (rc == GPW_OK) {
+    cudaEventRecord(e1, st);
+    cudaEventSynchronize(e1);
+    cudaEventElapsedTime(&t1, e0, e1);
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  GPW_TRY(rc);
+  rc = wrap_stage2(k, L, r_canon, s_canon, check, out_proof);
+  L->t_ms[0] = t1;
+  return rc;
+}
+
 extern "C" int gpw_wrap_prove_dev(gpw_wrap_key* k, uint64_t inputs_dev, const uint64_t* r_canon, const uint64_t* s_canon, int check,
                                   uint64_t* out_proof);
-static int wrap_stage2(gpw_wrap_key* k, Fr* wires, const uint64_t* r_canon, const uint64_t* s_canon, int check, uint64_t* out_proof);
 
 extern "C" int gpw_wrap_prove(gpw_wrap_key* k, const uint64_t* inputs, const uint64_t* r_canon, const uint64_t* s_canon, int check,
                               uint64_t* out_proof) {
@@ -301,9 +390,10 @@ extern "C" int gpw_wrap_prove(gpw_wrap_key* k, const uint64_t* inputs, const uin
     set_error("wrap_prove: null argument");
     return GPW_EINVAL;
   }
+  WrapLane* L = k->lanes[0];
   GPW_CUDA(cudaSetDevice(k->ctx->device));
-  GPW_CUDA(cudaMemcpyAsync(k->inputs_dev, inputs, (size_t)k->n_inputs * 32, cudaMemcpyHostToDevice, k->ctx->stream));
-  return gpw_wrap_prove_dev(k, (uint64_t)k->inputs_dev, r_canon, s_canon, check, out_proof);
+  GPW_CUDA(cudaMemcpyAsync(L->inputs_dev, inputs, (size_t)k->n_inputs * 32, cudaMemcpyHostToDevice, L->ctx->stream));
+  return gpw_wrap_prove_dev(k, (uint64_t)L->inputs_dev, r_canon, s_canon, check, out_proof);
 }
 
 // Same with the parsed inputs already resident on the device (n_inputs x 4 u64 canonical).
@@ -313,32 +403,16 @@ extern "C" int gpw_wrap_prove_dev(gpw_wrap_key* k, uint64_t inputs_dev, const ui
     set_error("wrap_prove: null argument");
     return GPW_EINVAL;
   }
-  gpw_ctx* ctx = k->ctx;
-  GPW_CUDA(cudaSetDevice(ctx->device));
-  cudaStream_t st = ctx->stream;
-  const size_t N = (size_t)1 << k->logN;
-  cudaEvent_t e0, e1;
-  GPW_CUDA(cudaEventCreate(&e0));
-  GPW_CUDA(cudaEventCreate(&e1));
-  GPW_CUDA(cudaEventRecord(e0, st));
-  GPW_TRY(gpw_witness_solve_phase1_dev(k->circ, inputs_dev, 1, (uint64_t)k->wires, k->m));
-  GPW_CUDA(cudaEventRecord(e1, st));
-  GPW_CUDA(cudaEventSynchronize(e1));
-  float t1 = 0;
-  GPW_CUDA(cudaEventElapsedTime(&t1, e0, e1));
-  cudaEventDestroy(e0);
-  cudaEventDestroy(e1);
-  int rc = wrap_stage2(k, k->wires, r_canon, s_canon, check, out_proof);
-  k->t_ms[0] = t1;
-  (void)N;
-  return rc;
+  GPW_CUDA(cudaSetDevice(k->ctx->device));
+  return wrap_one(k, k->lanes[0], inputs_dev, r_canon, s_canon, check, out_proof);
 }
 
 // Everything after the first solve phase, on the context's stream: commitment, second solve phase, R1CS evaluation,
 // computeH, MSMs, assembly. `wires` = the proof's wire vector (phase 1 complete).
-static int wrap_stage2(gpw_wrap_key* k, Fr* wires, const uint64_t* r_canon, const uint64_t* s_canon, int check, uint64_t* out_proof) {
-  gpw_ctx* ctx = k->ctx;
+static int wrap_stage2(gpw_wrap_key* k, WrapLane* L, const uint64_t* r_canon, const uint64_t* s_canon, int check, uint64_t* out_proof) {
+  gpw_ctx* ctx = L->ctx;
   cudaStream_t st = ctx->stream;
+  Fr* wires = L->wires;
   const size_t N = (size_t)1 << k->logN;
   cudaEvent_t ev[7];
   for (auto& e : ev) GPW_CUDA(cudaEventCreate(&e));
@@ -365,31 +439,31 @@ static int wrap_stage2(gpw_wrap_key* k, Fr* wires, const uint64_t* r_canon, cons
     hash_to_fr(ser, 64, "bsb22-commitment", X);
   }
   GPW_CUDA(cudaEventRecord(ev[2], st));
-  GPW_TRY(gpw_witness_solve_phase2_dev(k->circ, X, 1, (uint64_t)wires, k->m));
+  GPW_TRY(gpw_witness_solve_phase2_on(k->circ, ctx, X, 1, (uint64_t)wires, k->m));
   GPW_CUDA(cudaEventRecord(ev[3], st));
   // R1CS evaluation vectors, zero padded to the FFT domain
-  GPW_CUDA(cudaMemsetAsync(k->va, 0, N * sizeof(Fr), st));
-  GPW_CUDA(cudaMemsetAsync(k->vb, 0, N * sizeof(Fr), st));
-  GPW_CUDA(cudaMemsetAsync(k->vc, 0, N * sizeof(Fr), st));
+  GPW_CUDA(cudaMemsetAsync(L->va, 0, N * sizeof(Fr), st));
+  GPW_CUDA(cudaMemsetAsync(L->vb, 0, N * sizeof(Fr), st));
+  GPW_CUDA(cudaMemsetAsync(L->vc, 0, N * sizeof(Fr), st));
   uint64_t n_bad = 0;
-  int rc = gpw_r1cs_eval_dev(k->circ, (uint64_t)wires, (uint64_t)k->va, (uint64_t)k->vb, (uint64_t)k->vc, &n_bad);
+  int rc = gpw_r1cs_eval_on(k->circ, ctx, (uint64_t)wires, (uint64_t)L->va, (uint64_t)L->vb, (uint64_t)L->vc, &n_bad);
   if (rc != GPW_OK && (check || rc != GPW_EUNSAT)) return rc;
   GPW_CUDA(cudaEventRecord(ev[4], st));
-  GPW_TRY(gpw_groth16_compute_h_dev(ctx, (uint64_t)k->va, (uint64_t)k->vb, (uint64_t)k->vc, k->logN));
+  GPW_TRY(gpw_groth16_compute_h_dev(ctx, (uint64_t)L->va, (uint64_t)L->vb, (uint64_t)L->vc, k->logN));
   GPW_CUDA(cudaEventRecord(ev[5], st));
   // gather the scalars of the A / B supports
-  k_gather_fr<<<div_up(k->nA, 256), 256, 0, st>>>(wires, k->suppA, k->nA, k->gathA);
+  k_gather_fr<<<div_up(k->nA, 256), 256, 0, st>>>(wires, k->suppA, k->nA, L->gathA);
   GPW_CHECK_LAUNCH();
-  k_gather_fr<<<div_up(k->nB, 256), 256, 0, st>>>(wires, k->suppB, k->nB, k->gathB);
+  k_gather_fr<<<div_up(k->nB, 256), 256, 0, st>>>(wires, k->suppB, k->nB, L->gathB);
   GPW_CHECK_LAUNCH();
   ctx->launches += 2;
   G1Affine mA, mB1, mK1, mK2, mZ;
   G2Affine mB2;
-  GPW_TRY(gpw_msm_g1_dev(ctx, (uint64_t)k->gathA, (uint64_t)k->A, k->nA, 1, 0, 0, 0, (uint64_t*)&mA));
+  GPW_TRY(gpw_msm_g1_dev(ctx, (uint64_t)L->gathA, (uint64_t)k->A, k->nA, 1, 0, 0, 0, (uint64_t*)&mA));
   report("A", k->nA);
-  GPW_TRY(gpw_msm_g1_dev(ctx, (uint64_t)k->gathB, (uint64_t)k->B1, k->nB, 1, 0, 0, 0, (uint64_t*)&mB1));
+  GPW_TRY(gpw_msm_g1_dev(ctx, (uint64_t)L->gathB, (uint64_t)k->B1, k->nB, 1, 0, 0, 0, (uint64_t*)&mB1));
   report("B1", k->nB);
-  GPW_TRY(gpw_msm_g2_dev(ctx, (uint64_t)k->gathB, (uint64_t)k->B2, k->nB, 1, 0, 0, 0, (uint64_t*)&mB2));
+  GPW_TRY(gpw_msm_g2_dev(ctx, (uint64_t)L->gathB, (uint64_t)k->B2, k->nB, 1, 0, 0, 0, (uint64_t*)&mB2));
   report("B2", k->nB);
   // K: private wires that are not committed = [1 + n_pub, limb_start) U [limb_start + n_committed, m), minus the challenge wire
   const uint32_t k_lo = 1 + k->n_pub;
@@ -400,11 +474,11 @@ static int wrap_stage2(gpw_wrap_key* k, Fr* wires, const uint64_t* r_canon, cons
   if (c_hi < k->m)
     GPW_TRY(gpw_msm_g1_dev(ctx, (uint64_t)(wires + c_hi), (uint64_t)(k->K + c_hi), k->m - c_hi, 1, 0, 0, 0, (uint64_t*)&mK2));
   if (c_hi < k->m) report("K2", k->m - c_hi);
-  GPW_TRY(gpw_msm_g1_dev(ctx, (uint64_t)k->va, (uint64_t)k->Z, N - 1, 1, 0, 0, 0, (uint64_t*)&mZ));
+  GPW_TRY(gpw_msm_g1_dev(ctx, (uint64_t)L->va, (uint64_t)k->Z, N - 1, 1, 0, 0, 0, (uint64_t*)&mZ));
   report("Z", N - 1);
   GPW_CUDA(cudaEventRecord(ev[6], st));
   GPW_CUDA(cudaStreamSynchronize(st));
-  for (int i = 0; i < 6; i++) GPW_CUDA(cudaEventElapsedTime(&k->t_ms[i], ev[i], ev[i + 1]));
+  for (int i = 0; i < 6; i++) GPW_CUDA(cudaEventElapsedTime(&L->t_ms[i], ev[i], ev[i + 1]));
   for (auto& e : ev) cudaEventDestroy(e);
   // assembly (gnark groth16.Prove)
   uint32_t rw[8], sw[8];
@@ -448,56 +522,69 @@ static int wrap_stage2(gpw_wrap_key* k, Fr* wires, const uint64_t* r_canon, cons
 // ms: [inputs + solve phase 1, commitment MSMs + hash, solve phase 2, R1CS evaluation, computeH, gathers + MSMs]
 extern "C" int gpw_wrap_last_stats(const gpw_wrap_key* k, float* ms6) {
   if (!k || !ms6) return GPW_EINVAL;
-  for (int i = 0; i < 6; i++) ms6[i] = k->t_ms[i];
+  for (int i = 0; i < 6; i++) ms6[i] = k->lanes[0]->t_ms[i];
   return GPW_OK;
 }
 
-// A stream of n proofs with software pipelining: the sequential first solve phase of proof i+1 (one persistent CTA on
-// one SM, plus a few wide launches) runs on a side stream while the GPU-filling part of proof i (commitment MSMs,
-// log-derivative divisions, R1CS evaluation, NTTs, MSMs) runs on the context's stream. Two wire-vector slots.
-// inputs: n x n_inputs x 4 u64 canonical (host); r, s: n x 4 u64 each; out: n x 64 u64.
+// A stream of n proofs, `lanes` of them in flight at a time (gpw_wrap_set_lanes / GPW_WRAP_LANES, default 4): one host
+// thread per lane takes the next unproved input, copies it to the device and runs the whole wrap on the lane's own
+// stream. Proofs are independent, so nothing is exchanged between lanes; the device interleaves their kernels.
+// inputs: n x n_inputs x 4 u64 canonical (host or device memory); r, s: n x 4 u64 each (host); out: n x 64 u64 (host).
 extern "C" int gpw_wrap_prove_many(gpw_wrap_key* k, const uint64_t* inputs, int n, const uint64_t* r_canon, const uint64_t* s_canon,
                                    int check, uint64_t* out_proofs) {
   if (!k || !inputs || n < 1 || !r_canon || !s_canon || !out_proofs) {
     set_error("wrap_prove_many: bad argument");
     return GPW_EINVAL;
   }
-  gpw_ctx* ctx = k->ctx;
-  GPW_CUDA(cudaSetDevice(ctx->device));
-  // Proofs are solved in GROUPS of G: one launch runs the spines of G proofs on G SMs (they take as long as one),
-  // while the G proofs of the previous group go through stage 2 one after the other. Two groups of wire slots.
-  constexpr int G = PIPE_GROUP;
-  if (!k->side) {
-    GPW_CUDA(cudaStreamCreateWithFlags(&k->side, cudaStreamNonBlocking));
-    GPW_TRY(wk_alloc((void**)&k->wires2, (size_t)k->m * sizeof(Fr) * (2 * G)));
-    GPW_TRY(wk_alloc((void**)&k->inputs_dev2, (size_t)k->n_inputs * 32 * (2 * G)));
+  GPW_CUDA(cudaSetDevice(k->ctx->device));
+  const int n_lanes = std::min(k->want_lanes, n);
+  while ((int)k->lanes.size() < n_lanes) {
+    WrapLane* l = nullptr;
+    GPW_TRY(lane_create(k, nullptr, &l));
+    k->lanes.push_back(l);
   }
   const size_t in_words = (size_t)k->n_inputs * 4;
-  auto group_wires = [&](int g) { return k->wires2 + (size_t)(g & 1) * G * k->m; };
-  auto group_inputs = [&](int g) { return k->inputs_dev2 + (size_t)(g & 1) * G * in_words; };
-  const int n_groups = (n + G - 1) / G;
-  auto group_size = [&](int g) { return std::min(G, n - g * G); };
-  auto launch1 = [&](int g) -> int {
-    GPW_TRY(gpw_circuit_set_stream_slot(k->circ, k->side, g & 1));
-    GPW_CUDA(cudaMemcpyAsync(group_inputs(g), inputs + (size_t)g * G * in_words, in_words * 8 * group_size(g), cudaMemcpyHostToDevice,
-                             k->side));
-    return gpw_witness_solve_phase1_launch_dev(k->circ, (uint64_t)group_inputs(g), group_size(g), (uint64_t)group_wires(g), k->m);
-  };
-  int rc = launch1(0);
-  for (int g = 0; g < n_groups && rc == GPW_OK; g++) {
-    rc = gpw_circuit_set_stream_slot(k->circ, k->side, g & 1);
-    if (rc == GPW_OK) rc = gpw_witness_solve_phase1_finish(k->circ, group_size(g));  // waits for the side stream
-    if (rc == GPW_OK && g + 1 < n_groups) rc = launch1(g + 1);                         // overlaps with stage 2 below
-    if (rc != GPW_OK) break;
-    gpw_circuit_set_stream_slot(k->circ, nullptr, 2 + (g & 1));
-    for (int j = 0; j < group_size(g) && rc == GPW_OK; j++) {
-      const int i = g * G + j;
-      rc = wrap_stage2(k, group_wires(g) + (size_t)j * k->m, r_canon + 4 * i, s_canon + 4 * i, check, out_proofs + 64 * (size_t)i);
+  std::atomic<int> next{0};
+  std::atomic<int> first_rc{GPW_OK};
+  std::mutex err_mu;
+  std::string err_text;
+  auto worker = [&](WrapLane* L) {
+    cudaSetDevice(k->ctx->device);
+    for (;;) {
+      const int i = next.fetch_add(1);
+      if (i >= n || first_rc.load() != GPW_OK) break;
+      int rc = GPW_OK;
+      if (cudaMemcpyAsync(L->inputs_dev, inputs + (size_t)i * in_words, in_words * 8, cudaMemcpyDefault, L->ctx->stream) != cudaSuccess) {
+        set_error("wrap_prove_many: input copy failed: %s", cudaGetErrorString(cudaGetLastError()));
+        rc = GPW_ECUDA;
+      }
+      if (rc == GPW_OK) rc = wrap_one(k, L, (uint64_t)L->inputs_dev, r_canon + 4 * i, s_canon + 4 * i, check, out_proofs + 64 * (size_t)i);
+      if (rc == GPW_OK && getenv("GPW_DEBUG_LANES"))
+        fprintf(stderr, "[gpw lanes] proof %2d: solve1 %6.1f | commit %5.1f solve2 %5.1f r1cs %5.1f H %5.1f msm %6.1f ms\n", i, L->t_ms[0],
+                L->t_ms[1], L->t_ms[2], L->t_ms[3], L->t_ms[4], L->t_ms[5]);
+      if (rc != GPW_OK) {
+        int expected = GPW_OK;
+        if (first_rc.compare_exchange_strong(expected, rc)) {
+          std::lock_guard<std::mutex> g(err_mu);
+          err_text = std::string("proof ") + std::to_string(i) + ": " + gpw_last_error();  // set_error is thread-local
+        }
+        break;
+      }
     }
+    cudaEventRecord(L->done, L->ctx->stream);
+  };
+  std::vector<std::thread> threads;
+  for (int j = 1; j < n_lanes; j++) threads.emplace_back(worker, k->lanes[j]);
+  worker(k->lanes[0]);
+  for (auto& t : threads) t.join();
+  // order the caller's stream after every lane (lane 0 already is the caller's stream)
+  for (int j = 1; j < n_lanes; j++) {
+    cudaStreamWaitEvent(k->ctx->stream, k->lanes[j]->done, 0);
+    k->ctx->launches += k->lanes[j]->ctx->launches;
+    k->lanes[j]->ctx->launches = 0;
   }
-  cudaStreamSynchronize(k->side);
-  gpw_circuit_set_stream_slot(k->circ, nullptr, 0);
-  return rc;
+  if (first_rc.load() != GPW_OK) set_error("%s", err_text.c_str());
+  return first_rc.load();
 }
 
 extern "C" int gpw_hash_to_fr(const uint8_t* msg, size_t len, const char* dst, uint64_t* out_canonical) {

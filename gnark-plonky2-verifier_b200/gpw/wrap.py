@@ -32,9 +32,11 @@ _NEW = {
     "gpw_wrap_prove_dev": (C.c_int, [_vp, C.c_uint64, _vp, _vp, C.c_int, _vp]),
     "gpw_msm_cumulative_stats": (C.c_int, [_vp, C.c_int, C.c_int, _vp]),
     "gpw_wrap_prove_many": (C.c_int, [_vp, _vp, C.c_int, _vp, _vp, C.c_int, _vp]),
-    "gpw_witness_solve_phase1_launch_dev": (C.c_int, [_vp, C.c_uint64, C.c_int, C.c_uint64, C.c_size_t]),
-    "gpw_witness_solve_phase1_finish": (C.c_int, [_vp, C.c_int]),
-    "gpw_circuit_set_stream_slot": (C.c_int, [_vp, _vp, C.c_int]),
+    "gpw_witness_solve_phase1_on": (C.c_int, [_vp, _vp, C.c_uint64, C.c_int, C.c_uint64, C.c_size_t]),
+    "gpw_witness_solve_phase2_on": (C.c_int, [_vp, _vp, _vp, C.c_int, C.c_uint64, C.c_size_t]),
+    "gpw_r1cs_eval_on": (C.c_int, [_vp, _vp, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64, _vp]),
+    "gpw_wrap_set_lanes": (C.c_int, [_vp, C.c_int]),
+    "gpw_ntt_share_tables": (C.c_int, [_vp, _vp, C.c_int]),
     "gpw_wrap_last_stats": (C.c_int, [_vp, _vp]),
     "gpw_hash_to_fr": (C.c_int, [C.c_char_p, C.c_size_t, C.c_char_p, _vp]),
 }
@@ -173,8 +175,12 @@ class WrapKey:
             _check(_lib.gpw_wrap_prove(self._h, _vp(inputs_ptr), _p(r), _p(s), int(check), _p(out)))
         return self._unpack(out)
 
+    def set_lanes(self, n):
+        """proofs gpw_wrap_prove_many keeps in flight (one host thread + stream + scratch each)"""
+        _check(_lib.gpw_wrap_set_lanes(self._h, int(n)))
+
     def prove_many(self, inputs_ptr, n, r_ints, s_ints, check=True):
-        """n proofs, software-pipelined (gpw_wrap_prove_many). inputs_ptr: host address of n x n_inputs x 4 u64."""
+        """n independent proofs, several in flight (gpw_wrap_prove_many). inputs_ptr: host address of n x n_inputs x 4 u64."""
         r = ints_to_limbs(list(r_ints))
         s = ints_to_limbs(list(s_ints))
         out = np.zeros((n, 64), dtype=np.uint64)

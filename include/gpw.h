@@ -99,6 +99,8 @@ int gpw_msm_cumulative_stats(gpw_ctx* ctx, int group, int reset, double* out5);
  * DIT: bitrev->nat; nat->nat adds one permutation pass).                                       */
 int gpw_ntt_fr(gpw_ctx* ctx, uint64_t* data, int logn, int inverse, int coset, int in_bitrev, int out_bitrev);
 int gpw_ntt_fr_dev(gpw_ctx* ctx, uint64_t data_dev, int logn, int inverse, int coset, int in_bitrev, int out_bitrev);
+/* `to` (another context of the same device) borrows `from`'s twiddle / coset tables for 2^logn; `from` must outlive it. */
+int gpw_ntt_share_tables(gpw_ctx* from, gpw_ctx* to, int logn);
 
 /* ---- Groth16 prover glue (gnark backend/groth16 bn254 Prove, benchmark.go:249) -----------
  * computeH pointwise step on the coset: a[i] = (a[i] * b[i] - c[i]) * k, all Fr Montgomery, device.   */
@@ -150,13 +152,15 @@ int gpw_circuit_parse_inputs(const gpw_circuit* c, const char* proof_with_public
 int gpw_witness_solve_phase1_dev(gpw_circuit* c, uint64_t inputs_dev, int n_proofs, uint64_t wires_dev, size_t wire_stride);
 int gpw_witness_solve_phase2_dev(gpw_circuit* c, const uint64_t* challenges_canonical, int n_proofs, uint64_t wires_dev,
                                  size_t wire_stride);
-/* phase 1 split into an asynchronous launch and a status-collecting finish; gpw_circuit_set_stream_slot selects the
- * stream (0 = the context's) and scratch slot (0..7) that subsequent solve calls on the circuit use.               */
-int gpw_witness_solve_phase1_launch_dev(gpw_circuit* c, uint64_t inputs_dev, int n_proofs, uint64_t wires_dev, size_t wire_stride);
-int gpw_witness_solve_phase1_finish(gpw_circuit* c, int n_proofs);
-int gpw_circuit_set_stream_slot(gpw_circuit* c, void* cuda_stream, int slot);
 /* a = L.w, b = R.w, c = O.w (device, >= n_constraints Fr each; pass 0 to only check). GPW_EUNSAT if a*b != c somewhere. */
 int gpw_r1cs_eval_dev(gpw_circuit* c, uint64_t wires_dev, uint64_t a_dev, uint64_t b_dev, uint64_t c_dev, uint64_t* n_unsatisfied);
+/* The same three calls on `lane`, any other context of the circuit's device (a context = a stream + its scratch
+ * memory): the compiled circuit is read-only, so several proofs can be solved side by side, one per lane.          */
+int gpw_witness_solve_phase1_on(gpw_circuit* c, gpw_ctx* lane, uint64_t inputs_dev, int n_proofs, uint64_t wires_dev, size_t wire_stride);
+int gpw_witness_solve_phase2_on(gpw_circuit* c, gpw_ctx* lane, const uint64_t* challenges_canonical, int n_proofs, uint64_t wires_dev,
+                                size_t wire_stride);
+int gpw_r1cs_eval_on(gpw_circuit* c, gpw_ctx* lane, uint64_t wires_dev, uint64_t a_dev, uint64_t b_dev, uint64_t c_dev,
+                     uint64_t* n_unsatisfied);
 int gpw_circuit_supports(const gpw_circuit* c, int side, uint32_t* out, size_t cap, size_t* n);
 /* output wires of every tape instruction of one opcode (1 MulAddHint, 2 ReduceHint, 3 InverseHint, 4 SplitLimbsHint),
  * in the order the reference's gadget code requests them.                                                       */
@@ -176,10 +180,13 @@ int gpw_wrap_prove(gpw_wrap_key* k, const uint64_t* inputs, const uint64_t* r_ca
 /* same, with the parsed inputs already resident on the device (n_inputs x 4 u64 canonical) */
 int gpw_wrap_prove_dev(gpw_wrap_key* k, uint64_t inputs_dev, const uint64_t* r_canonical, const uint64_t* s_canonical, int check,
                        uint64_t* out_proof);
-/* A stream of n proofs, software-pipelined: the sequential first solve phase of proof i+1 (one SM) overlaps the
- * GPU-filling remainder of proof i. inputs: n x n_inputs x 4 u64 (host); r, s: n x 4 u64; out: n x 64 u64.        */
+/* A stream of n independent proofs with several of them in flight: one host thread + stream + scratch ("lane") per
+ * in-flight proof, so that the sequential solve spine of one proof (one SM) and the host glue of another overlap the
+ * MSMs / NTTs of the rest. inputs: n x n_inputs x 4 u64 (host or device); r, s: n x 4 u64; out: n x 64 u64. Blocking.
+ * gpw_wrap_set_lanes: proofs in flight (default 4, env GPW_WRAP_LANES; 1 = strictly one after the other).           */
 int gpw_wrap_prove_many(gpw_wrap_key* k, const uint64_t* inputs, int n, const uint64_t* r_canonical, const uint64_t* s_canonical,
                         int check, uint64_t* out_proofs);
+int gpw_wrap_set_lanes(gpw_wrap_key* k, int n);
 int gpw_wrap_last_stats(const gpw_wrap_key* k, float* ms6);
 int gpw_hash_to_fr(const uint8_t* msg, size_t len, const char* dst, uint64_t* out_canonical);
 
