@@ -293,9 +293,9 @@ def main():
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      # dram__bytes_read.sum + dram__bytes_write.sum of one captured launch (profiles/r01_msm_accumulate_ncu.md):
-                     # 2 528 030 full-width points, 16 non-zero digits each -> 3.22 GB vs 243 MB algorithmic: windowed Pippenger
+                     # 2 528 030 full-width points, 16 non-zero digits each -> 3.19 GB vs 243 MB algorithmic: windowed Pippenger
                      # reads every base once per non-zero digit
-                     "traffic": 3221501528, "traffic_launch_points": 2528030,
+                     "traffic": 3185633760, "traffic_launch_points": 2528030,
                      "peak_source": peak_kind, "kernel": "k_msm_accumulate<Fp> (MSM G1 bucket accumulation)",
                      "launches_per_step": g1["calls"] / n_lat, "avg_launch_ms": avg_ms,
                      "avg_points_per_launch": g1["points"] / max(g1["calls"], 1),
