@@ -190,6 +190,8 @@ std::vector<Variable> API::NewHint(Op op, uint32_t nout, const Variable* a, cons
   outs.reserve(nout);
   for (uint32_t i = 0; i < nout; i++) outs.push_back(wire_var(new_wire(lvl)));
   tape_.push_back({(uint8_t)op, first, nout, {le[0], le[1], le[2]}, lvl});
+  if (op == OP_HINT_MULADD || op == OP_HINT_REDUCE || op == OP_HINT_GLINV || op == OP_HINT_SPLIT)
+    for (uint32_t i = 0; i < nout; i++) hint_log_.push_back({(uint8_t)op, first + i});
   switch (op) {
     case OP_HINT_MULADD: counts_.muladd++; break;
     case OP_HINT_REDUCE: counts_.reduce++; break;
@@ -328,6 +330,68 @@ void API::FuseAsMacro(Op op, size_t tape_begin, uint32_t wire_begin, const Varia
   tape_.push_back(m);
 }
 
+uint32_t API::intern_raw_le(const std::vector<Term>& terms) {
+  const uint32_t id = (uint32_t)le_off_.size() - 1;
+  for (const Term& t : terms) {
+    le_wire_.push_back(t.wire);
+    le_coeff_.push_back(intern_coeff(t.coeff));
+  }
+  le_off_.push_back((uint32_t)le_wire_.size());
+  return id;
+}
+
+void API::BeginFuse() {
+  if (fuse_active_) throw std::logic_error("BeginFuse: already capturing");
+  fuse_active_ = true;
+  fuse_begin_ = tape_.size();
+  fuse_marked_.clear();
+}
+
+void API::FuseMarkSince(size_t tape_before) {
+  if (!fuse_active_) return;
+  for (size_t i = tape_before; i < tape_.size(); i++) fuse_marked_.push_back(i);
+}
+
+bool API::EndFuse(Op op, const Variable* in, size_t n_in, uint32_t expect_nout) {
+  if (!fuse_active_) throw std::logic_error("EndFuse without BeginFuse");
+  fuse_active_ = false;
+  // inputs: term k of the vector expression = input k (constant -> coefficient on the ONE wire)
+  std::vector<Term> vec;
+  uint32_t lvl = 0;
+  for (size_t k = 0; k < n_in; k++) {
+    const Variable& v = in[k];
+    if (v.t.empty()) vec.push_back({0, Fr::zero()});
+    else if (v.t.size() == 1) vec.push_back(v.t[0]);
+    else return false;
+    lvl = std::max(lvl, level_of(v));
+  }
+  std::vector<uint32_t> outs;
+  for (size_t i : fuse_marked_) {
+    const Instr& m = tape_[i];
+    if (i < fuse_begin_ || !(m.op == OP_MUL || m.op == OP_HINT_MULADD || m.op == OP_HINT_REDUCE) || m.outs_off != NO_LE)
+      throw std::logic_error("EndFuse: unexpected instruction marked for fusion");
+    for (uint32_t k = 0; k < m.nout; k++) outs.push_back(m.out + k);
+  }
+  if (outs.size() != expect_nout) return false;  // some product folded to a constant: keep the plain tape
+  lvl += 1;
+  // the macro takes the place of the first instruction of the region (the tape stays in dependency order: the
+  // retained instructions - range checks of the hint outputs - read the macro's outputs); the marked ones go
+  std::vector<uint8_t> drop(tape_.size() - fuse_begin_, 0);
+  for (size_t i : fuse_marked_) drop[i - fuse_begin_] = 1;
+  std::vector<Instr> kept;
+  for (size_t i = fuse_begin_; i < tape_.size(); i++)
+    if (!drop[i - fuse_begin_]) kept.push_back(tape_[i]);
+  tape_.resize(fuse_begin_);
+  for (uint32_t o : outs) wire_level_[o] = lvl;
+  if (lvl > max_level_) max_level_ = lvl;
+  Instr m{(uint8_t)op, outs.front(), (uint32_t)outs.size(), {intern_raw_le(vec), NO_LE, NO_LE}, lvl};
+  m.outs_off = (uint32_t)macro_outs_.size();
+  macro_outs_.insert(macro_outs_.end(), outs.begin(), outs.end());
+  tape_.push_back(m);
+  tape_.insert(tape_.end(), kept.begin(), kept.end());
+  return true;
+}
+
 void API::RangeCheckCollect(const Variable& v, int bits) {
   if (bits % 16 != 0) throw std::logic_error("v.bits is not nbBits aligned");  // goldilocks/base.go:433-435
   rc_.push_back({intern_le(v), bits});
@@ -399,7 +463,7 @@ void API::ScheduleALAP() {
   const uint32_t L = max_level_;
   std::vector<uint32_t> producer(next_wire_, NO_LE);  // wire -> tape index
   for (uint32_t i = 0; i < tape_.size(); i++)
-    for (uint32_t k = 0; k < tape_[i].nout; k++) producer[tape_[i].out + k] = i;
+    for (uint32_t k = 0; k < tape_[i].nout; k++) producer[tape_[i].out_wire(k, macro_outs_)] = i;
   std::vector<uint32_t> alap(tape_.size(), L);
   int64_t count_idx = -1, commit_idx = -1;
   for (uint32_t i = 0; i < tape_.size(); i++) {
@@ -424,7 +488,7 @@ void API::ScheduleALAP() {
   for (uint32_t i = 0; i < tape_.size(); i++) {
     if (alap[i] < tape_[i].level) throw std::logic_error("ALAP level below ASAP level");
     tape_[i].level = alap[i];
-    for (uint32_t k = 0; k < tape_[i].nout; k++) wire_level_[tape_[i].out + k] = alap[i];
+    for (uint32_t k = 0; k < tape_[i].nout; k++) wire_level_[tape_[i].out_wire(k, macro_outs_)] = alap[i];
     if (tape_[i].op == OP_COMMIT) commit_level_ = alap[i];
   }
 }
@@ -434,7 +498,7 @@ void API::ScheduleSpineAndTail() {
   const size_t n = tape_.size();
   std::vector<uint32_t> producer(next_wire_, NO_LE);
   for (uint32_t i = 0; i < n; i++)
-    for (uint32_t k = 0; k < tape_[i].nout; k++) producer[tape_[i].out + k] = i;
+    for (uint32_t k = 0; k < tape_[i].nout; k++) producer[tape_[i].out_wire(k, macro_outs_)] = i;
   // 1. height = longest path (in instructions) from an instruction down to a sink of the tape. The spine of the
   //    verifier (sponge -> FRI) has heights in the tens of thousands; the side branches every hinted operation
   //    sprouts (SplitLimbs -> IsZero inverse -> select, limb decomposition -> histogram -> commitment -> divisions)
@@ -493,7 +557,7 @@ void API::ScheduleSpineAndTail() {
   }
   for (size_t i = 0; i < n; i++) {
     if (tail[i]) tape_[i].level = tl[i];
-    for (uint32_t k = 0; k < tape_[i].nout; k++) wire_level_[tape_[i].out + k] = tape_[i].level;
+    for (uint32_t k = 0; k < tape_[i].nout; k++) wire_level_[tape_[i].out_wire(k, macro_outs_)] = tape_[i].level;
     if (tape_[i].op == OP_COMMIT) commit_level_ = tape_[i].level;
   }
   max_level_ = max_level;

@@ -60,6 +60,14 @@ enum Op : uint8_t {
   // 264 multiplication constraints stay - only the SOLVER computes the permutation natively instead of replaying
   // 264 separate multiplications whose operands are long linear expressions.
   OP_POSEIDON_BN254 = 11,
+  // Macro instruction: one whole Poseidon-Goldilocks permutation (poseidon/goldilocks.go:30-37) as the gadget lays it
+  // out: 130 MulAddHint + 630 ReduceHint calls and the 472 S-box products, a dependency chain ~264 instructions long
+  // (x134 permutations = the solver's whole sequential spine). Input: ONE "vector" expression of 12 terms, term k =
+  // state[k] (a wire or a constant; not summed). Outputs: the 1992 wires of those hints / products in the order the
+  // gadget creates them - they are NOT consecutive (the range-check wires of every hint sit between them and stay
+  // ordinary tape instructions), so the instruction carries an explicit output list (API::MacroOuts). The R1CS and the
+  // hint call order are untouched; only the solver evaluates the permutation natively in 64-bit arithmetic.
+  OP_POSEIDON_GL = 12,
 };
 
 struct Instr {
@@ -69,6 +77,11 @@ struct Instr {
   uint32_t le[3];  // linear-expression ids of the inputs (NO_LE if unused)
   uint32_t level;
   uint32_t le3 = 0xffffffffu;  // 4th input (macro instructions only)
+  uint32_t outs_off = 0xffffffffu;  // scattered outputs: index of the first of `nout` wire ids in API::MacroOuts()
+  // wire id of output k
+  uint32_t out_wire(uint32_t k, const std::vector<uint32_t>& macro_outs) const {
+    return outs_off == 0xffffffffu ? out + k : macro_outs[outs_off + k];
+  }
 };
 constexpr uint32_t NO_LE = 0xffffffffu;
 
@@ -113,6 +126,16 @@ class API {
   // consecutive wires [wire_begin, NumWires()) - by ONE macro instruction with the given 4 inputs.
   size_t TapeSize() const { return tape_.size(); }
   void FuseAsMacro(Op op, size_t tape_begin, uint32_t wire_begin, const Variable in[4]);
+  // Scattered fusion (OP_POSEIDON_GL): between BeginFuse and EndFuse the gadget code marks the instructions it wants
+  // computed by the macro (FuseMarkSince(tape size before creating them)); EndFuse removes exactly those from the tape
+  // and appends one macro instruction whose outputs are their output wires in creation order. Everything else created
+  // in between stays. Returns false (tape untouched) if an input is neither a constant nor a single wire.
+  void BeginFuse();
+  void FuseMarkSince(size_t tape_before);
+  bool EndFuse(Op op, const Variable* in, size_t n_in, uint32_t expect_nout);
+  const std::vector<uint32_t>& MacroOuts() const { return macro_outs_; }
+  // output wires of every reference hint call (MulAdd / Reduce / Inverse / SplitLimbs) in call order, fused or not
+  const std::vector<std::pair<uint8_t, uint32_t>>& HintLog() const { return hint_log_; }
   void RangeCheckCollect(const Variable& v, int bits);  // goldilocks/base.go:411-421, COMMIT_RANGE_CHECKER branch
   // Runs the deferred range-check construction (goldilocks/base.go:423-442 + gnark rangecheck commit):
   // limb decomposition, multiplicity histogram, commitment, log-derivative sums. Call once, at the end.
@@ -183,6 +206,12 @@ class API {
   uint32_t commit_level_ = 0;
   uint32_t limb_wire_start_ = 0, n_limb_wires_ = 0, count_wire_start_ = 0, commit_wire_ = 0;
   uint32_t le_one_ = NO_LE;
+  std::vector<uint32_t> macro_outs_;
+  std::vector<std::pair<uint8_t, uint32_t>> hint_log_;  // (op, output wire)
+  bool fuse_active_ = false;
+  size_t fuse_begin_ = 0;
+  std::vector<size_t> fuse_marked_;
+  uint32_t intern_raw_le(const std::vector<Term>& terms);
 };
 
 }  // namespace fe

@@ -53,7 +53,12 @@ class GlChip {
   Variable Sub(const Variable& a, const Variable& b) { return MulAdd(b, C(GL_NEG_ONE), a); }
   Variable SubNoReduce(const Variable& a, const Variable& b) { return api->Add(a, api->Mul(b, C(GL_NEG_ONE))); }
   Variable Mul(const Variable& a, const Variable& b) { return MulAdd(a, b, C(0)); }
-  Variable MulNoReduce(const Variable& a, const Variable& b) { return api->Mul(a, b); }
+  Variable MulNoReduce(const Variable& a, const Variable& b) {
+    const size_t before = api->TapeSize();
+    Variable v = api->Mul(a, b);
+    api->FuseMarkSince(before);  // no-op outside a BeginFuse / EndFuse region (PoseidonGlChip::Poseidon)
+    return v;
+  }
   Variable MulAdd(const Variable& a, const Variable& b, const Variable& c);
   Variable MulAddNoReduce(const Variable& a, const Variable& b, const Variable& c) { return api->MulAcc(c, a, b); }
   Variable Reduce(const Variable& x) { return ReduceWithMaxBits(x, RANGE_CHECK_NB_BITS); }

@@ -40,7 +40,9 @@ std::vector<uint64_t> TwoAdicSubgroup(uint64_t n_log) {
 // ---- goldilocks.Chip (goldilocks/base.go) -----------------------------------------------------------------
 Variable GlChip::MulAdd(const Variable& a, const Variable& b, const Variable& c) {
   // base.go:196-213
+  const size_t before = api->TapeSize();
   auto res = api->NewHint(fe::OP_HINT_MULADD, 2, &a, &b, &c);
+  api->FuseMarkSince(before);
   const Variable& quotient = res[0];
   const Variable& remainder = res[1];
   Variable lhs = api->MulAcc(c, a, b);
@@ -53,7 +55,9 @@ Variable GlChip::MulAdd(const Variable& a, const Variable& b, const Variable& c)
 
 Variable GlChip::ReduceWithMaxBits(const Variable& x, int max_nb_bits) {
   // base.go:259-281
+  const size_t before = api->TapeSize();
   auto res = api->NewHint(fe::OP_HINT_REDUCE, 2, &x);
+  api->FuseMarkSince(before);
   const Variable& quotient = res[0];
   api->RangeCheckCollect(quotient, max_nb_bits);
   const Variable& remainder = res[1];
@@ -182,9 +186,13 @@ GlState PoseidonGlChip::Poseidon(const GlState& input) {
   num_perms++;
   GlState state = input;
   int rc = 0;
+  // same hints, same wires, same constraints; the solver evaluates the whole permutation with one macro instruction
+  // (130 MulAdd + 630 Reduce hints and 472 S-box products = 1992 wires, csrc/poseidon_gl_macro.cuh)
+  api->BeginFuse();
   state = fullRounds(state, &rc);
   state = partialRounds(state, &rc);
   state = fullRounds(state, &rc);
+  api->EndFuse(fe::OP_POSEIDON_GL, input.data(), 12, 1992);
   return state;
 }
 

@@ -22,6 +22,7 @@
 #include "host/frontend.h"
 #include "host/gadgets.h"
 #include "poseidon_bn254_macro.cuh"
+#include "poseidon_gl_macro.cuh"
 #include "poseidon_constants.inc"
 
 namespace gpw {
@@ -50,6 +51,8 @@ struct DevCircuit {
   uint32_t long_le[8];
   Fr* long_val;  // per-proof scratch is not needed: evaluated right before use on the stream
   const Fr* bn_tables;  // Poseidon-BN254 constants: C[88] | S[392] | M[16] | P[16], Montgomery
+  const uint64_t* gl_tables;   // Poseidon-Goldilocks constants, layout of glm::T_* (poseidon_gl_macro.cuh)
+  const uint32_t* macro_outs;  // output wire lists of the OP_POSEIDON_GL instructions (DInstr.out = offset into it)
 };
 constexpr uint32_t LONG_LE_TERMS = 2048;
 
@@ -144,11 +147,24 @@ struct OutRef {
   uint32_t out;
   Fr* ring;
   uint32_t slot;
+  const uint32_t* outs = nullptr;  // scattered outputs (OP_POSEIDON_GL): wire id of output k
   __device__ __forceinline__ void put(uint32_t k, const Fr& v) const {
-    st_w(W + out + k, v);
+    st_w(W + (outs ? outs[k] : out + k), v);
     if (ring) st_w(ring + ((slot + k) & (RING_SLOTS - 1)), v);
   }
 };
+
+// value of term k of a "vector" expression (macro inputs): coefficient * wire, or the coefficient itself on the ONE wire
+__device__ __forceinline__ Fr eval_term(const DevCircuit& c, const Fr* W, const LeRef& r, uint32_t k) {
+  const uint32_t cid = r.cids[k * r.stride];
+  const uint32_t loc = r.wires[k * r.stride];
+  if (loc == 0) return ld_w(c.coeffs + cid);
+  const Fr v = ld_term(W, r.ring, loc);
+  if (cid == 0) return v;
+  if (cid == 1) return neg(v);
+  return mul(ld_w(c.coeffs + cid), v);
+}
+
 
 __device__ __forceinline__ Fr eval_le(const DevCircuit& c, const Fr* W, uint32_t le) { return eval_ref(c, W, csr_ref(c, le)); }
 
@@ -168,6 +184,10 @@ __device__ __forceinline__ Fr from_u64x4(const uint64_t x[4]) {
 }
 __device__ __forceinline__ Fr from_u64(uint64_t v) {
   uint64_t x[4] = {v, 0, 0, 0};
+  return from_u64x4(x);
+}
+__device__ __forceinline__ Fr fr_from_u192(const glm::U192& v) {
+  const uint64_t x[4] = {v.l[0], v.l[1], v.l[2], 0};
   return from_u64x4(x);
 }
 
@@ -268,25 +288,47 @@ __device__ void exec_op(const DevCircuit& c, const Fr* W, uint32_t op_nout, cons
       poseidon_bn254_trace(st, isc, T, [&](const Fr& v) { O.put(idx++, v); });
       break;
     }
+    case fe::OP_POSEIDON_GL: {
+      // one thread, sequential (wide levels / the unstaged debugging walker); the staged spine runs the warp form
+      uint64_t st[12];
+      bool bad = false;
+      for (uint32_t k = 0; k < 12; k++) {
+        uint64_t x[4];
+        to_u64x4(eval_term(c, W, A, k), x);
+        bad |= (x[1] | x[2] | x[3]) != 0 || x[0] >= gl::P;
+        st[k] = x[0];
+      }
+      if (bad) {
+        atomicCAS(err, 0, ERR_MULADD);  // the permutation starts with gl.Add = MulAddHint: goldilocks/base.go:228-232
+        return;
+      }
+      glm::trace_seq(st, c.gl_tables, [&](uint32_t slot, const glm::U192& v) { O.put(slot, fr_from_u192(v)); });
+      break;
+    }
     default: break;
   }
 }
 
 __device__ __forceinline__ void exec_instr(const DevCircuit& c, Fr* W, const DInstr& in, int* err, uint32_t* hist) {
-  exec_op(c, W, in.op_nout, OutRef{W, in.out, nullptr, 0}, csr_ref(c, in.le[0]), csr_ref(c, in.le[1]), csr_ref(c, in.le[2]),
-          csr_ref(c, in.le[3]), err, hist);
+  OutRef O{W, in.out, nullptr, 0};
+  if ((in.op_nout & 0xffu) == fe::OP_POSEIDON_GL) O.outs = c.macro_outs + in.out;
+  exec_op(c, W, in.op_nout, O, csr_ref(c, in.le[0]), csr_ref(c, in.le[1]), csr_ref(c, in.le[2]), csr_ref(c, in.le[3]), err, hist);
 }
 
 // ---- staged narrow tape ---------------------------------------------------------------------------------------------
 // The narrow levels are re-encoded as a flat stream of CHUNKS (u32 words), each self-contained:
-//   [0] n_instr   [1] words of the NEXT chunk (0 = last)   [2] 1 if a level ends with this chunk   [3] reserved
+//   [0] n_instr   [1] words of the NEXT chunk (0 = last)   [2] 1 if a level ends with this chunk   [3] flags
 //   [4 .. 4+n_instr) word offset of each instruction record inside the chunk
-//   records: op|nout<<8, out, nA, nB, nC, then (wire, coeff-id) pairs of A, B, C
+//   records: op|nout<<8, out, nA, nB, nC, ring slot, nD, then (wire, coeff-id) pairs of A, B, C, D
+//   (a Poseidon-Goldilocks macro sits alone in its chunk, flag CHUNK_FLAG_GL_MACRO, its 1992 output wire ids after A)
 // so one contiguous copy brings everything an instruction needs except the wire values themselves. The CTA keeps
 // two chunk buffers in shared memory and prefetches chunk i+1 with cp.async while it executes chunk i: the only
 // exposed global-memory latency per level is the load of the operand wires.
 constexpr uint32_t CHUNK_MAX_WORDS = 6144;  // 24 KB per buffer
-constexpr size_t STAGED_SMEM_BYTES = 2 * CHUNK_MAX_WORDS * 4 + RING_SLOTS * sizeof(Fr);  // 48 KB + 64 KB
+// + the Poseidon-Goldilocks macro's trace (1992 integers of 192 bits) and its 2 x 12-word exchange buffers
+constexpr size_t GLM_TRACE_WORDS64 = (size_t)glm::N_OUT * 3 + 24;
+constexpr size_t STAGED_SMEM_BYTES = 2 * CHUNK_MAX_WORDS * 4 + RING_SLOTS * sizeof(Fr) + GLM_TRACE_WORDS64 * 8;  // 48 + 64 + 47 KB
+constexpr uint32_t CHUNK_FLAG_GL_MACRO = 1;  // chunk header word [3]: the chunk is ONE OP_POSEIDON_GL instruction
 // The spine CTA is latency bound and shares nothing: when other proofs' MSM / NTT kernels run next to it (several
 // proofs in flight, wrap.cu) their warps would saturate the SM's IMAD pipe and stretch every level of the spine. It
 // therefore asks for the SM's whole shared memory, which keeps every kernel that uses shared memory off its SM.
@@ -309,6 +351,8 @@ __global__ void __launch_bounds__(NARROW_THREADS)
   extern __shared__ __align__(16) uint32_t dyn_smem[];
   uint32_t(*buf)[CHUNK_MAX_WORDS] = reinterpret_cast<uint32_t(*)[CHUNK_MAX_WORDS]>(dyn_smem);
   Fr* ring = reinterpret_cast<Fr*>(dyn_smem + 2 * CHUNK_MAX_WORDS);
+  uint64_t* glm_io = reinterpret_cast<uint64_t*>(dyn_smem + 2 * CHUNK_MAX_WORDS + RING_SLOTS * 8);  // [0,12) inputs, [12,24) exchange
+  uint64_t* glm_trace = glm_io + 24;
   Fr* W = wires + (size_t)blockIdx.x * wire_stride;
   int* e = err + blockIdx.x;
   uint32_t* h = hist + (size_t)blockIdx.x * 65536;
@@ -325,6 +369,36 @@ __global__ void __launch_bounds__(NARROW_THREADS)
     const uint32_t* next_src = src + words;
     for (uint32_t i = threadIdx.x * 4; i < next_words; i += blockDim.x * 4) cp_async_16(&buf[cur ^ 1][i], next_src + i);
     cp_async_commit();
+    if (ch[3] == CHUNK_FLAG_GL_MACRO) {
+      // One whole Poseidon-Goldilocks permutation, cooperatively: 12 threads fetch the state, warp 0 evaluates the
+      // permutation natively (lane k owns element k) leaving the 1992 hint / product integers in shared memory, then
+      // all threads convert them to Montgomery form and store them to their wires and to the ring.
+      const uint32_t* rec = ch + ch[4];
+      const uint32_t nout = rec[0] >> 8;
+      const uint32_t* t = rec + 7;
+      const uint32_t* outs = t + 24;
+      const uint32_t slot0 = rec[5];
+      if (threadIdx.x < 12) {
+        const LeRef A{t, t + 1, 12, 2, true, ring};
+        uint64_t x[4];
+        to_u64x4(eval_term(c, W, A, threadIdx.x), x);
+        if ((x[1] | x[2] | x[3]) != 0 || x[0] >= gl::P) atomicCAS(e, 0, ERR_MULADD);  // goldilocks/base.go:228-232
+        glm_io[threadIdx.x] = x[0];
+      }
+      __syncthreads();
+      if (threadIdx.x < 32)
+        glm::trace_warp(threadIdx.x < 12 ? glm_io[threadIdx.x] : 0ull, glm_io + 12, c.gl_tables, [&](uint32_t slot, const glm::U192& v) {
+          glm_trace[3 * slot] = v.l[0];
+          glm_trace[3 * slot + 1] = v.l[1];
+          glm_trace[3 * slot + 2] = v.l[2];
+        });
+      __syncthreads();
+      for (uint32_t k = threadIdx.x; k < nout; k += blockDim.x) {
+        const Fr v = fr_from_u192(glm::U192{{glm_trace[3 * k], glm_trace[3 * k + 1], glm_trace[3 * k + 2]}});
+        st_w(W + outs[k], v);
+        st_w(ring + ((slot0 + k) & (RING_SLOTS - 1)), v);
+      }
+    } else
     for (uint32_t i = threadIdx.x; i < n_instr; i += blockDim.x) {
       const uint32_t* rec = ch + ch[4 + i];
       const uint32_t nA = rec[2], nB = rec[3], nC = rec[4], nD = rec[6];
@@ -549,7 +623,8 @@ static int finish_compile(gpw_circuit* c) {
       commit_level = in.level;
       continue;
     }
-    di.push_back({(uint32_t)in.op | (in.nout << 8), in.out, {in.le[0], in.le[1], in.le[2], in.le3}});
+    // (a macro with scattered outputs carries the offset of its output list instead of a first wire)
+    di.push_back({(uint32_t)in.op | (in.nout << 8), in.outs_off != NO_LE ? in.outs_off : in.out, {in.le[0], in.le[1], in.le[2], in.le3}});
     level_off[in.level + 1]++;
   }
   for (uint32_t l = 0; l < L; l++) level_off[l + 1] += level_off[l];
@@ -625,8 +700,12 @@ static int finish_compile(gpw_circuit* c) {
         while (i < end) {
           // greedily take instructions [i, j) that fit one chunk
           uint32_t j = i, words = 4;
+          const auto& mouts = api.MacroOuts();
+          auto is_gl_macro = [&](uint32_t k) { return (di[k].op_nout & 0xffu) == fe::OP_POSEIDON_GL; };
           while (j < end) {
+            if (is_gl_macro(j) && j > i) break;  // a Poseidon-Goldilocks macro gets a chunk of its own
             uint32_t rec = 7 + le_words(di[j].le[0]) + le_words(di[j].le[1]) + le_words(di[j].le[2]) + le_words(di[j].le[3]);
+            if (is_gl_macro(j)) rec += di[j].op_nout >> 8;
             if ((di[j].op_nout >> 8) >= RING_SLOTS) {
               set_error("tape instruction with %u outputs exceeds the ring", di[j].op_nout >> 8);
               return GPW_EINVAL;
@@ -638,12 +717,14 @@ static int finish_compile(gpw_circuit* c) {
             if (words + 1 + rec > CHUNK_MAX_WORDS - 4) break;
             words += 1 + rec;
             j++;
+            if (is_gl_macro(j - 1)) break;
           }
           const size_t base = stream.size();
           const uint32_t n = j - i;
           stream.resize(base + 4 + n, 0);
           stream[base] = n;
           stream[base + 2] = (j == end) ? 1u : 0u;
+          stream[base + 3] = is_gl_macro(i) ? CHUNK_FLAG_GL_MACRO : 0u;
           // ring bookkeeping: every wire produced on the spine gets the next slot of the shared-memory ring; a later
           // operand reads the ring instead of HBM if its slot cannot have been overwritten before the END of the
           // consuming chunk (the chunk's own outputs are written concurrently with its reads)
@@ -685,9 +766,11 @@ static int finish_compile(gpw_circuit* c) {
             }
             stream.push_back((uint32_t)(ring_seq % RING_SLOTS));
             stream.push_back(in.le[3] == NO_LE ? 0u : ((off[in.le[3] + 1] - off[in.le[3]]) | 0x80000000u));
+            const bool glm_instr = (in.op_nout & 0xffu) == fe::OP_POSEIDON_GL;
             for (uint32_t o = 0; o < (in.op_nout >> 8); o++) {
-              wire_seq[in.out + o] = ring_seq++;
-              wire_seg[in.out + o] = seg_id;
+              const uint32_t ow = glm_instr ? mouts[in.out + o] : in.out + o;
+              wire_seq[ow] = ring_seq++;
+              wire_seg[ow] = seg_id;
             }
             for (int t = 0; t < 4; t++) {
               uint32_t le = in.le[t];
@@ -701,6 +784,8 @@ static int finish_compile(gpw_circuit* c) {
                 ring_total++;
               }
             }
+            if (glm_instr)
+              for (uint32_t o = 0; o < (in.op_nout >> 8); o++) stream.push_back(mouts[in.out + o]);
           }
           while ((stream.size() - base) % 4) stream.push_back(0);
           const uint32_t cw = (uint32_t)(stream.size() - base);
@@ -747,6 +832,22 @@ static int finish_compile(gpw_circuit* c) {
     memcpy(tb.data() + 88 + 392, GPW_BN_M_MONT, 16 * 32);
     memcpy(tb.data() + 88 + 392 + 16, GPW_BN_P_MONT, 16 * 32);
     GPW_TRY(upload(c, tb, &dc.bn_tables));
+  }
+  {
+    std::vector<uint64_t> gt(glm::T_TOTAL);
+    memcpy(gt.data() + glm::T_RC, GPW_GL_ALL_ROUND_CONSTANTS, sizeof(GPW_GL_ALL_ROUND_CONSTANTS));
+    memcpy(gt.data() + glm::T_CIRC, GPW_GL_MDS_CIRC, sizeof(GPW_GL_MDS_CIRC));
+    memcpy(gt.data() + glm::T_DIAG, GPW_GL_MDS_DIAG, sizeof(GPW_GL_MDS_DIAG));
+    memcpy(gt.data() + glm::T_FIRST, GPW_GL_FAST_PARTIAL_FIRST_ROUND_CONSTANT, sizeof(GPW_GL_FAST_PARTIAL_FIRST_ROUND_CONSTANT));
+    memcpy(gt.data() + glm::T_PRC, GPW_GL_FAST_PARTIAL_ROUND_CONSTANTS, sizeof(GPW_GL_FAST_PARTIAL_ROUND_CONSTANTS));
+    memcpy(gt.data() + glm::T_VS, GPW_GL_FAST_PARTIAL_ROUND_VS, sizeof(GPW_GL_FAST_PARTIAL_ROUND_VS));
+    memcpy(gt.data() + glm::T_WHATS, GPW_GL_FAST_PARTIAL_ROUND_W_HATS, sizeof(GPW_GL_FAST_PARTIAL_ROUND_W_HATS));
+    memcpy(gt.data() + glm::T_INIT, GPW_GL_FAST_PARTIAL_ROUND_INITIAL_MATRIX, sizeof(GPW_GL_FAST_PARTIAL_ROUND_INITIAL_MATRIX));
+    static_assert(GPW_GL_MDS0TO0 == glm::MDS0TO0, "MDS0TO0");
+    GPW_TRY(upload(c, gt, &dc.gl_tables));
+    std::vector<uint32_t> mo = api.MacroOuts();
+    if (mo.empty()) mo.push_back(0);
+    GPW_TRY(upload(c, mo, &dc.macro_outs));
   }
   dc.n_long = 0;
   {
@@ -1060,15 +1161,14 @@ extern "C" int gpw_circuit_supports(const gpw_circuit* c, int side, uint32_t* ou
 extern "C" int gpw_circuit_hint_wires(const gpw_circuit* c, int op, uint32_t* out, size_t cap, size_t* n) {
   if (!c || !n) return GPW_EINVAL;
   size_t cnt = 0;
-  for (const auto& in : c->api.Tape()) {
-    if (in.op != op) continue;
-    for (uint32_t i = 0; i < in.nout; i++) {
-      if (out) {
-        if (cnt >= cap) return GPW_EINVAL;
-        out[cnt] = in.out + i;
-      }
-      cnt++;
+  // the builder's log of hint calls: hints fused into a macro instruction are no longer tape instructions of their own
+  for (const auto& h : c->api.HintLog()) {
+    if (h.first != op) continue;
+    if (out) {
+      if (cnt >= cap) return GPW_EINVAL;
+      out[cnt] = h.second;
     }
+    cnt++;
   }
   *n = cnt;
   return GPW_OK;

@@ -13,6 +13,7 @@
 #include "../../gnark-plonky2-verifier_b200/csrc/host/frontend.h"
 #include "../../gnark-plonky2-verifier_b200/csrc/host/gadgets.h"
 #include "../../gnark-plonky2-verifier_b200/csrc/poseidon_bn254_macro.cuh"
+#include "../../gnark-plonky2-verifier_b200/csrc/poseidon_gl_macro.cuh"
 #include "../../gnark-plonky2-verifier_b200/csrc/poseidon_constants.inc"
 
 using namespace gpw;
@@ -252,6 +253,41 @@ int ct_solve_inputs(void* h, const uint64_t* pub, size_t npub, const uint64_t* s
         if (idx != in.nout) { g_err = "poseidon macro emitted a different number of wires than the builder created"; return -1; }
         break;
       }
+      case OP_POSEIDON_GL: {
+        // term k of the vector expression = state element k (coefficient x wire, or the coefficient on the ONE wire)
+        const auto& off = api.LeOffsets();
+        const auto& wi = api.LeWires();
+        const auto& ci = api.LeCoeffIds();
+        if (off[in.le[0] + 1] - off[in.le[0]] != 12) { g_err = "poseidon-gl macro: input vector must have 12 terms"; return -1; }
+        uint64_t st[12];
+        for (uint32_t k = 0; k < 12; k++) {
+          const uint32_t q = off[in.le[0]] + k;
+          const Fr v = wi[q] == 0 ? api.Coeffs()[ci[q]] : mul(api.Coeffs()[ci[q]], c->w[wi[q]]);
+          uint64_t x[4];
+          canon(v, x);
+          if (x[1] | x[2] | x[3] || x[0] >= gl::P) {
+            g_err = "MulAddHint: operand is not in the field";  // the permutation starts with gl.Add (base.go:228-232)
+            return -5;
+          }
+          st[k] = x[0];
+        }
+        std::vector<uint64_t> gt(glm::T_TOTAL);
+        memcpy(gt.data() + glm::T_RC, GPW_GL_ALL_ROUND_CONSTANTS, sizeof(GPW_GL_ALL_ROUND_CONSTANTS));
+        memcpy(gt.data() + glm::T_CIRC, GPW_GL_MDS_CIRC, sizeof(GPW_GL_MDS_CIRC));
+        memcpy(gt.data() + glm::T_DIAG, GPW_GL_MDS_DIAG, sizeof(GPW_GL_MDS_DIAG));
+        memcpy(gt.data() + glm::T_FIRST, GPW_GL_FAST_PARTIAL_FIRST_ROUND_CONSTANT, sizeof(GPW_GL_FAST_PARTIAL_FIRST_ROUND_CONSTANT));
+        memcpy(gt.data() + glm::T_PRC, GPW_GL_FAST_PARTIAL_ROUND_CONSTANTS, sizeof(GPW_GL_FAST_PARTIAL_ROUND_CONSTANTS));
+        memcpy(gt.data() + glm::T_VS, GPW_GL_FAST_PARTIAL_ROUND_VS, sizeof(GPW_GL_FAST_PARTIAL_ROUND_VS));
+        memcpy(gt.data() + glm::T_WHATS, GPW_GL_FAST_PARTIAL_ROUND_W_HATS, sizeof(GPW_GL_FAST_PARTIAL_ROUND_W_HATS));
+        memcpy(gt.data() + glm::T_INIT, GPW_GL_FAST_PARTIAL_ROUND_INITIAL_MATRIX, sizeof(GPW_GL_FAST_PARTIAL_ROUND_INITIAL_MATRIX));
+        if (in.nout != glm::N_OUT) { g_err = "poseidon-gl macro: unexpected output count"; return -1; }
+        const auto& mo = api.MacroOuts();
+        glm::trace_seq(st, gt.data(), [&](uint32_t slot, const glm::U192& v) {
+          const uint64_t l[4] = {v.l[0], v.l[1], v.l[2], 0};
+          c->w[mo[in.outs_off + slot]] = fr_from_limbs(l);
+        });
+        break;
+      }
       default: g_err = "unknown opcode"; return -1;
     }
   }
@@ -304,13 +340,12 @@ uint64_t ct_check(void* h, int64_t* first_bad) {
 size_t ct_hint_outputs(void* h, int op, uint64_t* out, size_t cap_u64) {
   Circuit* c = (Circuit*)h;
   size_t n = 0;
-  for (const auto& in : c->api.Tape()) {
-    if (in.op != op) continue;
-    for (uint32_t i = 0; i < in.nout; i++) {
-      if (n + 4 > cap_u64) return n;
-      canon(c->w[in.out + i], out + n);
-      n += 4;
-    }
+  // the builder's log of hint calls (hints fused into a Poseidon macro are not tape instructions of their own)
+  for (const auto& hl : c->api.HintLog()) {
+    if (hl.first != op) continue;
+    if (n + 4 > cap_u64) return n;
+    canon(c->w[hl.second], out + n);
+    n += 4;
   }
   return n;
 }
