@@ -176,3 +176,63 @@ def test_wrap_prove_step(ctx, step):
     assert gpw.points_to_ints(1, pr["commitment"])[0] == ob.point_key(1, ob.ec_mul(1, ob.G1_GEN, sD))
     print("wrap stats (ms):", key.last_stats(), "key:", info)
     key.close()
+
+
+def test_prove_many_lanes_match_single_proofs(ctx, step):
+    # a stream of proofs with several in flight (one host thread + stream + scratch per lane) must return, proof for
+    # proof, exactly what the one-at-a-time entry point returns - with the inputs in host memory and in device memory
+    import torch
+    circ, inputs, d = step
+    key = gpw.WrapKey(ctx, circ, seed=7)
+    n = 5
+    rs = [(0x1000 + 17 * i, 0x2000 + 31 * i) for i in range(n)]
+    single = [key.prove(inputs, r_, s_, check=True)["raw"].copy() for r_, s_ in rs[:3]]
+    many_host = np.ascontiguousarray(np.tile(inputs, (n, 1, 1)))
+    key.set_lanes(3)
+    out = key.prove_many(many_host.ctypes.data, n, [r for r, _ in rs], [s for _, s in rs], check=True)
+    assert len(out) == n and all(p["n_unsatisfied"] == 0 for p in out)
+    for i in range(3):
+        assert (out[i]["raw"] == single[i]).all(), i
+    assert len({p["raw"].tobytes() for p in out}) == n          # distinct (r, s) -> distinct proofs
+    dev = torch.from_numpy(many_host.view(np.int64)).cuda()
+    torch.cuda.synchronize()
+    key.set_lanes(2)
+    out2 = key.prove_many(dev.data_ptr(), n, [r for r, _ in rs], [s for _, s in rs], check=True)
+    assert all((a["raw"] == b["raw"]).all() for a, b in zip(out, out2))
+    # a bad proof in the stream fails the call loudly (unsatisfiable -> GPW_EUNSAT), it is not skipped
+    bad = many_host.copy()
+    bad[2, circ.info["public"] + 40, 0] ^= 1
+    with pytest.raises(gpw.GpwError) as e:
+        key.prove_many(bad.ctypes.data, n, [r for r, _ in rs], [s for _, s in rs], check=True)
+    assert e.value.code in (-5, -6) and "proof 2" in str(e.value)
+    key.close()
+
+
+def test_wrap_prove_decode_block(ctx, testdata_dir):
+    # BASELINE.json configs[0]: the reference's other fixture (degree_bits 12, ConstantGate, no ExponentiationGate)
+    d = os.path.join(testdata_dir, "decode_block")
+    rd = lambda f: open(os.path.join(d, f), "rb").read()
+    circ = gpw.Circuit.compile_verifier(ctx, rd("common_circuit_data.json"))
+    inputs = circ.parse_inputs(rd("proof_with_public_inputs.json"), rd("verifier_only_circuit_data.json"))
+    w = _solve(ctx, circ, inputs)
+    assert circ.r1cs_eval_dev(w.data_ptr()) == 0
+    api, _ = verify_testdata(d)
+    for kind, op in (("muladd", 1), ("reduce", 2), ("inverse", 3), ("split", 4)):
+        exp = [o for k, _, outs in api.hints if k == kind for o in outs]
+        assert _wire_ints(w, circ.hint_wires(op)) == exp, kind
+    key = gpw.WrapKey(ctx, circ, seed=5)
+    pr = key.prove(inputs, 3, 4, check=True)
+    assert pr["n_unsatisfied"] == 0
+    for g, name in ((1, "Ar"), (2, "Bs"), (1, "Krs"), (1, "commitment"), (1, "pok")):
+        assert gpw.host_ec_is_on_curve(g, pr[name]) and pr[name].any()
+    key.close()
+    circ.close()
+
+
+def test_poseidon_gl_macro_rejects_noncanonical_state(ctx):
+    # the permutation starts with gl.Add = MulAddHint, which refuses operands >= p (goldilocks/base.go:228-232)
+    circ = gpw.Circuit.compile_gadget(ctx, "poseidon_gl")
+    with pytest.raises(gpw.GpwError) as e:
+        _solve(ctx, circ, circ.inputs_from_ints([0] * 12, [ogl.P] + [0] * 11))
+    assert e.value.code == -5 and "MulAddHint" in str(e.value)
+    circ.close()
