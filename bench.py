@@ -82,7 +82,8 @@ def cpu_baseline(threads=None):
     if not os.path.exists(so):
         subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle", "c")], stdout=subprocess.DEVNULL)
     lib = C.CDLL(so)
-    nthreads = threads or lib.ref_max_threads()
+    # torchrun exports OMP_NUM_THREADS=1: ask for the box's cores explicitly
+    nthreads = threads or max(int(lib.ref_max_threads()), os.cpu_count() or 1)
     vp = C.c_void_p
     lib.ref_msm_g1.argtypes = [vp, vp, C.c_size_t, C.c_int, C.c_int, C.c_int, vp]
     lib.ref_msm_g2.argtypes = [vp, vp, C.c_size_t, C.c_int, C.c_int, C.c_int, vp]
@@ -159,7 +160,7 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=16)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--lanes", type=int, default=int(os.environ.get("GPW_WRAP_LANES", "4")),
+    ap.add_argument("--lanes", type=int, default=int(os.environ.get("GPW_WRAP_LANES", "6")),
                     help="proofs in flight per GPU (gpw_wrap_set_lanes)")
     ap.add_argument("--impl", default="gpw", choices=["gpw", "reference"])
     args = ap.parse_args()

@@ -15,6 +15,23 @@ extern "C" int gpw_msm_g1_dev(gpw_ctx* ctx, uint64_t scalars_dev, uint64_t point
                           win_lo, win_hi, out_affine, "msm1");
 }
 
+// Fixed-base MSM (bases known at setup, e.g. a proving key): gpw_msm_g1_fixed_table precomputes 2^(c w) P_i for the
+// W = ceil(255 / c) windows (table_dev: W * n affine points), gpw_msm_g1_fixed_dev then needs ceil(255 / c) bucket
+// additions per full-width scalar into a single bucket set.
+extern "C" int gpw_msm_g1_fixed_table(gpw_ctx* ctx, uint64_t points_dev, size_t n, int window_bits, int n_windows, uint64_t table_dev) {
+  return msm_fixed_table_impl<Fp>(ctx, (const Affine<Fp>*)points_dev, n, window_bits, n_windows, (Affine<Fp>*)table_dev);
+}
+
+extern "C" int gpw_msm_g1_fixed_dev(gpw_ctx* ctx, uint64_t scalars_dev, uint64_t table_dev, size_t n, int scalars_mont, int window_bits,
+                                    int n_windows, uint64_t* out_affine) {
+  if (!ctx || !out_affine || window_bits < 2 || n_windows < 1) {
+    set_error("msm_fixed: bad argument");
+    return GPW_EINVAL;
+  }
+  return msm_dev_impl<Fp>(ctx, (const Fr*)scalars_dev, (const Affine<Fp>*)table_dev, n, scalars_mont, window_bits, 0, 0, out_affine,
+                          "msm1f", n_windows);
+}
+
 extern "C" int gpw_msm_last_stats(gpw_ctx* ctx, float* accumulate_ms, float* total_ms, uint64_t* nonzero_digits) {
   if (!ctx) return GPW_EINVAL;
   if (accumulate_ms) *accumulate_ms = ctx->msm_acc_ms;

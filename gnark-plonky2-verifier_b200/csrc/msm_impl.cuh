@@ -57,9 +57,11 @@ __device__ __forceinline__ uint32_t get_bits(const uint32_t* s, int lo, int c) {
 // count) so that the warp can aggregate its atomics: lanes that hit the same bucket - bit wires and small constants make
 // (window 0, digit 1) and its neighbours receive millions of entries - are found with match.any and served by ONE
 // atomic of the group's size instead of a same-address atomic per lane (which the L2 serialises).
+// fixed != 0 (fixed-base mode, see msm_dev_impl): all windows share ONE bucket set and digit w of scalar i refers to
+// the precomputed point 2^(c w) P_i stored at index w n + i.
 template <bool SCATTER>
 static __global__ void __launch_bounds__(256) k_msm_digits(const Fr* __restrict__ scalars, size_t n, int mont, int c, int nwin,
-                                                           int win_lo, int win_hi, uint32_t* __restrict__ counters,
+                                                           int win_lo, int win_hi, int fixed, uint32_t* __restrict__ counters,
                                                            uint32_t* __restrict__ sorted) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   const uint32_t lane = threadIdx.x & 31u;
@@ -78,7 +80,7 @@ static __global__ void __launch_bounds__(256) k_msm_digits(const Fr* __restrict_
     carry = negv ? 1u : 0u;
     const bool has = mag != 0 && w >= win_lo;
     if (!__any_sync(0xffffffffu, has)) continue;
-    const uint32_t key = has ? (uint32_t)(w - win_lo) * half + (mag - 1u) : (0xffffffffu - lane);
+    const uint32_t key = has ? (fixed ? 0u : (uint32_t)(w - win_lo) * half) + (mag - 1u) : (0xffffffffu - lane);
     const uint32_t peers = __match_any_sync(0xffffffffu, key);
     if (has) {
       const uint32_t leader = (uint32_t)__ffs(peers) - 1u;
@@ -90,7 +92,7 @@ static __global__ void __launch_bounds__(256) k_msm_digits(const Fr* __restrict_
         if (lane == leader) base = atomicAdd(&counters[key], cnt);
         base = __shfl_sync(peers, base, leader);
         const uint32_t rank = (uint32_t)__popc(peers & ((1u << lane) - 1u));
-        sorted[base + rank] = (uint32_t)i | (negv ? 0x80000000u : 0u);
+        sorted[base + rank] = (uint32_t)(fixed ? (size_t)w * n + i : i) | (negv ? 0x80000000u : 0u);
       }
     }
   }
@@ -427,11 +429,18 @@ __global__ void __launch_bounds__(256)
   }
 }
 
-// sum_{b in chunk} (b+1) * B[w][b]   (running-sum trick + one small scalar mul per chunk)
+// Window reduction sum_b (b + 1) B[w][b], two levels deep. Level 0 (chunk_sums != nullptr): one thread per chunk of
+// `chunk` buckets computes with the running-sum trick T = sum_j (j + 1) B[lo + j] -> partials and the plain chunk sum
+// S = sum_j B[lo + j] -> chunk_sums; what is still owed, lo * S with lo = chunk * ci, is chunk * sum_ci ci * S_ci: the
+// same problem on 16x fewer elements with weights ci instead of ci + 1. Level 1 (chunk_sums == nullptr, weight_off = 0)
+// runs this kernel again on the chunk sums and pays the small scalar multiplication by its chunk offset there - on
+// 1/256 of the elements - instead of once per level-0 chunk, which used to be ~45 % of the reduction's work.
+// partial = sum_j (lo + j + weight_off) E[lo + j] when chunk_sums == nullptr, sum_j (j + weight_off) E[lo + j] otherwise.
 template <class F>
 __global__ void __launch_bounds__(128)
     k_msm_window_partial(const XYZZ<F>* __restrict__ buckets, const uint32_t* __restrict__ offsets, uint32_t half,
-                         uint32_t chunk, uint32_t nwin, XYZZ<F>* __restrict__ partials) {
+                         uint32_t chunk, uint32_t nwin, uint32_t weight_off, XYZZ<F>* __restrict__ partials,
+                         XYZZ<F>* __restrict__ chunk_sums) {
   const uint32_t gid = blockIdx.x * blockDim.x + threadIdx.x;
   const uint32_t nchunks = half / chunk;
   const uint32_t w = gid / nchunks, ci = gid % nchunks;
@@ -439,8 +448,9 @@ __global__ void __launch_bounds__(128)
   const uint32_t lo = ci * chunk;
   XYZZ<F> acc = XYZZ<F>::inf(), sum = XYZZ<F>::inf();
   // chunks without a single entry (the upper windows of an MSM over 16-bit limbs or 64-bit values) cost nothing
-  if (offsets[w * half + lo] == offsets[w * half + lo + chunk]) {
+  if (offsets && offsets[w * half + lo] == offsets[w * half + lo + chunk]) {
     st_struct(partials + gid, sum);
+    if (chunk_sums) st_struct(chunk_sums + gid, acc);
     return;
   }
   for (int b = (int)(lo + chunk) - 1; b >= (int)lo; b--) {
@@ -448,21 +458,31 @@ __global__ void __launch_bounds__(128)
     add_full(acc, bk);
     add_full(sum, acc);
   }
-  if (lo > 0 && !acc.is_inf()) {
+  // sum = sum_j (j + 1) E[lo + j], acc = sum_j E[lo + j]
+  if (weight_off == 0 && !acc.is_inf()) {
+    XYZZ<F> t = neg(acc);
+    add_full(sum, t);
+  }
+  if (chunk_sums) {
+    st_struct(chunk_sums + gid, acc);
+  } else if (lo > 0 && !acc.is_inf()) {
     XYZZ<F> t = mul_small(acc, lo);
     add_full(sum, t);
   }
   st_struct(partials + gid, sum);
 }
 
+// out[w * gridDim.x + g] = sum of partials[w][g * per_cta .. (g + 1) * per_cta)   (grid: (groups, windows))
+constexpr uint32_t WINDOW_FINAL_PER_CTA = 2048;
 template <class F>
 __global__ void __launch_bounds__(128)
-    k_msm_window_final(const XYZZ<F>* __restrict__ partials, uint32_t nchunks, XYZZ<F>* __restrict__ window_sums) {
+    k_msm_window_final(const XYZZ<F>* __restrict__ partials, uint32_t nchunks, uint32_t per_cta, XYZZ<F>* __restrict__ window_sums) {
   extern __shared__ uint4 smem_raw[];
   XYZZ<F>* sm = reinterpret_cast<XYZZ<F>*>(smem_raw);
-  const uint32_t w = blockIdx.x, tid = threadIdx.x;
+  const uint32_t w = blockIdx.y, tid = threadIdx.x;
+  const uint32_t lo = blockIdx.x * per_cta, hi = min(nchunks, lo + per_cta);
   XYZZ<F> acc = XYZZ<F>::inf();
-  for (uint32_t i = tid; i < nchunks; i += blockDim.x) {
+  for (uint32_t i = lo + tid; i < hi; i += blockDim.x) {
     XYZZ<F> p = partials[(size_t)w * nchunks + i];
     add_full(acc, p);
   }
@@ -476,7 +496,7 @@ __global__ void __launch_bounds__(128)
     }
     __syncthreads();
   }
-  if (tid == 0) st_struct(window_sums + w, acc);
+  if (tid == 0) st_struct(window_sums + (size_t)w * gridDim.x + blockIdx.x, acc);
 }
 
 static int choose_window(size_t n) {
@@ -488,20 +508,29 @@ static int choose_window(size_t n) {
   return c;
 }
 
+// fixed_windows == 0: windowed Pippenger over `points` (n bases).
+// fixed_windows == W > 0 (fixed-base mode): `points` is a table of W n bases, entry w n + i = 2^(c w) P_i
+// (gpw_msm_g1_fixed_table); W must equal the number of c-bit windows of a scalar. Every digit of every scalar then
+// lands in ONE set of 2^(c-1) buckets, so the bucket reduction is paid once instead of once per window and wide
+// windows become affordable: c = 22 needs 12 additions per full-width scalar instead of the 16 of c = 16.
 template <class F>
 static int msm_dev_impl(gpw_ctx* ctx, const Fr* scalars, const Affine<F>* points, size_t n, int mont, int c,
-                        int win_lo, int win_hi, uint64_t* out_affine, const char* tag) {
+                        int win_lo, int win_hi, uint64_t* out_affine, const char* tag, int fixed_windows = 0) {
   constexpr int OUT_WORDS = (int)(sizeof(Affine<F>) / 8);
   if (n >= (1ull << 31)) {
     set_error("msm: n=%zu too large (max 2^31-1)", n);
     return GPW_EINVAL;
   }
   if (c == 0) c = choose_window(n ? n : 1);
-  if (c < 2 || c > 16) {
-    set_error("msm: window_bits=%d out of range [2,16]", c);
+  if (c < 2 || c > (fixed_windows ? 24 : 16)) {
+    set_error("msm: window_bits=%d out of range [2,%d]", c, fixed_windows ? 24 : 16);
     return GPW_EINVAL;
   }
   const int nwin = (254 + c) / c;  // ceil(255 / c): room for the final signed-digit carry
+  if (fixed_windows && (fixed_windows != nwin || win_lo != 0 || (win_hi != 0 && win_hi != nwin))) {
+    set_error("msm: fixed-base table must hold all %d windows of %d bits (got %d)", nwin, c, fixed_windows);
+    return GPW_EINVAL;
+  }
   if (win_lo == 0 && win_hi == 0) win_hi = nwin;
   if (win_lo < 0 || win_hi > nwin || win_lo >= win_hi) {
     set_error("msm: bad window range [%d,%d) of %d", win_lo, win_hi, nwin);
@@ -513,10 +542,14 @@ static int msm_dev_impl(gpw_ctx* ctx, const Fr* scalars, const Affine<F>* points
   }
   GPW_CUDA(cudaSetDevice(ctx->device));
   cudaStream_t st = ctx->stream;
-  const int nw = win_hi - win_lo;
+  const int nw = fixed_windows ? 1 : win_hi - win_lo;  // bucket sets
   const uint32_t half = 1u << (c - 1);
   const uint32_t B = (uint32_t)nw * half;
-  const uint64_t max_entries = (uint64_t)n * nw;
+  const uint64_t max_entries = (uint64_t)n * (win_hi - win_lo);
+  if (fixed_windows && max_entries >= (1ull << 31)) {
+    set_error("msm: fixed-base table index n * windows = %llu exceeds 2^31", (unsigned long long)max_entries);
+    return GPW_EINVAL;
+  }
   if (max_entries >= (1ull << 32)) {
     set_error("msm: n * windows = %llu exceeds 2^32 entries; split the call", (unsigned long long)max_entries);
     return GPW_EINVAL;
@@ -542,14 +575,27 @@ static int msm_dev_impl(gpw_ctx* ctx, const Fr* scalars, const Affine<F>* points
   GPW_TRY(ctx->get_scratch((T + ".buckets").c_str(), (size_t)B * sizeof(XYZZ<F>), (void**)&buckets));
   GPW_TRY(ctx->get_scratch((T + ".head").c_str(), (size_t)ntasks * sizeof(XYZZ<F>), (void**)&head));
   GPW_TRY(ctx->get_scratch((T + ".tail").c_str(), (size_t)ntasks * sizeof(XYZZ<F>), (void**)&tail));
-  GPW_TRY(ctx->get_scratch((T + ".partials").c_str(), (size_t)nw * nchunks * sizeof(XYZZ<F>), (void**)&partials));
-  GPW_TRY(ctx->get_scratch((T + ".wsums").c_str(), (size_t)nw * sizeof(XYZZ<F>), (void**)&wsums));
+  const uint32_t ngroups = (nchunks + WINDOW_FINAL_PER_CTA - 1) / WINDOW_FINAL_PER_CTA;
+  if (ngroups > WINDOW_FINAL_PER_CTA) {
+    set_error("msm: too many buckets per window");
+    return GPW_EINVAL;
+  }
+  // level 1 of the window reduction works on the nchunks chunk sums of each window
+  const uint32_t chunk2 = nchunks < 16u ? nchunks : 16u;
+  const uint32_t nchunks2 = nchunks / chunk2;
+  const uint32_t ngroups2 = (nchunks2 + WINDOW_FINAL_PER_CTA - 1) / WINDOW_FINAL_PER_CTA;  // <= ngroups
+  XYZZ<F>*chunk_sums, *partials2;
+  GPW_TRY(ctx->get_scratch((T + ".partials").c_str(), (size_t)nw * (2 * (size_t)nchunks + nchunks2) * sizeof(XYZZ<F>), (void**)&partials));
+  chunk_sums = partials + (size_t)nw * nchunks;
+  partials2 = chunk_sums + (size_t)nw * nchunks;
+  // wsums: [0, nw) level-0 sums T_w | [nw, 2 nw) level-1 sums | intermediates of the two-round sums
+  GPW_TRY(ctx->get_scratch((T + ".wsums").c_str(), (size_t)nw * (2 + ngroups + ngroups2) * sizeof(XYZZ<F>), (void**)&wsums));
 
   GPW_CUDA(cudaEventRecord(ctx->ev[0], st));
   GPW_CUDA(cudaMemsetAsync(counts, 0, (size_t)(B + 1) * 4 * 3 + 64, st));
   GPW_CUDA(cudaMemsetAsync(buckets, 0, (size_t)B * sizeof(XYZZ<F>), st));
   const int TPB = 256;
-  k_msm_digits<false><<<div_up(n, TPB), TPB, 0, st>>>(scalars, n, mont, c, nwin, win_lo, win_hi, counts, nullptr);
+  k_msm_digits<false><<<div_up(n, TPB), TPB, 0, st>>>(scalars, n, mont, c, nwin, win_lo, win_hi, fixed_windows, counts, nullptr);
   GPW_CHECK_LAUNCH();
   k_msm_scan_sums<<<nscan_blocks, SCAN_THREADS, 0, st>>>(counts, B, block_sums);
   GPW_CHECK_LAUNCH();
@@ -557,7 +603,7 @@ static int msm_dev_impl(gpw_ctx* ctx, const Fr* scalars, const Affine<F>* points
   GPW_CHECK_LAUNCH();
   k_msm_scan_final<<<nscan_blocks, SCAN_THREADS, 0, st>>>(counts, B, block_sums, offsets, cursor);
   GPW_CHECK_LAUNCH();
-  k_msm_digits<true><<<div_up(n, TPB), TPB, 0, st>>>(scalars, n, mont, c, nwin, win_lo, win_hi, cursor, sorted);
+  k_msm_digits<true><<<div_up(n, TPB), TPB, 0, st>>>(scalars, n, mont, c, nwin, win_lo, win_hi, fixed_windows, cursor, sorted);
   GPW_CHECK_LAUNCH();
   GPW_CUDA(cudaEventRecord(ctx->ev[1], st));
   k_msm_accumulate<F><<<div_up(ntasks, MSM_ACC_THREADS), MSM_ACC_THREADS, MSM_ACC_THREADS * sizeof(XYZZ<F>), st>>>(
@@ -572,14 +618,33 @@ static int msm_dev_impl(gpw_ctx* ctx, const Fr* scalars, const Affine<F>* points
                                                                                           nbig, buckets);
   }
   GPW_CHECK_LAUNCH();
-  k_msm_window_partial<F><<<div_up((size_t)nw * nchunks, 128), 128, 0, st>>>(buckets, offsets, half, chunk, (uint32_t)nw, partials);
+  k_msm_window_partial<F><<<div_up((size_t)nw * nchunks, 128), 128, 0, st>>>(buckets, offsets, half, chunk, (uint32_t)nw, 1u, partials,
+                                                                             chunk_sums);
   GPW_CHECK_LAUNCH();
-  k_msm_window_final<F><<<nw, 128, 128 * sizeof(XYZZ<F>), st>>>(partials, nchunks, wsums);
+  k_msm_window_partial<F><<<div_up((size_t)nw * nchunks2, 128), 128, 0, st>>>(chunk_sums, nullptr, nchunks, chunk2, (uint32_t)nw, 0u,
+                                                                              partials2, nullptr);
   GPW_CHECK_LAUNCH();
+  // per-window sums of an array of `cnt` partials per window -> dst[0 .. nw)  (two rounds above 2048 partials)
+  auto sum_partials = [&](const XYZZ<F>* src, uint32_t cnt, uint32_t groups, XYZZ<F>* tmp, XYZZ<F>* dst) -> int {
+    if (groups == 1) {
+      k_msm_window_final<F><<<dim3(1, nw), 128, 128 * sizeof(XYZZ<F>), st>>>(src, cnt, WINDOW_FINAL_PER_CTA, dst);
+      GPW_CHECK_LAUNCH();
+      ctx->launches += 1;
+    } else {
+      k_msm_window_final<F><<<dim3(groups, nw), 128, 128 * sizeof(XYZZ<F>), st>>>(src, cnt, WINDOW_FINAL_PER_CTA, tmp);
+      GPW_CHECK_LAUNCH();
+      k_msm_window_final<F><<<dim3(1, nw), 128, 128 * sizeof(XYZZ<F>), st>>>(tmp, groups, WINDOW_FINAL_PER_CTA, dst);
+      GPW_CHECK_LAUNCH();
+      ctx->launches += 2;
+    }
+    return GPW_OK;
+  };
+  GPW_TRY(sum_partials(partials, nchunks, ngroups, wsums + 2 * nw, wsums));
+  GPW_TRY(sum_partials(partials2, nchunks2, ngroups2, wsums + (size_t)nw * (2 + ngroups), wsums + nw));
   ctx->launches += 10;
-  const XYZZ<F>* hw = (const XYZZ<F>*)ctx->pin_take((size_t)nw * sizeof(XYZZ<F>));
+  const XYZZ<F>* hw = (const XYZZ<F>*)ctx->pin_take((size_t)2 * nw * sizeof(XYZZ<F>));
   const uint32_t* Mp = (const uint32_t*)ctx->pin_take(4);
-  GPW_CUDA(cudaMemcpyAsync((void*)hw, wsums, (size_t)nw * sizeof(XYZZ<F>), cudaMemcpyDeviceToHost, st));
+  GPW_CUDA(cudaMemcpyAsync((void*)hw, wsums, (size_t)2 * nw * sizeof(XYZZ<F>), cudaMemcpyDeviceToHost, st));
   GPW_CUDA(cudaMemcpyAsync((void*)Mp, offsets + B, 4, cudaMemcpyDeviceToHost, st));
   GPW_CUDA(cudaEventRecord(ctx->ev[3], st));
   GPW_CUDA(cudaStreamSynchronize(st));
@@ -599,11 +664,48 @@ static int msm_dev_impl(gpw_ctx* ctx, const Fr* scalars, const Affine<F>* points
   XYZZ<F> R = XYZZ<F>::inf();
   for (int w = nw - 1; w >= 0; w--) {
     for (int k = 0; k < c; k++) R = dbl(R);
+    // window sum = level-0 sum + chunk * level-1 sum
+    XYZZ<F> l1 = hw[nw + w];
+    for (uint32_t k = 1; k < chunk; k <<= 1) l1 = dbl(l1);
     add_full(R, hw[w]);
+    add_full(R, l1);
   }
-  for (int k = 0; k < c * win_lo; k++) R = dbl(R);
+  for (int k = 0; k < c * win_lo; k++) R = dbl(R);  // (fixed-base mode: one bucket set, win_lo = 0 -> R = hw[0])
   Affine<F> a = to_affine(R);
   memcpy(out_affine, &a, sizeof(a));
+  return GPW_OK;
+}
+
+// table[w n + i] = 2^(c w) P_i, w < W (one thread per base: c doublings and one inversion per entry; setup only)
+template <class F>
+__global__ void __launch_bounds__(128)
+    k_msm_fixed_table(const Affine<F>* __restrict__ points, size_t n, int c, int W, Affine<F>* __restrict__ table) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const Affine<F> p = ld_struct(points + i);
+  st_struct(table + i, p);
+  XYZZ<F> cur = XYZZ<F>::from_affine(p);
+#pragma unroll 1
+  for (int w = 1; w < W; w++) {
+#pragma unroll 1
+    for (int k = 0; k < c; k++) cur = dbl(cur);
+    const Affine<F> a = to_affine(cur);
+    st_struct(table + (size_t)w * n + i, a);
+    cur = XYZZ<F>::from_affine(a);  // keeps the next doublings' operands short-lived and the result canonical
+  }
+}
+
+template <class F>
+static int msm_fixed_table_impl(gpw_ctx* ctx, const Affine<F>* points, size_t n, int c, int W, Affine<F>* table) {
+  if (!ctx || (!points && n) || (!table && n) || c < 2 || c > 24 || W != (254 + c) / c) {
+    set_error("msm_fixed_table: bad argument (W must be ceil(255 / window_bits))");
+    return GPW_EINVAL;
+  }
+  if (!n) return GPW_OK;
+  GPW_CUDA(cudaSetDevice(ctx->device));
+  k_msm_fixed_table<F><<<div_up(n, 128), 128, 0, ctx->stream>>>(points, n, c, W, table);
+  GPW_CHECK_LAUNCH();
+  ctx->launches += 1;
   return GPW_OK;
 }
 

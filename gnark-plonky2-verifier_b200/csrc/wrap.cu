@@ -148,6 +148,8 @@ int gpw_ec_generator_multiples_dev(gpw_ctx* ctx, int group, uint64_t k0, size_t 
 int gpw_msm_g1_dev(gpw_ctx* ctx, uint64_t s, uint64_t p, size_t n, int mont, int c, int lo, int hi, uint64_t* out);
 int gpw_msm_g2_dev(gpw_ctx* ctx, uint64_t s, uint64_t p, size_t n, int mont, int c, int lo, int hi, uint64_t* out);
 int gpw_groth16_compute_h_dev(gpw_ctx* ctx, uint64_t a_dev, uint64_t b_dev, uint64_t c_dev, int logN);
+int gpw_msm_g1_fixed_table(gpw_ctx* ctx, uint64_t points_dev, size_t n, int window_bits, int n_windows, uint64_t table_dev);
+int gpw_msm_g1_fixed_dev(gpw_ctx* ctx, uint64_t s, uint64_t table, size_t n, int mont, int c, int n_windows, uint64_t* out);
 }
 
 // Proving key for a compiled circuit. Bases are synthetic (known discrete logs, documented below) - the analogue of
@@ -166,7 +168,8 @@ struct WrapLane {
   cudaEvent_t done = nullptr;
   float t_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 };
-constexpr int WRAP_DEFAULT_LANES = 4, WRAP_MAX_LANES = 16;
+constexpr int WRAP_DEFAULT_LANES = 6, WRAP_MAX_LANES = 16;
+constexpr int FIXED_C = 22, FIXED_W = (254 + FIXED_C) / FIXED_C;
 
 struct gpw_wrap_key {
   gpw_ctx* ctx = nullptr;
@@ -178,6 +181,10 @@ struct gpw_wrap_key {
   uint32_t *suppA = nullptr, *suppB = nullptr;  // device wire-id lists
   G1Affine *A = nullptr, *B1 = nullptr, *K = nullptr, *Z = nullptr, *CK = nullptr, *CKs = nullptr;
   G2Affine* B2 = nullptr;
+  // fixed-base tables (2^(22 w) P, 12 windows) for the two MSMs whose scalars are full-width field elements: Z (the
+  // quotient coefficients h) and the K range behind the committed wires (the log-derivative quotients). 12 instead of
+  // 16 bucket additions per scalar; 8.4 GB of HBM. GPW_FIXED_BASE=0 keeps the plain windowed MSMs.
+  G1Affine *Zt = nullptr, *K2t = nullptr;
   G1Affine alpha1, beta1, delta1;
   G2Affine beta2, delta2;
   uint32_t n_inputs = 0;
@@ -244,7 +251,7 @@ extern "C" void gpw_wrap_key_free(gpw_wrap_key* k) {
   if (!k) return;
   cudaSetDevice(k->ctx->device);
   for (WrapLane* l : k->lanes) lane_free(l);
-  void* ps[] = {k->suppA, k->suppB, k->A, k->B1, k->K, k->Z, k->CK, k->CKs, k->B2};
+  void* ps[] = {k->suppA, k->suppB, k->A, k->B1, k->K, k->Z, k->CK, k->CKs, k->B2, k->Zt, k->K2t};
   for (void* p : ps) cudaFree(p);
   delete k;
 }
@@ -313,6 +320,19 @@ extern "C" int gpw_wrap_key_synthetic(gpw_ctx* ctx, gpw_circuit* circ, uint64_t 
   GPW_TRY(gpw_ec_generator_multiples_dev(ctx, 1, 1ull << 34, N - 1, (uint64_t)k->Z));
   GPW_TRY(gpw_ec_generator_multiples_dev(ctx, 1, (1ull << 35) + k->limb_start, k->n_committed, (uint64_t)k->CK));
   GPW_TRY(gpw_ec_generator_multiples_dev(ctx, 1, (1ull << 36) + k->limb_start, k->n_committed, (uint64_t)k->CKs));
+  {
+    const char* e = getenv("GPW_FIXED_BASE");
+    const uint32_t c_hi = k->n_committed ? k->limb_start + k->n_committed : k->m;
+    if (!(e && atoi(e) == 0)) {
+      if ((rc = wk_alloc((void**)&k->Zt, (size_t)FIXED_W * (N - 1) * sizeof(G1Affine))) ||
+          (c_hi < k->m && (rc = wk_alloc((void**)&k->K2t, (size_t)FIXED_W * (k->m - c_hi) * sizeof(G1Affine))))) {
+        gpw_wrap_key_free(k);
+        return rc;
+      }
+      GPW_TRY(gpw_msm_g1_fixed_table(ctx, (uint64_t)k->Z, N - 1, FIXED_C, FIXED_W, (uint64_t)k->Zt));
+      if (k->K2t) GPW_TRY(gpw_msm_g1_fixed_table(ctx, (uint64_t)(k->K + c_hi), k->m - c_hi, FIXED_C, FIXED_W, (uint64_t)k->K2t));
+    }
+  }
   k->alpha1 = gen_mul_host<Fp>(seed + 1);
   k->beta1 = gen_mul_host<Fp>(seed + 2);
   k->delta1 = gen_mul_host<Fp>(seed + 3);
@@ -333,7 +353,7 @@ extern "C" int gpw_wrap_key_info(const gpw_wrap_key* k, uint64_t* info8) {
 
 extern "C" uint64_t gpw_wrap_key_wires_dev(const gpw_wrap_key* k) { return k ? (uint64_t)k->lanes[0]->wires : 0; }
 
-// Number of proofs gpw_wrap_prove_many keeps in flight (default 4; each lane holds ~1.5 GB of vectors plus its MSM scratch).
+// Number of proofs gpw_wrap_prove_many keeps in flight (default 6; each lane holds ~1.5 GB of vectors plus its MSM scratch).
 extern "C" int gpw_wrap_set_lanes(gpw_wrap_key* k, int n) {
   if (!k || n < 1 || n > WRAP_MAX_LANES) {
     set_error("wrap_set_lanes: n must be in [1, %d]", WRAP_MAX_LANES);
@@ -471,10 +491,13 @@ static int wrap_stage2(gpw_wrap_key* k, WrapLane* L, const uint64_t* r_canon, co
   GPW_TRY(gpw_msm_g1_dev(ctx, (uint64_t)(wires + k_lo), (uint64_t)(k->K + k_lo), c_lo - k_lo, 1, 0, 0, 0, (uint64_t*)&mK1));
   report("K1", c_lo - k_lo);
   mK2 = G1Affine{Fp::zero(), Fp::zero()};
-  if (c_hi < k->m)
-    GPW_TRY(gpw_msm_g1_dev(ctx, (uint64_t)(wires + c_hi), (uint64_t)(k->K + c_hi), k->m - c_hi, 1, 0, 0, 0, (uint64_t*)&mK2));
-  if (c_hi < k->m) report("K2", k->m - c_hi);
-  GPW_TRY(gpw_msm_g1_dev(ctx, (uint64_t)L->va, (uint64_t)k->Z, N - 1, 1, 0, 0, 0, (uint64_t*)&mZ));
+  if (c_hi < k->m) {
+    if (k->K2t) GPW_TRY(gpw_msm_g1_fixed_dev(ctx, (uint64_t)(wires + c_hi), (uint64_t)k->K2t, k->m - c_hi, 1, FIXED_C, FIXED_W, (uint64_t*)&mK2));
+    else GPW_TRY(gpw_msm_g1_dev(ctx, (uint64_t)(wires + c_hi), (uint64_t)(k->K + c_hi), k->m - c_hi, 1, 0, 0, 0, (uint64_t*)&mK2));
+    report("K2", k->m - c_hi);
+  }
+  if (k->Zt) GPW_TRY(gpw_msm_g1_fixed_dev(ctx, (uint64_t)L->va, (uint64_t)k->Zt, N - 1, 1, FIXED_C, FIXED_W, (uint64_t*)&mZ));
+  else GPW_TRY(gpw_msm_g1_dev(ctx, (uint64_t)L->va, (uint64_t)k->Z, N - 1, 1, 0, 0, 0, (uint64_t*)&mZ));
   report("Z", N - 1);
   GPW_CUDA(cudaEventRecord(ev[6], st));
   GPW_CUDA(cudaStreamSynchronize(st));

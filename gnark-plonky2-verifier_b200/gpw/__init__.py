@@ -57,6 +57,8 @@ SYMBOLS = {
     "gpw_msm_g2": (C.c_int, [_vp, _vp, _vp, C.c_size_t, C.c_int, C.c_int, _vp]),
     "gpw_msm_g1_dev": (C.c_int, [_vp, C.c_uint64, C.c_uint64, C.c_size_t, C.c_int, C.c_int, C.c_int, C.c_int, _vp]),
     "gpw_msm_g2_dev": (C.c_int, [_vp, C.c_uint64, C.c_uint64, C.c_size_t, C.c_int, C.c_int, C.c_int, C.c_int, _vp]),
+    "gpw_msm_g1_fixed_table": (C.c_int, [_vp, C.c_uint64, C.c_size_t, C.c_int, C.c_int, C.c_uint64]),
+    "gpw_msm_g1_fixed_dev": (C.c_int, [_vp, C.c_uint64, C.c_uint64, C.c_size_t, C.c_int, C.c_int, C.c_int, _vp]),
     "gpw_msm_last_stats": (C.c_int, [_vp, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_uint64)]),
     "gpw_ntt_fr": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
     "gpw_ntt_fr_dev": (C.c_int, [_vp, C.c_uint64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
@@ -256,6 +258,20 @@ class Context:
         out = np.zeros(_pt_words(group), dtype=np.uint64)
         fn = _lib.gpw_msm_g1_dev if group == 1 else _lib.gpw_msm_g2_dev
         _check(fn(self._h, scalars_ptr, points_ptr, n, int(scalars_mont), window_bits, win_lo, win_hi, _p(out)))
+        return out
+
+    @staticmethod
+    def msm_fixed_windows(window_bits):
+        return (254 + window_bits) // window_bits
+
+    def msm_g1_fixed_table(self, points_ptr, n, window_bits, table_ptr):
+        """table (device, msm_fixed_windows(window_bits) * n G1 affine points) <- 2^(window_bits w) P_i"""
+        _check(_lib.gpw_msm_g1_fixed_table(self._h, points_ptr, n, window_bits, self.msm_fixed_windows(window_bits), table_ptr))
+
+    def msm_g1_fixed_dev(self, scalars_ptr, table_ptr, n, window_bits, scalars_mont=False):
+        out = np.zeros(_pt_words(1), dtype=np.uint64)
+        _check(_lib.gpw_msm_g1_fixed_dev(self._h, scalars_ptr, table_ptr, n, int(scalars_mont), window_bits,
+                                         self.msm_fixed_windows(window_bits), _p(out)))
         return out
 
     def msm_last_stats(self):

@@ -81,6 +81,13 @@ int gpw_msm_g2(gpw_ctx* ctx, const uint64_t* scalars, const uint64_t* points, si
  * split (pass 0, 0 for all): the returned point is then sum_{w in range} 2^(c w) W_w.            */
 int gpw_msm_g1_dev(gpw_ctx* ctx, uint64_t scalars_dev, uint64_t points_dev, size_t n, int scalars_mont,
                    int window_bits, int win_lo, int win_hi, uint64_t* out_affine);
+/* Fixed-base MSM for bases known at setup (a proving key): gpw_msm_g1_fixed_table fills table_dev (n_windows * n affine
+ * points, entry w n + i = 2^(window_bits w) P_i) with n_windows = ceil(255 / window_bits), window_bits <= 24;
+ * gpw_msm_g1_fixed_dev then puts every digit of every scalar into ONE bucket set: ceil(255 / window_bits) bucket
+ * additions per full-width scalar (12 at 22 bits instead of 16 at 16 bits) and one bucket reduction.                  */
+int gpw_msm_g1_fixed_table(gpw_ctx* ctx, uint64_t points_dev, size_t n, int window_bits, int n_windows, uint64_t table_dev);
+int gpw_msm_g1_fixed_dev(gpw_ctx* ctx, uint64_t scalars_dev, uint64_t table_dev, size_t n, int scalars_mont, int window_bits,
+                         int n_windows, uint64_t* out_affine);
 int gpw_msm_g2_dev(gpw_ctx* ctx, uint64_t scalars_dev, uint64_t points_dev, size_t n, int scalars_mont,
                    int window_bits, int win_lo, int win_hi, uint64_t* out_affine);
 /* Time (ms, CUDA events on the ctx stream) spent in the bucket-accumulation kernel of the most
@@ -183,7 +190,7 @@ int gpw_wrap_prove_dev(gpw_wrap_key* k, uint64_t inputs_dev, const uint64_t* r_c
 /* A stream of n independent proofs with several of them in flight: one host thread + stream + scratch ("lane") per
  * in-flight proof, so that the sequential solve spine of one proof (one SM) and the host glue of another overlap the
  * MSMs / NTTs of the rest. inputs: n x n_inputs x 4 u64 (host or device); r, s: n x 4 u64; out: n x 64 u64. Blocking.
- * gpw_wrap_set_lanes: proofs in flight (default 4, env GPW_WRAP_LANES; 1 = strictly one after the other).           */
+ * gpw_wrap_set_lanes: proofs in flight (default 6, env GPW_WRAP_LANES; 1 = strictly one after the other).           */
 int gpw_wrap_prove_many(gpw_wrap_key* k, const uint64_t* inputs, int n, const uint64_t* r_canonical, const uint64_t* s_canonical,
                         int check, uint64_t* out_proofs);
 int gpw_wrap_set_lanes(gpw_wrap_key* k, int n);

@@ -282,6 +282,32 @@ def test_msm_window_split_matches_full(ctx):
     assert (acc == full).all()
 
 
+@pytest.mark.parametrize("window_bits", [7, 16, 22])
+def test_msm_fixed_base_matches_windowed(ctx, window_bits):
+    # fixed-base mode (precomputed 2^(c w) P_i, one bucket set) must give the same group element as the windowed MSM
+    import torch
+    rng = random.Random(40 + window_bits)
+    n = 3000
+    pts = gpw.host_ec_generator_multiples(1, 5, n)
+    pts[17] = 0                                              # a base at infinity
+    scalars = [rng.randrange(ob.R) if i % 4 else rng.randrange(1 << 20) for i in range(n)]
+    scalars[0], scalars[1], scalars[2] = 0, 1, ob.R - 1
+    sl = gpw.ints_to_limbs(scalars)
+    ref = ctx.msm(1, sl, pts)
+    ds = torch.from_numpy(sl.view(np.int64)).cuda()
+    dp = torch.from_numpy(pts.view(np.int64)).cuda()
+    W = ctx.msm_fixed_windows(window_bits)
+    table = torch.zeros((W * n, 8), dtype=torch.int64, device="cuda")
+    torch.cuda.synchronize()
+    ctx.msm_g1_fixed_table(dp.data_ptr(), n, window_bits, table.data_ptr())
+    out = ctx.msm_g1_fixed_dev(ds.data_ptr(), table.data_ptr(), n, window_bits)
+    assert (out == ref).all()
+    # table rows really are 2^(c w) P_i
+    row = table[2 * n + 3].cpu().numpy().view(np.uint64)
+    exp = ob.ec_mul(1, ob.G1_GEN, (8 << (2 * window_bits)) % ob.R)
+    assert gpw.points_to_ints(1, row)[0] == ob.point_key(1, exp)
+
+
 # ---- K8: NTT ------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("logn", [0, 1, 2, 3, 5, 8, 9, 10])
 def test_ntt_small_vs_definition(ctx, logn):
