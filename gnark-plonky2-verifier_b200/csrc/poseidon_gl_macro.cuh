@@ -64,13 +64,33 @@ GPW_HD U192 mul128x64(uint64_t a0, uint64_t a1, uint64_t b) {
   return r;
 }
 
-// ReduceHint of a 192-bit integer: emits (q, r) at slot, slot + 1 and returns r
+// ReduceHint (goldilocks/base.go:284-294) specialised to x < p 2^128 (top limb < p; everything the permutation reduces
+// is below p^3), so q = floor(x / p) < 2^128. r by three 2^64 = 2^32 - 1 foldings; q = (x - r) * p^-1 mod 2^128 (exact
+// division by the odd p) with p^-1 mod 2^128 = (2^64 - 2^32) 2^64 + (2^32 + 1): three 64-bit multiplies instead of the ten
+// of the general form. gl::reduce_hint is the general (256-bit) form; the circuit tests hold the two against each other
+// (every hint output of the macro is compared with the oracle's trace).
+GPW_HD void reduce192(const U192& v, uint64_t& q0, uint64_t& q1, uint64_t& r) {
+  uint64_t acc = v.l[2] >= gl::P ? v.l[2] - gl::P : v.l[2];
+  acc = gl::reduce128(v.l[1], acc);
+  acc = gl::reduce128(v.l[0], acc);
+  r = acc;
+  const uint64_t d0 = v.l[0] - r;
+  const uint64_t d1 = v.l[1] - (v.l[0] < r ? 1u : 0u);
+  // q = (d1 2^64 + d0) * ((2^64 - 2^32) 2^64 + (2^32 + 1)) mod 2^128. Written with plain 64-bit multiplies: the
+  // hand-expanded shift-and-add form (q0 = d0 + (d0 << 32), q1 = carry + (d0 >> 32) - (d0 << 32) + d1 + (d1 << 32)) is
+  // correct on the host but came out of nvcc 12.9 / sm_100a with the "- (d0 << 32)" term added; tools/scratch/
+  // t_reduce192.cu checks this function against gl::reduce_hint ON THE DEVICE. Three multiplies do not bound the macro.
+  uint64_t hi0;
+  gl::mul64(d0, 0x100000001ull, q0, hi0);
+  q1 = hi0 + d0 * 0xffffffff00000000ull + d1 * 0x100000001ull;
+}
+
+// emits (q, r) of Reduce(v) at slot, slot + 1 and returns r
 template <class Emit>
 GPW_HD uint64_t reduce_emit(const U192& v, uint32_t slot, Emit& emit) {
-  const uint64_t x[4] = {v.l[0], v.l[1], v.l[2], 0};
-  uint64_t q[4], r;
-  gl::reduce_hint(x, q, r);
-  emit(slot, U192{{q[0], q[1], q[2]}});
+  uint64_t q0, q1, r;
+  reduce192(v, q0, q1, r);
+  emit(slot, U192{{q0, q1, 0}});
   emit(slot + 1, u192(r));
   return r;
 }

@@ -70,7 +70,7 @@ struct Segment {
 };
 
 constexpr uint32_t WIDE_THRESHOLD = 8192;
-constexpr int NARROW_THREADS = 128;
+constexpr int NARROW_THREADS = 256;  // upper bound (launch bounds); the spine launches spine_threads() of them
 
 __device__ __forceinline__ Fr ld_w(const Fr* p) {
   Fr r;
@@ -333,6 +333,14 @@ constexpr uint32_t CHUNK_FLAG_GL_MACRO = 1;  // chunk header word [3]: the chunk
 // proofs in flight, wrap.cu) their warps would saturate the SM's IMAD pipe and stretch every level of the spine. It
 // therefore asks for the SM's whole shared memory, which keeps every kernel that uses shared memory off its SM.
 constexpr size_t SPINE_EXCLUSIVE_SMEM_BYTES = 227 * 1024;
+static int spine_threads() {
+  static const int v = [] {
+    const char* e = getenv("GPW_SPINE_THREADS");
+    int t = e ? atoi(e) : NARROW_THREADS;
+    return (t >= 32 && t <= NARROW_THREADS && t % 32 == 0) ? t : NARROW_THREADS;
+  }();
+  return v;
+}
 static size_t spine_smem_bytes() {
   static const size_t v = getenv("GPW_SPINE_SHARED_SM") ? STAGED_SMEM_BYTES : SPINE_EXCLUSIVE_SMEM_BYTES;
   return v;
@@ -347,7 +355,7 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 
 __global__ void __launch_bounds__(NARROW_THREADS)
     k_tape_staged(DevCircuit c, const uint32_t* __restrict__ stream, uint32_t first_words, Fr* __restrict__ wires, size_t wire_stride,
-                  int* __restrict__ err, uint32_t* __restrict__ hist) {
+                  int* __restrict__ err, uint32_t* __restrict__ hist, unsigned long long* __restrict__ prof) {
   extern __shared__ __align__(16) uint32_t dyn_smem[];
   uint32_t(*buf)[CHUNK_MAX_WORDS] = reinterpret_cast<uint32_t(*)[CHUNK_MAX_WORDS]>(dyn_smem);
   Fr* ring = reinterpret_cast<Fr*>(dyn_smem + 2 * CHUNK_MAX_WORDS);
@@ -361,9 +369,19 @@ __global__ void __launch_bounds__(NARROW_THREADS)
   for (uint32_t i = threadIdx.x * 4; i < words; i += blockDim.x * 4) cp_async_16(&buf[0][i], src + i);
   cp_async_commit();
   int cur = 0;
+  // development profile (GPW_SPINE_PROFILE): cycles of thread 0 spent [0] waiting for the chunk, [1] in macro input fetch,
+  // [2] in the native permutation, [3] in the macro's conversion + stores, [4] in ordinary chunks; [5] macros, [6] chunks
+  unsigned long long pc[7] = {0, 0, 0, 0, 0, 0, 0};
+  long long t_prev = clock64();
+  auto lap = [&](int k) {
+    const long long now = clock64();
+    pc[k] += (unsigned long long)(now - t_prev);
+    t_prev = now;
+  };
   while (words) {
     cp_async_wait_all();
     __syncthreads();  // chunk `cur` is resident; wires written by the previous chunk are visible
+    lap(0);
     const uint32_t* ch = buf[cur];
     const uint32_t n_instr = ch[0], next_words = ch[1];
     const uint32_t* next_src = src + words;
@@ -386,6 +404,7 @@ __global__ void __launch_bounds__(NARROW_THREADS)
         glm_io[threadIdx.x] = x[0];
       }
       __syncthreads();
+      lap(1);
       if (threadIdx.x < 32)
         glm::trace_warp(threadIdx.x < 12 ? glm_io[threadIdx.x] : 0ull, glm_io + 12, c.gl_tables, [&](uint32_t slot, const glm::U192& v) {
           glm_trace[3 * slot] = v.l[0];
@@ -393,11 +412,13 @@ __global__ void __launch_bounds__(NARROW_THREADS)
           glm_trace[3 * slot + 2] = v.l[2];
         });
       __syncthreads();
+      lap(2);
       for (uint32_t k = threadIdx.x; k < nout; k += blockDim.x) {
         const Fr v = fr_from_u192(glm::U192{{glm_trace[3 * k], glm_trace[3 * k + 1], glm_trace[3 * k + 2]}});
         st_w(W + outs[k], v);
         st_w(ring + ((slot0 + k) & (RING_SLOTS - 1)), v);
       }
+      pc[5]++;
     } else
     for (uint32_t i = threadIdx.x; i < n_instr; i += blockDim.x) {
       const uint32_t* rec = ch + ch[4 + i];
@@ -417,7 +438,11 @@ __global__ void __launch_bounds__(NARROW_THREADS)
     words = next_words;
     cur ^= 1;
     __syncthreads();  // everyone is done reading chunk `cur^1`... (now the old buffer) before it is overwritten
+    lap(ch[3] == CHUNK_FLAG_GL_MACRO ? 3 : 4);
+    pc[6]++;
   }
+  if (prof && threadIdx.x == 0 && blockIdx.x == 0)
+    for (int k = 0; k < 7; k++) atomicAdd(prof + k, pc[k]);
 }
 
 // one CTA per proof walks levels [lo, hi)
@@ -942,10 +967,15 @@ static int run_segments(gpw_circuit* c, gpw_ctx* ctx, Fr* wires, size_t stride, 
     if (s.kind == SEG_NARROW) {
       if (!s.first_words) continue;
       if (getenv("GPW_SOLVER_UNSTAGED")) {  // debugging aid: the simple per-level walker over the CSR arrays
-        k_tape_narrow<<<n_proofs, NARROW_THREADS, 0, st>>>(c->dc, wires, stride, err, hist, s.lo, s.hi);
+        k_tape_narrow<<<n_proofs, spine_threads(), 0, st>>>(c->dc, wires, stride, err, hist, s.lo, s.hi);
       } else {
-        k_tape_staged<<<n_proofs, NARROW_THREADS, spine_smem_bytes(), st>>>(c->dc, c->stream_dev + s.stream_off, s.first_words, wires, stride, err,
-                                                           hist);
+        unsigned long long* prof = nullptr;
+        if (getenv("GPW_SPINE_PROFILE")) {
+          GPW_TRY(ctx->get_scratch("solve.prof", 7 * 8, (void**)&prof));
+          if (si == seg_lo) GPW_CUDA(cudaMemsetAsync(prof, 0, 7 * 8, st));
+        }
+        k_tape_staged<<<n_proofs, spine_threads(), spine_smem_bytes(), st>>>(c->dc, c->stream_dev + s.stream_off, s.first_words, wires, stride, err,
+                                                                           hist, prof);
       }
       GPW_CHECK_LAUNCH();
       ctx->launches++;
@@ -975,6 +1005,18 @@ static size_t commit_segment(const gpw_circuit* c) {
   for (size_t i = 0; i < c->plan.size(); i++)
     if (c->plan[i].kind == SEG_COMMIT) return i;
   return c->plan.size();
+}
+
+static void print_spine_profile(gpw_ctx* ctx) {
+  if (!getenv("GPW_SPINE_PROFILE")) return;
+  unsigned long long* prof = nullptr;
+  if (ctx->get_scratch("solve.prof", 7 * 8, (void**)&prof) != GPW_OK) return;
+  unsigned long long h[7];
+  cudaStreamSynchronize(ctx->stream);
+  cudaMemcpy(h, prof, sizeof(h), cudaMemcpyDeviceToHost);
+  const double us = 1.0 / 1965.0;  // cycles -> microseconds at the B200's 1965 MHz
+  fprintf(stderr, "[gpw spine] wait %.1f ms | macro: fetch %.1f, permutation %.1f, convert+store %.1f ms (%llu macros) | other chunks %.1f ms (%llu chunks)\n",
+          h[0] * us / 1e3, h[1] * us / 1e3, h[2] * us / 1e3, h[3] * us / 1e3, h[5], h[4] * us / 1e3, h[6] - h[5]);
 }
 
 static int check_err(gpw_ctx* ctx, int* err_dev, int n_proofs) {
@@ -1020,7 +1062,9 @@ extern "C" int gpw_witness_solve_phase1_on(gpw_circuit* c, gpw_ctx* lane, uint64
   GPW_CHECK_LAUNCH();
   ctx->launches++;
   GPW_TRY(run_segments(c, ctx, (Fr*)wires_dev, wire_stride, n_proofs, err, hist, 0, commit_segment(c)));
-  return check_err(ctx, err, n_proofs);
+  const int rc = check_err(ctx, err, n_proofs);
+  print_spine_profile(ctx);
+  return rc;
 }
 
 extern "C" int gpw_witness_solve_phase1_dev(gpw_circuit* c, uint64_t inputs_dev, int n_proofs, uint64_t wires_dev, size_t wire_stride) {

@@ -184,7 +184,9 @@ struct gpw_wrap_key {
   // fixed-base tables (2^(22 w) P, 12 windows) for the two MSMs whose scalars are full-width field elements: Z (the
   // quotient coefficients h) and the K range behind the committed wires (the log-derivative quotients). 12 instead of
   // 16 bucket additions per scalar; 8.4 GB of HBM. GPW_FIXED_BASE=0 keeps the plain windowed MSMs.
-  G1Affine *Zt = nullptr, *K2t = nullptr;
+  G1Affine *Zt = nullptr, *K2t = nullptr, *At = nullptr;
+  uint32_t nA_tail = 0;  // the last nA_tail wires of A's support are the log-derivative quotients too (they are the L side
+                         // of their own division constraints): that suffix of the A MSM also runs fixed-base
   G1Affine alpha1, beta1, delta1;
   G2Affine beta2, delta2;
   uint32_t n_inputs = 0;
@@ -251,7 +253,7 @@ extern "C" void gpw_wrap_key_free(gpw_wrap_key* k) {
   if (!k) return;
   cudaSetDevice(k->ctx->device);
   for (WrapLane* l : k->lanes) lane_free(l);
-  void* ps[] = {k->suppA, k->suppB, k->A, k->B1, k->K, k->Z, k->CK, k->CKs, k->B2, k->Zt, k->K2t};
+  void* ps[] = {k->suppA, k->suppB, k->A, k->B1, k->K, k->Z, k->CK, k->CKs, k->B2, k->Zt, k->K2t, k->At};
   for (void* p : ps) cudaFree(p);
   delete k;
 }
@@ -331,6 +333,14 @@ extern "C" int gpw_wrap_key_synthetic(gpw_ctx* ctx, gpw_circuit* circ, uint64_t 
       }
       GPW_TRY(gpw_msm_g1_fixed_table(ctx, (uint64_t)k->Z, N - 1, FIXED_C, FIXED_W, (uint64_t)k->Zt));
       if (k->K2t) GPW_TRY(gpw_msm_g1_fixed_table(ctx, (uint64_t)(k->K + c_hi), k->m - c_hi, FIXED_C, FIXED_W, (uint64_t)k->K2t));
+      while (k->nA_tail < na && sa[na - 1 - k->nA_tail] >= c_hi) k->nA_tail++;  // supports are sorted by wire id
+      if (k->nA_tail) {
+        if ((rc = wk_alloc((void**)&k->At, (size_t)FIXED_W * k->nA_tail * sizeof(G1Affine)))) {
+          gpw_wrap_key_free(k);
+          return rc;
+        }
+        GPW_TRY(gpw_msm_g1_fixed_table(ctx, (uint64_t)(k->A + (na - k->nA_tail)), k->nA_tail, FIXED_C, FIXED_W, (uint64_t)k->At));
+      }
     }
   }
   k->alpha1 = gen_mul_host<Fp>(seed + 1);
@@ -479,8 +489,19 @@ static int wrap_stage2(gpw_wrap_key* k, WrapLane* L, const uint64_t* r_canon, co
   ctx->launches += 2;
   G1Affine mA, mB1, mK1, mK2, mZ;
   G2Affine mB2;
-  GPW_TRY(gpw_msm_g1_dev(ctx, (uint64_t)L->gathA, (uint64_t)k->A, k->nA, 1, 0, 0, 0, (uint64_t*)&mA));
-  report("A", k->nA);
+  {
+    const uint32_t head = k->nA - k->nA_tail;
+    GPW_TRY(gpw_msm_g1_dev(ctx, (uint64_t)L->gathA, (uint64_t)k->A, head, 1, 0, 0, 0, (uint64_t*)&mA));
+    report("A", head);
+    if (k->nA_tail) {
+      G1Affine mA2;
+      GPW_TRY(gpw_msm_g1_fixed_dev(ctx, (uint64_t)(L->gathA + head), (uint64_t)k->At, k->nA_tail, 1, FIXED_C, FIXED_W, (uint64_t*)&mA2));
+      report("A2", k->nA_tail);
+      G1XYZZ t = G1XYZZ::from_affine(mA);
+      add_mixed(t, mA2, false);
+      mA = to_affine(t);
+    }
+  }
   GPW_TRY(gpw_msm_g1_dev(ctx, (uint64_t)L->gathB, (uint64_t)k->B1, k->nB, 1, 0, 0, 0, (uint64_t*)&mB1));
   report("B1", k->nB);
   GPW_TRY(gpw_msm_g2_dev(ctx, (uint64_t)L->gathB, (uint64_t)k->B2, k->nB, 1, 0, 0, 0, (uint64_t*)&mB2));
