@@ -52,14 +52,86 @@ struct NttPass {
   const Fr* scale_in;   // optional elementwise table applied on load  (index: position or bitrev(position))
   const Fr* scale_out;  // optional elementwise table applied on store
   int scale_in_bitrev, scale_out_bitrev;
+  int has_scale_const;  // multiply every output by scale_const on store (the 1/N of a plain inverse transform)
+  Fr scale_const;
 };
 
-__global__ void __launch_bounds__(512) k_ntt_pass(Fr* __restrict__ data, const Fr* __restrict__ tw, NttPass P) {
+// shared-memory tile: the two 16-byte halves of an element live in two separate arrays, so that the 8 lanes of a
+// quarter warp reading 8 consecutive elements with LDS.128 touch 8 x 16 contiguous bytes (no bank conflict); with the
+// halves interleaved (one 32-byte struct per element) every such access is a 2-way conflict
+struct NttTile {
+  uint4* lo;
+  uint4* hi;
+  __device__ __forceinline__ Fr ld(uint32_t e) const {
+    Fr r;
+    uint4* d = reinterpret_cast<uint4*>(&r);
+    d[0] = lo[e];
+    d[1] = hi[e];
+    return r;
+  }
+  __device__ __forceinline__ void st(uint32_t e, const Fr& v) const {
+    const uint4* s = reinterpret_cast<const uint4*>(&v);
+    lo[e] = s[0];
+    hi[e] = s[1];
+  }
+};
+
+// One stage for NB butterflies of a thread: all operands (and twiddles) are loaded first, then the NB independent
+// Montgomery multiplications run back to back (they interleave in the IMAD pipe), then everything is stored - loads and
+// stores through the same shared-memory pointers would otherwise keep the compiler from overlapping the butterflies.
+template <int NB>
+__device__ __forceinline__ void ntt_butterflies(const NttTile& sm, const Fr* __restrict__ tw, const NttPass& P, uint32_t bf0,
+                                                uint32_t bf_stride, int lb, uint32_t lo_base, uint32_t halfN) {
+  const uint32_t cols = (uint32_t)P.cols;
+  const uint32_t mask = (1u << lb) - 1u;
+  const int shift = P.L - 1 - (lb + P.lobits);
+  uint32_t i0[NB], i1[NB];
+  bool triv[NB];
+  Fr u[NB], v[NB], w[NB];
+#pragma unroll
+  for (int i = 0; i < NB; i++) {
+    const uint32_t bf = bf0 + (uint32_t)i * bf_stride;
+    const uint32_t c = bf % cols, pi = bf / cols;
+    const uint32_t t0 = ((pi & ~mask) << 1) | (pi & mask);
+    const uint32_t lo = P.col_in_lo ? (lo_base + c) : 0u;
+    const uint32_t e = ((((t0 & mask) << P.lobits) | lo)) << shift;  // < N/2
+    i0[i] = t0 * cols + c;
+    i1[i] = (t0 | (1u << lb)) * cols + c;
+    triv[i] = e == 0;
+    // inverse transforms use w^-e = -w^(N/2-e): the sign is folded into the butterfly below
+    w[i] = ld_fr(tw + (triv[i] ? 0u : (P.inverse ? halfN - e : e)));
+    u[i] = sm.ld(i0[i]);
+    v[i] = sm.ld(i1[i]);
+  }
+#pragma unroll
+  for (int i = 0; i < NB; i++) {
+    Fr r0, r1;
+    if (!P.dit) {
+      r0 = add(u[i], v[i]);
+      const Fr d = P.inverse && !triv[i] ? sub(v[i], u[i]) : sub(u[i], v[i]);
+      r1 = triv[i] ? d : mul(d, w[i]);
+    } else {
+      const Fr vw = triv[i] ? v[i] : mul(v[i], w[i]);
+      const bool flip = P.inverse && !triv[i];
+      r0 = flip ? sub(u[i], vw) : add(u[i], vw);
+      r1 = flip ? add(u[i], vw) : sub(u[i], vw);
+    }
+    u[i] = r0;
+    v[i] = r1;
+  }
+#pragma unroll
+  for (int i = 0; i < NB; i++) {
+    sm.st(i0[i], u[i]);
+    sm.st(i1[i], v[i]);
+  }
+}
+
+__global__ void __launch_bounds__(256) k_ntt_pass(Fr* __restrict__ data, const Fr* __restrict__ tw, NttPass P) {
   extern __shared__ uint4 smem_raw[];
-  Fr* sm = reinterpret_cast<Fr*>(smem_raw);
   const int k = P.k, cols = P.cols;
   const uint32_t tile = 1u << k;
   const uint32_t nelem = tile * cols;
+  const NttTile sm{smem_raw, smem_raw + nelem};
   const uint32_t tid = threadIdx.x;
   // CTA -> (hi, lo_base) or (tile_base)
   uint64_t cta = blockIdx.x;
@@ -85,60 +157,28 @@ __global__ void __launch_bounds__(512) k_ntt_pass(Fr* __restrict__ data, const F
       uint32_t si = P.scale_in_bitrev ? bitrev(gi, P.L) : gi;
       v = mul(v, ld_fr(P.scale_in + si));
     }
-    st_fr(sm + e, v);
+    sm.st(e, v);
   }
   __syncthreads();
   const uint32_t halfN = 1u << (P.L - 1);
+  const uint32_t nbf = nelem / 2;
   for (int q = 0; q < k; q++) {
     const int lb = P.dit ? q : (k - 1 - q);  // local pair bit
-    const uint32_t mask = (1u << lb) - 1u;
-    const int shift = P.L - 1 - (lb + P.lobits);
-    for (uint32_t bf = tid; bf < nelem / 2; bf += blockDim.x) {
-      uint32_t c = bf % cols, pi = bf / cols;
-      uint32_t t0 = ((pi & ~mask) << 1) | (pi & mask);
-      uint32_t t1 = t0 | (1u << lb);
-      uint32_t lo = P.col_in_lo ? (lo_base + c) : 0u;
-      uint32_t j = ((t0 & mask) << P.lobits) | lo;
-      uint32_t e = j << shift;  // < N/2
-      Fr u = ld_fr(sm + t0 * cols + c);
-      Fr v = ld_fr(sm + t1 * cols + c);
-      Fr r0, r1;
-      if (!P.dit) {
-        r0 = add(u, v);
-        if (e == 0) {
-          r1 = sub(u, v);
-        } else if (!P.inverse) {
-          r1 = mul(sub(u, v), ld_fr(tw + e));
-        } else {
-          r1 = mul(sub(v, u), ld_fr(tw + (halfN - e)));  // w^-e = -w^(N/2-e)
-        }
-      } else {
-        if (e == 0) {
-          r0 = add(u, v);
-          r1 = sub(u, v);
-        } else if (!P.inverse) {
-          Fr vw = mul(v, ld_fr(tw + e));
-          r0 = add(u, vw);
-          r1 = sub(u, vw);
-        } else {
-          Fr vw = mul(v, ld_fr(tw + (halfN - e)));
-          r0 = sub(u, vw);
-          r1 = add(u, vw);
-        }
-      }
-      st_fr(sm + t0 * cols + c, r0);
-      st_fr(sm + t1 * cols + c, r1);
-    }
+    // one butterfly at a time per thread: thread-level parallelism (7 CTAs of 128 threads per SM at 64 registers) beats
+    // unrolling 4 butterflies per thread (148 registers, 3 CTAs per SM: measured 2.3 ms instead of 1.9 ms for 2^23)
+#pragma unroll 1
+    for (uint32_t bf = tid; bf < nbf; bf += blockDim.x) ntt_butterflies<1>(sm, tw, P, bf, 0, lb, lo_base, halfN);
     __syncthreads();
   }
   for (uint32_t e = tid; e < nelem; e += blockDim.x) {
     uint32_t c = e % cols, t = e / cols;
     uint32_t gi = gindex(t, c);
-    Fr v = ld_fr(sm + e);
+    Fr v = sm.ld(e);
     if (P.scale_out) {
       uint32_t si = P.scale_out_bitrev ? bitrev(gi, P.L) : gi;
       v = mul(v, ld_fr(P.scale_out + si));
     }
+    if (P.has_scale_const) v = mul(v, P.scale_const);
     st_fr(data + gi, v);
   }
 }
@@ -152,12 +192,6 @@ __global__ void k_bitrev_permute(Fr* __restrict__ data, int L) {
     st_fr(data + i, b);
     st_fr(data + j, a);
   }
-}
-
-__global__ void k_scale_const(Fr* __restrict__ data, uint32_t n, Fr cst) {
-  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  st_fr(data + i, mul(ld_fr(data + i), cst));
 }
 
 // table[i] = base^i * c0 for i < n: each thread seeds base^(i0) by square-and-multiply, then walks
@@ -252,7 +286,9 @@ static int launch_pass(gpw_ctx* ctx, Fr* data, const NttTables* tb, NttPass P) {
   const uint32_t nelem = (1u << P.k) * cols;
   const uint32_t ctas = N / nelem;
   int threads = (int)(nelem / 2);
-  if (threads > 512) threads = 512;
+  static const int max_threads = getenv("GPW_NTT_THREADS") ? atoi(getenv("GPW_NTT_THREADS")) : 128;
+  if (threads > max_threads) threads = max_threads;
+  if (threads > 256) threads = 256;  // launch bounds of k_ntt_pass
   if (threads < 32) threads = 32;
   k_ntt_pass<<<ctas, threads, nelem * sizeof(Fr), ctx->stream>>>(data, (const Fr*)tb->tw, P);
   GPW_CHECK_LAUNCH();
@@ -314,13 +350,12 @@ static int ntt_dev_impl(gpw_ctx* ctx, Fr* data, int L, int inverse, int coset, i
       P.scale_out = post;
       P.scale_out_bitrev = dit ? 0 : 1;  // DIF leaves output bit-reversed: position p holds coefficient bitrev(p)
     }
+    if (pi + 1 == ks.size() && inverse && !coset) {  // 1/N fused into the last pass's store
+      P.has_scale_const = 1;
+      P.scale_const = inv(fr_from_u64(N));
+    }
     GPW_TRY(launch_pass(ctx, data, tb, P));
     bits_done += P.k;
-  }
-  if (inverse && !coset) {
-    k_scale_const<<<div_up(N, 256), 256, 0, st>>>(data, N, inv(fr_from_u64(N)));
-    GPW_CHECK_LAUNCH();
-    ctx->launches += 1;
   }
   const bool is_bitrev_now = !dit;
   if (is_bitrev_now != (out_bitrev != 0)) {
