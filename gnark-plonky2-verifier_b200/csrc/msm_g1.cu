@@ -32,6 +32,18 @@ extern "C" int gpw_msm_g1_fixed_dev(gpw_ctx* ctx, uint64_t scalars_dev, uint64_t
                           "msm1f", n_windows);
 }
 
+// Internal (wrap.cu): G1 MSM that shares its digit decomposition + bucket sort with other MSMs over the same scalars.
+// fixed_windows != 0: points_dev is a fixed-base table. reuse != 0: the sort named sort_tag is already in place.
+extern "C" int gpw_msm_g1_shared_dev(gpw_ctx* ctx, uint64_t scalars_dev, uint64_t points_dev, size_t n, int scalars_mont, int window_bits,
+                                     int fixed_windows, const char* sort_tag, int reuse, uint64_t* out_affine) {
+  if (!ctx || !out_affine || !sort_tag) {
+    set_error("msm: null argument");
+    return GPW_EINVAL;
+  }
+  return msm_dev_impl<Fp>(ctx, (const Fr*)scalars_dev, (const Affine<Fp>*)points_dev, n, scalars_mont, window_bits, 0, 0, out_affine,
+                          fixed_windows ? "msm1f" : "msm1", fixed_windows, sort_tag, reuse != 0);
+}
+
 extern "C" int gpw_msm_last_stats(gpw_ctx* ctx, float* accumulate_ms, float* total_ms, uint64_t* nonzero_digits) {
   if (!ctx) return GPW_EINVAL;
   if (accumulate_ms) *accumulate_ms = ctx->msm_acc_ms;

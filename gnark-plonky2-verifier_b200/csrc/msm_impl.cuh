@@ -516,9 +516,13 @@ static int choose_window(size_t n) {
 // (gpw_msm_g1_fixed_table); W must equal the number of c-bit windows of a scalar. Every digit of every scalar then
 // lands in ONE set of 2^(c-1) buckets, so the bucket reduction is paid once instead of once per window and wide
 // windows become affordable: c = 22 needs 12 additions per full-width scalar instead of the 16 of c = 16.
+// sort_tag / reuse_sort: MSMs over the SAME scalars (G1 and G2 sides of B, the commitment and its proof of knowledge,
+// the A and K bases of the log-derivative quotients) share one digit decomposition + bucket sort: the first call sorts
+// into the scratch named by sort_tag, the following ones pass reuse_sort = true (same n, c, window range, mode).
 template <class F>
 static int msm_dev_impl(gpw_ctx* ctx, const Fr* scalars, const Affine<F>* points, size_t n, int mont, int c,
-                        int win_lo, int win_hi, uint64_t* out_affine, const char* tag, int fixed_windows = 0) {
+                        int win_lo, int win_hi, uint64_t* out_affine, const char* tag, int fixed_windows = 0,
+                        const char* sort_tag = nullptr, bool reuse_sort = false) {
   constexpr int OUT_WORDS = (int)(sizeof(Affine<F>) / 8);
   if (n >= (1ull << 31)) {
     set_error("msm: n=%zu too large (max 2^31-1)", n);
@@ -563,15 +567,15 @@ static int msm_dev_impl(gpw_ctx* ctx, const Fr* scalars, const Affine<F>* points
 
   uint32_t *counts, *offsets, *cursor, *sorted, *tail_key, *tail_list, *ntail, *nbig, *big_list, *block_sums;
   XYZZ<F>*buckets, *head, *tail, *partials, *wsums;
-  std::string T(tag);
-  GPW_TRY(ctx->get_scratch((T + ".counts").c_str(), (size_t)(B + 1) * 4 * 3 + 64, (void**)&counts));
+  std::string T(tag), ST(sort_tag ? sort_tag : tag);
+  GPW_TRY(ctx->get_scratch((ST + ".counts").c_str(), (size_t)(B + 1) * 4 * 3 + 64, (void**)&counts));
   offsets = counts + (B + 1);
   cursor = offsets + (B + 1);
   ntail = cursor + (B + 1);
   nbig = ntail + 1;
   const uint32_t nscan_blocks = (B + SCAN_BLOCK - 1) / SCAN_BLOCK;
-  GPW_TRY(ctx->get_scratch((T + ".scanblk").c_str(), (size_t)nscan_blocks * 4 + 16, (void**)&block_sums));
-  GPW_TRY(ctx->get_scratch((T + ".sorted").c_str(), (size_t)max_entries * 4 + 16, (void**)&sorted));
+  GPW_TRY(ctx->get_scratch((ST + ".scanblk").c_str(), (size_t)nscan_blocks * 4 + 16, (void**)&block_sums));
+  GPW_TRY(ctx->get_scratch((ST + ".sorted").c_str(), (size_t)max_entries * 4 + 16, (void**)&sorted));
   GPW_TRY(ctx->get_scratch((T + ".keys").c_str(), (size_t)ntasks * 4 * 3, (void**)&tail_key));
   tail_list = tail_key + ntasks;
   big_list = tail_list + ntasks;
@@ -595,19 +599,24 @@ static int msm_dev_impl(gpw_ctx* ctx, const Fr* scalars, const Affine<F>* points
   GPW_TRY(ctx->get_scratch((T + ".wsums").c_str(), (size_t)nw * (2 + ngroups + ngroups2) * sizeof(XYZZ<F>), (void**)&wsums));
 
   GPW_CUDA(cudaEventRecord(ctx->ev[0], st));
-  GPW_CUDA(cudaMemsetAsync(counts, 0, (size_t)(B + 1) * 4 * 3 + 64, st));
   GPW_CUDA(cudaMemsetAsync(buckets, 0, (size_t)B * sizeof(XYZZ<F>), st));
-  const int TPB = 256;
-  k_msm_digits<false><<<div_up(n, TPB), TPB, 0, st>>>(scalars, n, mont, c, nwin, win_lo, win_hi, fixed_windows, counts, nullptr);
-  GPW_CHECK_LAUNCH();
-  k_msm_scan_sums<<<nscan_blocks, SCAN_THREADS, 0, st>>>(counts, B, block_sums);
-  GPW_CHECK_LAUNCH();
-  k_msm_scan_blocks<<<1, SCAN_THREADS, 0, st>>>(block_sums, nscan_blocks, offsets + B);
-  GPW_CHECK_LAUNCH();
-  k_msm_scan_final<<<nscan_blocks, SCAN_THREADS, 0, st>>>(counts, B, block_sums, offsets, cursor);
-  GPW_CHECK_LAUNCH();
-  k_msm_digits<true><<<div_up(n, TPB), TPB, 0, st>>>(scalars, n, mont, c, nwin, win_lo, win_hi, fixed_windows, cursor, sorted);
-  GPW_CHECK_LAUNCH();
+  if (reuse_sort) {
+    GPW_CUDA(cudaMemsetAsync(ntail, 0, 8, st));  // ntail, nbig: the only per-run state in the sort's scratch
+  } else {
+    GPW_CUDA(cudaMemsetAsync(counts, 0, (size_t)(B + 1) * 4 * 3 + 64, st));
+    const int TPB = 256;
+    k_msm_digits<false><<<div_up(n, TPB), TPB, 0, st>>>(scalars, n, mont, c, nwin, win_lo, win_hi, fixed_windows, counts, nullptr);
+    GPW_CHECK_LAUNCH();
+    k_msm_scan_sums<<<nscan_blocks, SCAN_THREADS, 0, st>>>(counts, B, block_sums);
+    GPW_CHECK_LAUNCH();
+    k_msm_scan_blocks<<<1, SCAN_THREADS, 0, st>>>(block_sums, nscan_blocks, offsets + B);
+    GPW_CHECK_LAUNCH();
+    k_msm_scan_final<<<nscan_blocks, SCAN_THREADS, 0, st>>>(counts, B, block_sums, offsets, cursor);
+    GPW_CHECK_LAUNCH();
+    k_msm_digits<true><<<div_up(n, TPB), TPB, 0, st>>>(scalars, n, mont, c, nwin, win_lo, win_hi, fixed_windows, cursor, sorted);
+    GPW_CHECK_LAUNCH();
+    ctx->launches += 5;
+  }
   GPW_CUDA(cudaEventRecord(ctx->ev[1], st));
   k_msm_accumulate<F><<<div_up(ntasks, MSM_ACC_THREADS), MSM_ACC_THREADS, MSM_ACC_THREADS * sizeof(XYZZ<F>), st>>>(
       points, sorted, offsets, B, buckets, head, tail, tail_key, tail_list, ntail);
@@ -644,7 +653,7 @@ static int msm_dev_impl(gpw_ctx* ctx, const Fr* scalars, const Affine<F>* points
   };
   GPW_TRY(sum_partials(partials, nchunks, ngroups, wsums + 2 * nw, wsums));
   GPW_TRY(sum_partials(partials2, nchunks2, ngroups2, wsums + (size_t)nw * (2 + ngroups), wsums + nw));
-  ctx->launches += 10;
+  ctx->launches += 5;
   const XYZZ<F>* hw = (const XYZZ<F>*)ctx->pin_take((size_t)2 * nw * sizeof(XYZZ<F>));
   const uint32_t* Mp = (const uint32_t*)ctx->pin_take(4);
   GPW_CUDA(cudaMemcpyAsync((void*)hw, wsums, (size_t)2 * nw * sizeof(XYZZ<F>), cudaMemcpyDeviceToHost, st));

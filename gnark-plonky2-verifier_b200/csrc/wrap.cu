@@ -150,6 +150,9 @@ int gpw_msm_g2_dev(gpw_ctx* ctx, uint64_t s, uint64_t p, size_t n, int mont, int
 int gpw_groth16_compute_h_dev(gpw_ctx* ctx, uint64_t a_dev, uint64_t b_dev, uint64_t c_dev, int logN);
 int gpw_msm_g1_fixed_table(gpw_ctx* ctx, uint64_t points_dev, size_t n, int window_bits, int n_windows, uint64_t table_dev);
 int gpw_msm_g1_fixed_dev(gpw_ctx* ctx, uint64_t s, uint64_t table, size_t n, int mont, int c, int n_windows, uint64_t* out);
+int gpw_msm_g1_shared_dev(gpw_ctx* ctx, uint64_t s, uint64_t p, size_t n, int mont, int c, int fixed_windows, const char* sort_tag, int reuse,
+                          uint64_t* out);
+int gpw_msm_g2_shared_dev(gpw_ctx* ctx, uint64_t s, uint64_t p, size_t n, int mont, int c, const char* sort_tag, int reuse, uint64_t* out);
 }
 
 // Proving key for a compiled circuit. Bases are synthetic (known discrete logs, documented below) - the analogue of
@@ -169,7 +172,11 @@ struct WrapLane {
   float t_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 };
 constexpr int WRAP_DEFAULT_LANES = 6, WRAP_MAX_LANES = 16;
+// window widths of the fixed-base tables: 22 bits (12 additions per scalar, 2^21 buckets) for the 8.4 M-point Z MSM; 20 bits
+// (13 additions, 2^19 buckets) for the 2.5 M-point quotient ranges of A and K, where the reduction of 2^21 buckets would
+// cost more than the thirteenth addition
 constexpr int FIXED_C = 22, FIXED_W = (254 + FIXED_C) / FIXED_C;
+constexpr int FIXED_CQ = 20, FIXED_WQ = (254 + FIXED_CQ) / FIXED_CQ;
 
 struct gpw_wrap_key {
   gpw_ctx* ctx = nullptr;
@@ -185,6 +192,12 @@ struct gpw_wrap_key {
   // quotient coefficients h) and the K range behind the committed wires (the log-derivative quotients). 12 instead of
   // 16 bucket additions per scalar; 8.4 GB of HBM. GPW_FIXED_BASE=0 keeps the plain windowed MSMs.
   G1Affine *Zt = nullptr, *K2t = nullptr, *At = nullptr;
+  // Behind the committed wires sit the commitment-challenge wire and then the log-derivative quotients. The challenge
+  // is a public input of the verifier (gnark appends commitment wires to the public witness, their bases live in vk.K),
+  // so it is not part of the prover's K MSM: the second K range starts at k2_lo, right behind it. That range is exactly
+  // the scalars of A's fixed-base suffix, whose bucket sort the K MSM then reuses.
+  uint32_t k2_lo = 0;
+  bool share_q_sort = false;
   uint32_t nA_tail = 0;  // the last nA_tail wires of A's support are the log-derivative quotients too (they are the L side
                          // of their own division constraints): that suffix of the A MSM also runs fixed-base
   G1Affine alpha1, beta1, delta1;
@@ -325,21 +338,25 @@ extern "C" int gpw_wrap_key_synthetic(gpw_ctx* ctx, gpw_circuit* circ, uint64_t 
   {
     const char* e = getenv("GPW_FIXED_BASE");
     const uint32_t c_hi = k->n_committed ? k->limb_start + k->n_committed : k->m;
+    // the challenge wire (if any) is the first wire behind the committed range
+    k->k2_lo = (k->n_committed && k->commit_wire == c_hi && c_hi < k->m) ? c_hi + 1 : c_hi;
     if (!(e && atoi(e) == 0)) {
       if ((rc = wk_alloc((void**)&k->Zt, (size_t)FIXED_W * (N - 1) * sizeof(G1Affine))) ||
-          (c_hi < k->m && (rc = wk_alloc((void**)&k->K2t, (size_t)FIXED_W * (k->m - c_hi) * sizeof(G1Affine))))) {
+          (k->k2_lo < k->m && (rc = wk_alloc((void**)&k->K2t, (size_t)FIXED_WQ * (k->m - k->k2_lo) * sizeof(G1Affine))))) {
         gpw_wrap_key_free(k);
         return rc;
       }
       GPW_TRY(gpw_msm_g1_fixed_table(ctx, (uint64_t)k->Z, N - 1, FIXED_C, FIXED_W, (uint64_t)k->Zt));
-      if (k->K2t) GPW_TRY(gpw_msm_g1_fixed_table(ctx, (uint64_t)(k->K + c_hi), k->m - c_hi, FIXED_C, FIXED_W, (uint64_t)k->K2t));
+      if (k->K2t) GPW_TRY(gpw_msm_g1_fixed_table(ctx, (uint64_t)(k->K + k->k2_lo), k->m - k->k2_lo, FIXED_CQ, FIXED_WQ, (uint64_t)k->K2t));
       while (k->nA_tail < na && sa[na - 1 - k->nA_tail] >= c_hi) k->nA_tail++;  // supports are sorted by wire id
+      // A's suffix is exactly the wires [k2_lo, m) iff it has that many entries and starts there (sorted, distinct)
+      k->share_q_sort = k->K2t && k->nA_tail == k->m - k->k2_lo && k->nA_tail > 0 && sa[na - k->nA_tail] == k->k2_lo;
       if (k->nA_tail) {
-        if ((rc = wk_alloc((void**)&k->At, (size_t)FIXED_W * k->nA_tail * sizeof(G1Affine)))) {
+        if ((rc = wk_alloc((void**)&k->At, (size_t)FIXED_WQ * k->nA_tail * sizeof(G1Affine)))) {
           gpw_wrap_key_free(k);
           return rc;
         }
-        GPW_TRY(gpw_msm_g1_fixed_table(ctx, (uint64_t)(k->A + (na - k->nA_tail)), k->nA_tail, FIXED_C, FIXED_W, (uint64_t)k->At));
+        GPW_TRY(gpw_msm_g1_fixed_table(ctx, (uint64_t)(k->A + (na - k->nA_tail)), k->nA_tail, FIXED_CQ, FIXED_WQ, (uint64_t)k->At));
       }
     }
   }
@@ -362,6 +379,8 @@ extern "C" int gpw_wrap_key_info(const gpw_wrap_key* k, uint64_t* info8) {
 }
 
 extern "C" uint64_t gpw_wrap_key_wires_dev(const gpw_wrap_key* k) { return k ? (uint64_t)k->lanes[0]->wires : 0; }
+// after a gpw_wrap_prove: the quotient polynomial's coefficients h_0 .. h_{N-2} (Fr, Montgomery) of that proof - test aid
+extern "C" uint64_t gpw_wrap_key_h_dev(const gpw_wrap_key* k) { return k ? (uint64_t)k->lanes[0]->va : 0; }
 
 // Number of proofs gpw_wrap_prove_many keeps in flight (default 6; each lane holds ~1.5 GB of vectors plus its MSM scratch).
 extern "C" int gpw_wrap_set_lanes(gpw_wrap_key* k, int n) {
@@ -460,9 +479,10 @@ static int wrap_stage2(gpw_wrap_key* k, WrapLane* L, const uint64_t* r_canon, co
   uint64_t X[4] = {0, 0, 0, 0};
   if (k->n_committed) {
     uint64_t sc = (uint64_t)(wires + k->limb_start);
-    GPW_TRY(gpw_msm_g1_dev(ctx, sc, (uint64_t)k->CK, k->n_committed, 1, 0, 0, 0, (uint64_t*)&D));
+    // commitment and proof of knowledge: same scalars, one bucket sort
+    GPW_TRY(gpw_msm_g1_shared_dev(ctx, sc, (uint64_t)k->CK, k->n_committed, 1, 0, 0, "sortC", 0, (uint64_t*)&D));
     report("CK", k->n_committed);
-    GPW_TRY(gpw_msm_g1_dev(ctx, sc, (uint64_t)k->CKs, k->n_committed, 1, 0, 0, 0, (uint64_t*)&PoK));
+    GPW_TRY(gpw_msm_g1_shared_dev(ctx, sc, (uint64_t)k->CKs, k->n_committed, 1, 0, 0, "sortC", 1, (uint64_t*)&PoK));
     report("CKs", k->n_committed);
     uint8_t ser[64];
     ser_g1_be(D, ser);
@@ -495,16 +515,18 @@ static int wrap_stage2(gpw_wrap_key* k, WrapLane* L, const uint64_t* r_canon, co
     report("A", head);
     if (k->nA_tail) {
       G1Affine mA2;
-      GPW_TRY(gpw_msm_g1_fixed_dev(ctx, (uint64_t)(L->gathA + head), (uint64_t)k->At, k->nA_tail, 1, FIXED_C, FIXED_W, (uint64_t*)&mA2));
+      // the same wires as the K2 MSM below (when both tables exist and cover the same range): K2 reuses this sort
+      GPW_TRY(gpw_msm_g1_shared_dev(ctx, (uint64_t)(L->gathA + head), (uint64_t)k->At, k->nA_tail, 1, FIXED_CQ, FIXED_WQ, "sortQ", 0,
+                                    (uint64_t*)&mA2));
       report("A2", k->nA_tail);
       G1XYZZ t = G1XYZZ::from_affine(mA);
       add_mixed(t, mA2, false);
       mA = to_affine(t);
     }
   }
-  GPW_TRY(gpw_msm_g1_dev(ctx, (uint64_t)L->gathB, (uint64_t)k->B1, k->nB, 1, 0, 0, 0, (uint64_t*)&mB1));
+  GPW_TRY(gpw_msm_g1_shared_dev(ctx, (uint64_t)L->gathB, (uint64_t)k->B1, k->nB, 1, 0, 0, "sortB", 0, (uint64_t*)&mB1));
   report("B1", k->nB);
-  GPW_TRY(gpw_msm_g2_dev(ctx, (uint64_t)L->gathB, (uint64_t)k->B2, k->nB, 1, 0, 0, 0, (uint64_t*)&mB2));
+  GPW_TRY(gpw_msm_g2_shared_dev(ctx, (uint64_t)L->gathB, (uint64_t)k->B2, k->nB, 1, 0, "sortB", 1, (uint64_t*)&mB2));
   report("B2", k->nB);
   // K: private wires that are not committed = [1 + n_pub, limb_start) U [limb_start + n_committed, m), minus the challenge wire
   const uint32_t k_lo = 1 + k->n_pub;
@@ -512,10 +534,13 @@ static int wrap_stage2(gpw_wrap_key* k, WrapLane* L, const uint64_t* r_canon, co
   GPW_TRY(gpw_msm_g1_dev(ctx, (uint64_t)(wires + k_lo), (uint64_t)(k->K + k_lo), c_lo - k_lo, 1, 0, 0, 0, (uint64_t*)&mK1));
   report("K1", c_lo - k_lo);
   mK2 = G1Affine{Fp::zero(), Fp::zero()};
-  if (c_hi < k->m) {
-    if (k->K2t) GPW_TRY(gpw_msm_g1_fixed_dev(ctx, (uint64_t)(wires + c_hi), (uint64_t)k->K2t, k->m - c_hi, 1, FIXED_C, FIXED_W, (uint64_t*)&mK2));
-    else GPW_TRY(gpw_msm_g1_dev(ctx, (uint64_t)(wires + c_hi), (uint64_t)(k->K + c_hi), k->m - c_hi, 1, 0, 0, 0, (uint64_t*)&mK2));
-    report("K2", k->m - c_hi);
+  if (k->k2_lo < k->m) {
+    const uint32_t n2 = k->m - k->k2_lo;
+    if (k->K2t)
+      GPW_TRY(gpw_msm_g1_shared_dev(ctx, (uint64_t)(wires + k->k2_lo), (uint64_t)k->K2t, n2, 1, FIXED_CQ, FIXED_WQ, "sortQ",
+                                    k->share_q_sort ? 1 : 0, (uint64_t*)&mK2));
+    else GPW_TRY(gpw_msm_g1_dev(ctx, (uint64_t)(wires + k->k2_lo), (uint64_t)(k->K + k->k2_lo), n2, 1, 0, 0, 0, (uint64_t*)&mK2));
+    report("K2", n2);
   }
   if (k->Zt) GPW_TRY(gpw_msm_g1_fixed_dev(ctx, (uint64_t)L->va, (uint64_t)k->Zt, N - 1, 1, FIXED_C, FIXED_W, (uint64_t*)&mZ));
   else GPW_TRY(gpw_msm_g1_dev(ctx, (uint64_t)L->va, (uint64_t)k->Z, N - 1, 1, 0, 0, 0, (uint64_t*)&mZ));

@@ -28,6 +28,7 @@ _NEW = {
     "gpw_wrap_key_free": (None, [_vp]),
     "gpw_wrap_key_info": (C.c_int, [_vp, _vp]),
     "gpw_wrap_key_wires_dev": (C.c_uint64, [_vp]),
+    "gpw_wrap_key_h_dev": (C.c_uint64, [_vp]),
     "gpw_wrap_prove": (C.c_int, [_vp, _vp, _vp, _vp, C.c_int, _vp]),
     "gpw_wrap_prove_dev": (C.c_int, [_vp, C.c_uint64, _vp, _vp, C.c_int, _vp]),
     "gpw_msm_cumulative_stats": (C.c_int, [_vp, C.c_int, C.c_int, _vp]),
@@ -144,6 +145,11 @@ class WrapKey:
     @property
     def wires_ptr(self):
         return int(_lib.gpw_wrap_key_wires_dev(self._h))
+
+    @property
+    def h_ptr(self):
+        """device address of the quotient coefficients h (N - 1 Fr, Montgomery) of the last prove()"""
+        return int(_lib.gpw_wrap_key_h_dev(self._h))
 
     def prove(self, inputs, r_int, s_int, check=True):
         """inputs: (n_inputs, 4) u64 canonical, host. -> dict with Ar, Bs, Krs, commitment, pok (affine Montgomery limbs),

@@ -182,6 +182,8 @@ int gpw_wrap_key_synthetic(gpw_ctx* ctx, gpw_circuit* circ, uint64_t seed, gpw_w
 void gpw_wrap_key_free(gpw_wrap_key* k);
 int gpw_wrap_key_info(const gpw_wrap_key* k, uint64_t* info8);
 uint64_t gpw_wrap_key_wires_dev(const gpw_wrap_key* k);
+/* device address of the quotient coefficients h_0 .. h_{N-2} (Fr, Montgomery) left by the last gpw_wrap_prove (test aid) */
+uint64_t gpw_wrap_key_h_dev(const gpw_wrap_key* k);
 int gpw_wrap_prove(gpw_wrap_key* k, const uint64_t* inputs, const uint64_t* r_canonical, const uint64_t* s_canonical, int check,
                    uint64_t* out_proof);
 /* same, with the parsed inputs already resident on the device (n_inputs x 4 u64 canonical) */

@@ -174,6 +174,25 @@ def test_wrap_prove_step(ctx, step):
     ls, nc = info["limb_start"], info["n_committed"]
     sD = sum(wv[ls + i] * ((1 << 35) + ls + i) for i in range(nc)) % R
     assert gpw.points_to_ints(1, pr["commitment"])[0] == ob.point_key(1, ob.ec_mul(1, ob.G1_GEN, sD))
+    # Bs (G2) and Krs in the exponent too. Discrete logs of the synthetic key (csrc/wrap.cu): B1_j = 2^32 + j,
+    # B2_j = 1 + j over B's support, K_i = 2^33 + i, Z_j = 2^34 + j, alpha/beta/delta = seed + 1/2/3.
+    suppB = circ.supports(1)
+    sB2 = (99 + 2 + sum(wv[w_] * (1 + j) for j, w_ in enumerate(suppB)) + s_ * (99 + 3)) % R
+    assert gpw.points_to_ints(2, pr["Bs"])[0] == ob.point_key(2, ob.ec_mul(2, ob.G2_GEN, sB2))
+    sB1 = (99 + 2 + sum(wv[w_] * ((1 << 32) + j) for j, w_ in enumerate(suppB)) + s_ * (99 + 3)) % R
+    N = 1 << info["logN"]
+    hbuf = torch.empty((N - 1, 4), dtype=torch.int64, device="cuda")
+    ctypes.cdll.LoadLibrary("libcudart.so").cudaMemcpy(ctypes.c_void_p(hbuf.data_ptr()), ctypes.c_void_p(key.h_ptr),
+                                                       ctypes.c_size_t((N - 1) * 32), ctypes.c_int(3))
+    hv = gpw.limbs_to_ints(gpw.host_ff_from_mont(0, hbuf.cpu().numpy().view(np.uint64)))
+    sZ = sum(h * ((1 << 34) + j) for j, h in enumerate(hv)) % R
+    # K: private wires that are neither committed nor the commitment challenge (a public input of the verifier)
+    npub, m = info["n_pub"], info["m"]
+    k_wires = list(range(1 + npub, ls)) + list(range(ls + nc + 1, m))
+    assert circ.info["commit_wire"] == ls + nc
+    sK = sum(wv[i] * ((1 << 33) + i) for i in k_wires) % R
+    sKrs = (sK + sZ + s_ * sA + r_ * sB1 - r_ * s_ * (99 + 3)) % R
+    assert gpw.points_to_ints(1, pr["Krs"])[0] == ob.point_key(1, ob.ec_mul(1, ob.G1_GEN, sKrs))
     print("wrap stats (ms):", key.last_stats(), "key:", info)
     key.close()
 
