@@ -158,7 +158,7 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=16)
+    ap.add_argument("--steps", type=int, default=32)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--lanes", type=int, default=int(os.environ.get("GPW_WRAP_LANES", "6")),
                     help="proofs in flight per GPU (gpw_wrap_set_lanes)")

@@ -285,7 +285,8 @@ __global__ void __launch_bounds__(MSM_ACC_THREADS, sizeof(F) == sizeof(Fp) ? MSM
     const uint32_t e = e_next;
     const Affine<F> p = p_next;
     pos++;
-    if (pos < pos1) {  // prefetch the next point while this add runs
+    if (pos < pos1) {  // prefetch the next point while this add runs (dropping the prefetch for G2, whose addition
+                       // is register bound, was measured: no faster)
       e_next = sorted[pos];
       p_next = ld_struct(points + (e_next & 0x7fffffffu));
     }
@@ -622,6 +623,11 @@ static int msm_dev_impl(gpw_ctx* ctx, const Fr* scalars, const Affine<F>* points
       points, sorted, offsets, B, buckets, head, tail, tail_key, tail_list, ntail);
   GPW_CHECK_LAUNCH();
   GPW_CUDA(cudaEventRecord(ctx->ev[2], st));
+  // development aid (GPW_DEBUG_MSM=1): split of the tail into fix-up / window reduction / sums
+  static const bool dbg_phases = getenv("GPW_DEBUG_MSM") != nullptr;
+  cudaEvent_t dbg_ev[3] = {nullptr, nullptr, nullptr};
+  if (dbg_phases)
+    for (auto& e : dbg_ev) cudaEventCreate(&e);
   k_msm_fixup<F><<<ctx->sm_count * 8, 128, 0, st>>>(head, tail, offsets, tail_key, tail_list, ntail, big_list, nbig, buckets);
   GPW_CHECK_LAUNCH();
   {
@@ -630,12 +636,14 @@ static int msm_dev_impl(gpw_ctx* ctx, const Fr* scalars, const Affine<F>* points
                                                                                           nbig, buckets);
   }
   GPW_CHECK_LAUNCH();
+  if (dbg_phases) cudaEventRecord(dbg_ev[0], st);
   k_msm_window_partial<F><<<div_up((size_t)nw * nchunks, 128), 128, 0, st>>>(buckets, offsets, half, chunk, (uint32_t)nw, 1u, partials,
                                                                              chunk_sums);
   GPW_CHECK_LAUNCH();
   k_msm_window_partial<F><<<div_up((size_t)nw * nchunks2, 128), 128, 0, st>>>(chunk_sums, nullptr, nchunks, chunk2, (uint32_t)nw, 0u,
                                                                               partials2, nullptr);
   GPW_CHECK_LAUNCH();
+  if (dbg_phases) cudaEventRecord(dbg_ev[1], st);
   // per-window sums of an array of `cnt` partials per window -> dst[0 .. nw)  (two rounds above 2048 partials)
   auto sum_partials = [&](const XYZZ<F>* src, uint32_t cnt, uint32_t groups, XYZZ<F>* tmp, XYZZ<F>* dst) -> int {
     if (groups == 1) {
@@ -662,6 +670,16 @@ static int msm_dev_impl(gpw_ctx* ctx, const Fr* scalars, const Affine<F>* points
   GPW_CUDA(cudaStreamSynchronize(st));
   GPW_CUDA(cudaEventElapsedTime(&ctx->msm_acc_ms, ctx->ev[1], ctx->ev[2]));
   GPW_CUDA(cudaEventElapsedTime(&ctx->msm_total_ms, ctx->ev[0], ctx->ev[3]));
+  if (dbg_phases) {
+    float t_sort, t_fix, t_part, t_sum;
+    cudaEventElapsedTime(&t_sort, ctx->ev[0], ctx->ev[1]);
+    cudaEventElapsedTime(&t_fix, ctx->ev[2], dbg_ev[0]);
+    cudaEventElapsedTime(&t_part, dbg_ev[0], dbg_ev[1]);
+    cudaEventElapsedTime(&t_sum, dbg_ev[1], ctx->ev[3]);
+    fprintf(stderr, "[gpw msm] %-6s n=%8zu c=%2d: sort %.2f | accumulate %.2f | fix-up %.2f | window partial %.2f | sums + copy %.2f ms\n", tag, n, c,
+            t_sort, ctx->msm_acc_ms, t_fix, t_part, t_sum);
+    for (auto& e : dbg_ev) cudaEventDestroy(e);
+  }
   const uint32_t M = *Mp;
   ctx->msm_digits = M;
   {
