@@ -355,6 +355,56 @@ void ct_wire_values(void* h, uint64_t first, uint64_t count, uint64_t* out) {
   for (uint64_t i = 0; i < count; i++) canon(c->w[first + i], out + 4 * i);
 }
 
+// Poseidon-Goldilocks macro (csrc/poseidon_gl_macro.cuh), host build: (1) the specialised 192-bit ReduceHint against the
+// general one on n pseudo-random inputs incl. the edges -> number of mismatches; (2) the sequential trace: output state of
+// one permutation and the number of slots it emitted.
+uint64_t ct_glm_reduce192_mismatches(uint64_t seed, uint64_t n) {
+  uint64_t s = seed ? seed : 1, bad = 0;
+  auto next = [&]() { s ^= s << 13; s ^= s >> 7; s ^= s << 17; return s; };
+  for (uint64_t it = 0; it < n; it++) {
+    glm::U192 v{{next(), next(), next() % gl::P}};
+    switch (it % 8) {
+      case 0: v.l[2] = 0; break;
+      case 1: v.l[2] = 0; v.l[1] = 0; break;
+      case 2: v.l[2] = gl::P - 1; v.l[1] = ~0ull; v.l[0] = ~0ull; break;
+      case 3: v = glm::U192{{gl::P - 1, 0, 0}}; break;
+      case 4: v = glm::U192{{gl::P, 0, 0}}; break;
+      case 5: v = glm::U192{{0, 0, 0}}; break;
+      default: break;
+    }
+    const uint64_t x[4] = {v.l[0], v.l[1], v.l[2], 0};
+    uint64_t q[4], r, q0, q1, r2;
+    gl::reduce_hint(x, q, r);
+    glm::reduce192(v, q0, q1, r2);
+    if (r != r2 || q0 != q[0] || q1 != q[1] || q[2] || q[3]) bad++;
+  }
+  return bad;
+}
+
+uint32_t ct_glm_permute(const uint64_t* in12, uint64_t* out12) {
+  std::vector<uint64_t> gt(glm::T_TOTAL);
+  memcpy(gt.data() + glm::T_RC, GPW_GL_ALL_ROUND_CONSTANTS, sizeof(GPW_GL_ALL_ROUND_CONSTANTS));
+  memcpy(gt.data() + glm::T_CIRC, GPW_GL_MDS_CIRC, sizeof(GPW_GL_MDS_CIRC));
+  memcpy(gt.data() + glm::T_DIAG, GPW_GL_MDS_DIAG, sizeof(GPW_GL_MDS_DIAG));
+  memcpy(gt.data() + glm::T_FIRST, GPW_GL_FAST_PARTIAL_FIRST_ROUND_CONSTANT, sizeof(GPW_GL_FAST_PARTIAL_FIRST_ROUND_CONSTANT));
+  memcpy(gt.data() + glm::T_PRC, GPW_GL_FAST_PARTIAL_ROUND_CONSTANTS, sizeof(GPW_GL_FAST_PARTIAL_ROUND_CONSTANTS));
+  memcpy(gt.data() + glm::T_VS, GPW_GL_FAST_PARTIAL_ROUND_VS, sizeof(GPW_GL_FAST_PARTIAL_ROUND_VS));
+  memcpy(gt.data() + glm::T_WHATS, GPW_GL_FAST_PARTIAL_ROUND_W_HATS, sizeof(GPW_GL_FAST_PARTIAL_ROUND_W_HATS));
+  memcpy(gt.data() + glm::T_INIT, GPW_GL_FAST_PARTIAL_ROUND_INITIAL_MATRIX, sizeof(GPW_GL_FAST_PARTIAL_ROUND_INITIAL_MATRIX));
+  uint64_t st[12];
+  memcpy(st, in12, sizeof(st));
+  std::vector<uint8_t> seen(glm::N_OUT, 0);
+  uint32_t emitted = 0;
+  glm::trace_seq(st, gt.data(), [&](uint32_t slot, const glm::U192&) {
+    if (slot < glm::N_OUT && !seen[slot]) {
+      seen[slot] = 1;
+      emitted++;
+    }
+  });
+  memcpy(out12, st, sizeof(st));
+  return emitted;
+}
+
 void ct_wires_mont(void* h, uint64_t* out) {
   Circuit* c = (Circuit*)h;
   memcpy(out, c->w.data(), c->w.size() * sizeof(Fr));

@@ -89,6 +89,31 @@ def test_small_circuits_satisfied_and_reject_wrong_outputs(lib, kats):
     lib.ct_free(h)
 
 
+def test_poseidon_gl_macro_host(lib, kats):
+    # the native evaluation behind the OP_POSEIDON_GL macro instruction (csrc/poseidon_gl_macro.cuh), host build:
+    # the specialised ReduceHint equals the general one; a permutation fills each of its 1992 output slots exactly once
+    # and ends in the reference's state (poseidon/goldilocks_test.go:47-53 and the oracle on random states)
+    import random
+    from oracle.engine import Api
+    from oracle.poseidon import GoldilocksChip
+    lib.ct_glm_reduce192_mismatches.restype = C.c_uint64
+    lib.ct_glm_reduce192_mismatches.argtypes = [C.c_uint64, C.c_uint64]
+    lib.ct_glm_permute.restype = C.c_uint32
+    lib.ct_glm_permute.argtypes = [C.c_void_p, C.c_void_p]
+    assert lib.ct_glm_reduce192_mismatches(7, 2_000_000) == 0
+    rng = random.Random(3)
+    P = (1 << 64) - (1 << 32) + 1
+    for state in ([0] * 12, [P - 1] * 12, [rng.randrange(P) for _ in range(12)]):
+        a = np.array(state, dtype=np.uint64)
+        out = np.zeros(12, dtype=np.uint64)
+        assert lib.ct_glm_permute(a.ctypes.data, out.ctypes.data) == 1992
+        exp = GoldilocksChip(Api(trace=False)).Poseidon(list(state))
+        assert [int(x) for x in out] == [int(x) for x in exp]
+    out = np.zeros(12, dtype=np.uint64)
+    lib.ct_glm_permute(np.zeros(12, dtype=np.uint64).ctypes.data, out.ctypes.data)
+    assert [int(x) for x in out] == [int(x) for x in kats["poseidon_gl_perm_zero"]]
+
+
 def test_full_verifier_circuit_on_step(lib, testdata_dir):
     d = os.path.join(testdata_dir, "step")
     rd = lambda f: open(os.path.join(d, f), "rb").read()
