@@ -293,10 +293,10 @@ def main():
         "e2e": {"value": e2e_value, "unit": "proofs/s", "h2d_bytes_per_step": int(inputs.nbytes), "d2h_bytes_per_step": 512},
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     # dram__bytes_read.sum + dram__bytes_write.sum of one captured launch (profiles/r01_msm_accumulate_ncu.md):
-                     # 2 528 030 full-width points, 16 non-zero digits each -> 3.19 GB vs 243 MB algorithmic: windowed Pippenger
-                     # reads every base once per non-zero digit
-                     "traffic": 3185633760, "traffic_launch_points": 2528030,
+                     # dram__bytes_read.sum + dram__bytes_write.sum of one captured launch (profiles/r01_msm_accumulate_ncu.md,
+                     # capture A): the Z MSM, 8 388 607 full-width points, 12 non-zero digits each against the fixed-base table
+                     # -> 13.9 GB vs 805 MB algorithmic: every digit gathers its own 64-byte precomputed base
+                     "traffic": 13927985312, "traffic_launch_points": 8388607,
                      "peak_source": peak_kind, "kernel": "k_msm_accumulate<Fp> (MSM G1 bucket accumulation)",
                      "launches_per_step": g1["calls"] / n_lat, "avg_launch_ms": avg_ms,
                      "avg_points_per_launch": g1["points"] / max(g1["calls"], 1),
@@ -305,8 +305,14 @@ def main():
                      "timed_in": "the single-proof latency run (one lane, kernel alone on the device), CUDA events on the launching stream",
                      "msm_g1_whole_GBps": 96.0 * g1["points"] / (g1["total_ms"] * 1e-3) / 1e9 if g1["total_ms"] else None,
                      "msm_g2_whole_GBps": 160.0 * g2["points"] / (g2["total_ms"] * 1e-3) / 1e9 if g2["total_ms"] else None,
-                     "note": "BN254 MSM is integer-pipe (IMAD) bound, ~3000 IMADs per 96 B point-digit; the HBM fraction is low "
-                             "by construction (BASELINE.md 4)"},
+                     # the bound that actually holds: additions/s against the IMAD.WIDE issue ceiling (1 350 IMAD.WIDE per mixed
+                     # addition, one warp instruction per 4 cycles per SM sub-partition: 148 x 32 x 1.965 GHz / 1 350)
+                     "integer_pipe": {"achieved_Gadds_per_s": g1["digits"] / (g1["accumulate_ms"] * 1e-3) / 1e9 if g1["accumulate_ms"] else None,
+                                      "peak_Gadds_per_s": 148 * 32 * 1.965 / 1350.0,
+                                      "frac": (g1["digits"] / (g1["accumulate_ms"] * 1e-3) / 1e9) / (148 * 32 * 1.965 / 1350.0)
+                                      if g1["accumulate_ms"] else None},
+                     "note": "BN254 MSM is integer-pipe (IMAD) bound, ~1350 IMAD.WIDE per 96-byte point-digit; the HBM fraction is "
+                             "low by construction (BASELINE.md 4)"},
         "clocks": sampler.summary(),
         "pipelining": "gpw_wrap_prove_many: %d proofs in flight per GPU (host thread + stream + scratch each)" % args.lanes,
         "single_proof_latency_ms": latency_ms,
