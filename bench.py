@@ -305,13 +305,14 @@ def main():
                      "timed_in": "the single-proof latency run (one lane, kernel alone on the device), CUDA events on the launching stream",
                      "msm_g1_whole_GBps": 96.0 * g1["points"] / (g1["total_ms"] * 1e-3) / 1e9 if g1["total_ms"] else None,
                      "msm_g2_whole_GBps": 160.0 * g2["points"] / (g2["total_ms"] * 1e-3) / 1e9 if g2["total_ms"] else None,
-                     # the bound that actually holds: additions/s against the IMAD.WIDE issue ceiling (1 350 IMAD.WIDE per mixed
-                     # addition, one warp instruction per 4 cycles per SM sub-partition: 148 x 32 x 1.965 GHz / 1 350)
+                     # the bound that actually holds: additions/s against the IMAD.WIDE issue ceiling. One mixed addition = 8
+                     # Montgomery multiplications of 136 IMAD + the dual-product Y3 of 200 = 1 288; IMAD.WIDE issues one warp
+                     # instruction per 4 cycles per SM sub-partition: 148 SMs x 32 lanes/clk x 1.965 GHz / 1 288
                      "integer_pipe": {"achieved_Gadds_per_s": g1["digits"] / (g1["accumulate_ms"] * 1e-3) / 1e9 if g1["accumulate_ms"] else None,
-                                      "peak_Gadds_per_s": 148 * 32 * 1.965 / 1350.0,
-                                      "frac": (g1["digits"] / (g1["accumulate_ms"] * 1e-3) / 1e9) / (148 * 32 * 1.965 / 1350.0)
+                                      "peak_Gadds_per_s": 148 * 32 * 1.965 / 1288.0,
+                                      "frac": (g1["digits"] / (g1["accumulate_ms"] * 1e-3) / 1e9) / (148 * 32 * 1.965 / 1288.0)
                                       if g1["accumulate_ms"] else None},
-                     "note": "BN254 MSM is integer-pipe (IMAD) bound, ~1350 IMAD.WIDE per 96-byte point-digit; the HBM fraction is "
+                     "note": "BN254 MSM is integer-pipe (IMAD) bound, ~1290 IMAD.WIDE per 96-byte point-digit; the HBM fraction is "
                              "low by construction (BASELINE.md 4)"},
         "clocks": sampler.summary(),
         "pipelining": "gpw_wrap_prove_many: %d proofs in flight per GPU (host thread + stream + scratch each)" % args.lanes,

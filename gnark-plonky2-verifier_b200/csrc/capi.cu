@@ -145,6 +145,29 @@ extern "C" int gpw_host_ff_mul(int field, int impl, const uint64_t* a, const uin
   return GPW_OK;
 }
 
+// out = a b - c d through mont_mul2 (host emulation of the schedule the GPU runs): one reduction for both products
+template <class P>
+static void host_mul_sub2(const uint64_t* a, const uint64_t* b, const uint64_t* c, const uint64_t* d, uint64_t* out, size_t n) {
+  for (size_t i = 0; i < n; i++) {
+    Fe<P> x, y, z, w;
+    memcpy(&x, a + 4 * i, 32);
+    memcpy(&y, b + 4 * i, 32);
+    memcpy(&z, c + 4 * i, 32);
+    memcpy(&w, d + 4 * i, 32);
+    Fe<P> r = mul_sub2(x, y, z, w);
+    memcpy(out + 4 * i, &r, 32);
+  }
+}
+
+extern "C" int gpw_host_ff_mul_sub2(int field, const uint64_t* a, const uint64_t* b, const uint64_t* c, const uint64_t* d, uint64_t* out,
+                                    size_t n) {
+  if ((!a || !b || !c || !d || !out) && n) return GPW_EINVAL;
+  if (field == 0) host_mul_sub2<FrParams>(a, b, c, d, out, n);
+  else if (field == 1) host_mul_sub2<FpParams>(a, b, c, d, out, n);
+  else return GPW_EINVAL;
+  return GPW_OK;
+}
+
 template <class P, class Fn>
 static void host_map(const uint64_t* a, uint64_t* o, size_t n, Fn f) {
   for (size_t i = 0; i < n; i++) {

@@ -48,7 +48,7 @@ GPW_HD_CALL XYZZ<F> dbl_affine(const Affine<F>& p) {
   F X2 = sqr(p.x);
   F M = add(dbl(X2), X2);
   F X3 = sub(sqr(M), dbl(S));
-  F Y3 = sub(mul(M, sub(S, X3)), mul(W, p.y));
+  F Y3 = mul_sub2(M, sub(S, X3), W, p.y);
   return {X3, Y3, V, W};
 }
 
@@ -63,7 +63,7 @@ GPW_HD_CALL XYZZ<F> dbl(const XYZZ<F>& p) {
   F X2 = sqr(p.X);
   F M = add(dbl(X2), X2);
   F X3 = sub(sqr(M), dbl(S));
-  F Y3 = sub(mul(M, sub(S, X3)), mul(W, p.Y));
+  F Y3 = mul_sub2(M, sub(S, X3), W, p.Y);
   return {X3, Y3, mul(V, p.ZZ), mul(W, p.ZZZ)};
 }
 
@@ -92,7 +92,7 @@ GPW_HD void add_mixed(XYZZ<F>& acc, const Affine<F>& q, bool negate) {
   F PPP = mul(Pv, PP);
   F Q = mul(acc.X, PP);
   F X3 = sub(sub(sqr(R), PPP), dbl(Q));
-  F Y3 = sub(mul(R, sub(Q, X3)), mul(acc.Y, PPP));
+  F Y3 = mul_sub2(R, sub(Q, X3), acc.Y, PPP);
   acc.X = X3;
   acc.Y = Y3;
   acc.ZZ = mul(acc.ZZ, PP);
@@ -125,7 +125,7 @@ GPW_HD_CALL void add_full(XYZZ<F>& acc, const XYZZ<F>& q) {
   F PPP = mul(Pv, PP);
   F Q = mul(U1, PP);
   F X3 = sub(sub(sqr(R), PPP), dbl(Q));
-  F Y3 = sub(mul(R, sub(Q, X3)), mul(S1, PPP));
+  F Y3 = mul_sub2(R, sub(Q, X3), S1, PPP);
   acc.X = X3;
   acc.Y = Y3;
   acc.ZZ = mul(mul(acc.ZZ, q.ZZ), PP);

@@ -219,7 +219,7 @@ __device__ __forceinline__ void add_mixed_flat(XYZZ<F>& acc, const Affine<F>& q,
   const F PPP = mul(Pv, PP);
   const F Q = mul(acc.X, PP);
   const F X3 = sub(sub(sqr(R), PPP), dbl(Q));
-  const F Y3 = sub(mul(R, sub(Q, X3)), mul(acc.Y, PPP));
+  const F Y3 = mul_sub2(R, sub(Q, X3), acc.Y, PPP);  // G1: both products under one Montgomery reduction
   const F Z2 = mul(acc.ZZ, PP);
   const F Z3 = mul(acc.ZZZ, PPP);
   // a_inf: the sum is q itself; q_inf: acc unchanged

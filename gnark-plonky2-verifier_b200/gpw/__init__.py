@@ -45,6 +45,7 @@ SYMBOLS = {
     "gpw_ctx_sync": (C.c_int, [_vp]),
     "gpw_ctx_launch_count": (C.c_uint64, [_vp]),
     "gpw_host_ff_mul": (C.c_int, [C.c_int, C.c_int, _vp, _vp, _vp, C.c_size_t]),
+    "gpw_host_ff_mul_sub2": (C.c_int, [C.c_int, _vp, _vp, _vp, _vp, _vp, C.c_size_t]),
     "gpw_host_ff_to_mont": (C.c_int, [C.c_int, _vp, _vp, C.c_size_t]),
     "gpw_host_ff_from_mont": (C.c_int, [C.c_int, _vp, _vp, C.c_size_t]),
     "gpw_host_ff_inv": (C.c_int, [C.c_int, _vp, _vp, C.c_size_t]),
@@ -136,6 +137,13 @@ def host_ff_mul(field, impl, a, b):
     a, b = _u64(a, (-1, 4)), _u64(b, (-1, 4))
     out = np.empty_like(a)
     _check(_lib.gpw_host_ff_mul(field, impl, _p(a), _p(b), _p(out), a.shape[0]))
+    return out
+
+
+def host_ff_mul_sub2(field, a, b, c, d):
+    a, b, c, d = (_u64(x, (-1, 4)) for x in (a, b, c, d))
+    out = np.empty_like(a)
+    _check(_lib.gpw_host_ff_mul_sub2(field, _p(a), _p(b), _p(c), _p(d), _p(out), a.shape[0]))
     return out
 
 

@@ -52,6 +52,9 @@ uint64_t gpw_ctx_launch_count(const gpw_ctx* ctx);
 /* ---- host-side arithmetic (no GPU): setup glue and the unit tests of the shared host/device code */
 /* field: 0 = Fr, 1 = Fp. impl: 0 = even/odd IMAD.WIDE schedule (host emulation), 1 = plain CIOS.  */
 int gpw_host_ff_mul(int field, int impl, const uint64_t* a_mont, const uint64_t* b_mont, uint64_t* out_mont, size_t n);
+/* a b - c d with one Montgomery reduction for both products (the form the bucket accumulation uses for Y3) */
+int gpw_host_ff_mul_sub2(int field, const uint64_t* a_mont, const uint64_t* b_mont, const uint64_t* c_mont, const uint64_t* d_mont,
+                         uint64_t* out_mont, size_t n);
 int gpw_host_ff_to_mont(int field, const uint64_t* a, uint64_t* out, size_t n);
 int gpw_host_ff_from_mont(int field, const uint64_t* a, uint64_t* out, size_t n);
 int gpw_host_ff_inv(int field, const uint64_t* a_mont, uint64_t* out_mont, size_t n);

@@ -33,6 +33,23 @@ def test_mont_mul_matches_bigint(field, impl):
 
 
 @pytest.mark.parametrize("field", [0, 1])
+def test_dual_product_mul_matches_bigint(field):
+    # a b - c d under ONE Montgomery reduction (mont_mul2): extreme operands exercise the accumulator's head-room
+    rng = random.Random(200 + field)
+    mod = MODS[field]
+    n = 3000
+    ext = [0, 1, mod - 1, mod - 2, mod // 2]
+    vals = [[rng.choice(ext) if i < 700 else rng.randrange(mod) for i in range(n)] for _ in range(4)]
+    for i in range(len(ext) ** 4):          # every combination of the extreme values
+        for k in range(4):
+            vals[k][700 + i] = ext[(i // len(ext) ** k) % len(ext)]
+    mont = [gpw.host_ff_to_mont(field, gpw.ints_to_limbs(v)) for v in vals]
+    out = gpw.limbs_to_ints(gpw.host_ff_from_mont(field, gpw.host_ff_mul_sub2(field, *mont)))
+    a, b, c, d = vals
+    assert out == [(a[i] * b[i] - c[i] * d[i]) % mod for i in range(n)]
+
+
+@pytest.mark.parametrize("field", [0, 1])
 def test_montgomery_constants(field):
     # to_mont(1) must equal R mod p from SURVEY A.1
     mod = MODS[field]
