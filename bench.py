@@ -296,7 +296,7 @@ def main():
                      # dram__bytes_read.sum + dram__bytes_write.sum of one captured launch (profiles/r01_msm_accumulate_ncu.md,
                      # capture A): the Z MSM, 8 388 607 full-width points, 12 non-zero digits each against the fixed-base table
                      # -> 13.9 GB vs 805 MB algorithmic: every digit gathers its own 64-byte precomputed base
-                     "traffic": 13927985312, "traffic_launch_points": 8388607,
+                     "traffic": 13925827096, "traffic_launch_points": 8388607,
                      "peak_source": peak_kind, "kernel": "k_msm_accumulate<Fp> (MSM G1 bucket accumulation)",
                      "launches_per_step": g1["calls"] / n_lat, "avg_launch_ms": avg_ms,
                      "avg_points_per_launch": g1["points"] / max(g1["calls"], 1),
