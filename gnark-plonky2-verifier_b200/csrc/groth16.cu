@@ -132,6 +132,7 @@ struct gpw_pk {
   // scratch for computeH
   Fr *ha = nullptr, *hb = nullptr, *hc = nullptr;
   float t_h_ms = 0, t_msm_ms[5] = {0, 0, 0, 0, 0};
+  cudaEvent_t h0 = nullptr, h1 = nullptr;  // computeH timing, created on first use
 };
 
 static int dev_alloc(void** p, size_t bytes) {
@@ -154,6 +155,8 @@ extern "C" void gpw_groth16_pk_free(gpw_pk* pk) {
   cudaFree(pk->ha);
   cudaFree(pk->hb);
   cudaFree(pk->hc);
+  if (pk->h0) cudaEventDestroy(pk->h0);
+  if (pk->h1) cudaEventDestroy(pk->h1);
   delete pk;
 }
 
@@ -249,15 +252,14 @@ extern "C" int gpw_groth16_prove_dev(gpw_pk* pk, uint64_t w_dev, uint64_t a_dev,
   gpw_ctx* ctx = pk->ctx;
   GPW_CUDA(cudaSetDevice(ctx->device));
   const size_t N = (size_t)1 << pk->logN;
-  cudaEvent_t e0 = ctx->ev[0], e1 = ctx->ev[1];
-  cudaEvent_t h0, h1;
-  GPW_CUDA(cudaEventCreate(&h0));
-  GPW_CUDA(cudaEventCreate(&h1));
+  if (!pk->h0 && (cudaEventCreate(&pk->h0) != cudaSuccess || cudaEventCreate(&pk->h1) != cudaSuccess)) {
+    set_error("cudaEventCreate failed");
+    return GPW_ECUDA;
+  }
+  cudaEvent_t h0 = pk->h0, h1 = pk->h1;
   GPW_CUDA(cudaEventRecord(h0, ctx->stream));
   GPW_TRY(gpw_groth16_compute_h_dev(ctx, a_dev, b_dev, c_dev, pk->logN));
   GPW_CUDA(cudaEventRecord(h1, ctx->stream));
-  (void)e0;
-  (void)e1;
   G1Affine mA, mB1, mK, mZ;
   G2Affine mB2;
   GPW_TRY(gpw_msm_g1_dev(ctx, w_dev, (uint64_t)pk->A, pk->m, 1, 0, 0, 0, (uint64_t*)&mA));
@@ -272,8 +274,6 @@ extern "C" int gpw_groth16_prove_dev(gpw_pk* pk, uint64_t w_dev, uint64_t a_dev,
   GPW_TRY(gpw_msm_g1_dev(ctx, a_dev, (uint64_t)pk->Z, N - 1, 1, 0, 0, 0, (uint64_t*)&mZ));
   pk->t_msm_ms[4] = ctx->msm_total_ms;
   GPW_CUDA(cudaEventElapsedTime(&pk->t_h_ms, h0, h1));
-  cudaEventDestroy(h0);
-  cudaEventDestroy(h1);
   // host assembly (a few hundred group operations)
   uint32_t rw[8], sw[8];
   memcpy(rw, r_canon, 32);

@@ -471,9 +471,9 @@ __global__ void __launch_bounds__(128)
 // The Fr inversions of a wide level - gnark's IsZero hint (one per range check) and the 2.5 M divisions of the
 // log-derivative argument - with Montgomery's trick: a thread owns INV_G instructions (strided by the grid so that
 // neighbouring lanes touch neighbouring wires), multiplies their denominators up, inverts the product once (Fermat,
-// ~380 multiplies) and peels the individual inverses off on the way back: ~27 multiplies per inversion instead of ~380.
+// ~380 multiplies) and peels the individual inverses off on the way back: ~15 multiplies per inversion instead of ~380.
 // Zero denominators (IsZero of 0 -> 0; a division by zero is reported and yields 0 like inv(0) = 0 did) sit out.
-constexpr int INV_G = 16;
+constexpr int INV_G = 32;
 __global__ void __launch_bounds__(128)
     k_tape_wide_inv(DevCircuit c, Fr* __restrict__ wires, size_t wire_stride, int* __restrict__ err, uint32_t s, uint32_t t) {
   Fr* W = wires + (size_t)blockIdx.y * wire_stride;

@@ -169,6 +169,7 @@ struct WrapLane {
   Fr *wires = nullptr, *va = nullptr, *vb = nullptr, *vc = nullptr, *gathA = nullptr, *gathB = nullptr;
   uint64_t* inputs_dev = nullptr;
   cudaEvent_t done = nullptr;
+  cudaEvent_t tev[9] = {};  // phase timing events of a wrap ([0,1]: solve phase 1, [2..8]: stage 2), created once per lane
   float t_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 };
 constexpr int WRAP_DEFAULT_LANES = 6, WRAP_MAX_LANES = 16;
@@ -222,6 +223,8 @@ static void lane_free(WrapLane* l) {
   void* ps[] = {l->wires, l->va, l->vb, l->vc, l->gathA, l->gathB, l->inputs_dev};
   for (void* p : ps) cudaFree(p);
   if (l->done) cudaEventDestroy(l->done);
+  for (cudaEvent_t e : l->tev)
+    if (e) cudaEventDestroy(e);
   if (l->own_ctx) gpw_ctx_destroy(l->ctx);
   delete l;
 }
@@ -253,7 +256,9 @@ static int lane_create(gpw_wrap_key* k, gpw_ctx* ctx, WrapLane** out) {
     lane_free(l);
     return rc;
   }
-  if (cudaEventCreateWithFlags(&l->done, cudaEventDisableTiming) != cudaSuccess) {
+  bool ev_ok = cudaEventCreateWithFlags(&l->done, cudaEventDisableTiming) == cudaSuccess;
+  for (cudaEvent_t& e : l->tev) ev_ok = ev_ok && cudaEventCreate(&e) == cudaSuccess;
+  if (!ev_ok) {
     set_error("cudaEventCreate failed");
     lane_free(l);
     return GPW_ECUDA;
@@ -411,21 +416,14 @@ static int wrap_stage2(gpw_wrap_key* k, WrapLane* L, const uint64_t* r_canon, co
 static int wrap_one(gpw_wrap_key* k, WrapLane* L, uint64_t inputs_dev, const uint64_t* r_canon, const uint64_t* s_canon, int check,
                     uint64_t* out_proof) {
   cudaStream_t st = L->ctx->stream;
-  cudaEvent_t e0, e1;
-  GPW_CUDA(cudaEventCreate(&e0));
-  GPW_CUDA(cudaEventCreate(&e1));
+  cudaEvent_t e0 = L->tev[0], e1 = L->tev[1];
   GPW_CUDA(cudaEventRecord(e0, st));
-  int rc = gpw_witness_solve_phase1_on(k->circ, L->ctx, inputs_dev, 1, (uint64_t)L->wires, k->m);
+  GPW_TRY(gpw_witness_solve_phase1_on(k->circ, L->ctx, inputs_dev, 1, (uint64_t)L->wires, k->m));
   float t1 = 0;
-  if (rc == GPW_OK) {
-    cudaEventRecord(e1, st);
-    cudaEventSynchronize(e1);
-    cudaEventElapsedTime(&t1, e0, e1);
-  }
-  cudaEventDestroy(e0);
-  cudaEventDestroy(e1);
-  GPW_TRY(rc);
-  rc = wrap_stage2(k, L, r_canon, s_canon, check, out_proof);
+  GPW_CUDA(cudaEventRecord(e1, st));
+  GPW_CUDA(cudaEventSynchronize(e1));
+  GPW_CUDA(cudaEventElapsedTime(&t1, e0, e1));
+  int rc = wrap_stage2(k, L, r_canon, s_canon, check, out_proof);
   L->t_ms[0] = t1;
   return rc;
 }
@@ -463,8 +461,7 @@ static int wrap_stage2(gpw_wrap_key* k, WrapLane* L, const uint64_t* r_canon, co
   cudaStream_t st = ctx->stream;
   Fr* wires = L->wires;
   const size_t N = (size_t)1 << k->logN;
-  cudaEvent_t ev[7];
-  for (auto& e : ev) GPW_CUDA(cudaEventCreate(&e));
+  cudaEvent_t* ev = L->tev + 2;  // 7 events
   memset(out_proof, 0, 64 * 8);
   const bool dbg = getenv("GPW_DEBUG_WRAP") != nullptr;
   auto report = [&](const char* what, size_t n) {
@@ -548,7 +545,6 @@ static int wrap_stage2(gpw_wrap_key* k, WrapLane* L, const uint64_t* r_canon, co
   GPW_CUDA(cudaEventRecord(ev[6], st));
   GPW_CUDA(cudaStreamSynchronize(st));
   for (int i = 0; i < 6; i++) GPW_CUDA(cudaEventElapsedTime(&L->t_ms[i], ev[i], ev[i + 1]));
-  for (auto& e : ev) cudaEventDestroy(e);
   // assembly (gnark groth16.Prove)
   uint32_t rw[8], sw[8];
   memcpy(rw, r_canon, 32);
