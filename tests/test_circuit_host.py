@@ -114,6 +114,24 @@ def test_poseidon_gl_macro_host(lib, kats):
     assert [int(x) for x in out] == [int(x) for x in kats["poseidon_gl_perm_zero"]]
 
 
+def test_compile_rejects_unsupported_circuits(lib, testdata_dir):
+    # types/common_data.go:121-124 panics on hiding = true; an unknown gate id is refused by GateInstanceFromId
+    # (plonk/gates/gates.go:37-54); both must fail loudly here too, in the C++ frontend and in the oracle
+    import json
+    from oracle.types import CommonCircuitData
+    src = open(os.path.join(testdata_dir, "step", "common_circuit_data.json")).read()
+    d = json.loads(src)
+    d["fri_params"]["hiding"] = True
+    assert not lib.ct_compile(json.dumps(d).encode())
+    assert b"hiding" in lib.ct_last_error()
+    with pytest.raises(ValueError):
+        CommonCircuitData(d)
+    d = json.loads(src)
+    d["gates"][0] = "NotAGate { num_things: 3 }"
+    assert not lib.ct_compile(json.dumps(d).encode())
+    assert lib.ct_last_error()
+
+
 def test_full_verifier_circuit_on_step(lib, testdata_dir):
     d = os.path.join(testdata_dir, "step")
     rd = lambda f: open(os.path.join(d, f), "rb").read()
