@@ -388,7 +388,22 @@ bool API::EndFuse(Op op, const Variable* in, size_t n_in, uint32_t expect_nout) 
   m.outs_off = (uint32_t)macro_outs_.size();
   macro_outs_.insert(macro_outs_.end(), outs.begin(), outs.end());
   tape_.push_back(m);
-  tape_.insert(tape_.end(), kept.begin(), kept.end());
+  // The kept instructions were levelled against the hints' own (per-element) levels; the macro sits at the level of its
+  // latest input, which can be later than that. Re-level them in tape (= dependency) order.
+  for (Instr& in : kept) {
+    uint32_t need = 0;
+    const uint32_t les[4] = {in.le[0], in.le[1], in.le[2], in.le3};
+    for (uint32_t le : les) {
+      if (le == NO_LE) continue;
+      for (uint32_t t = le_off_[le]; t < le_off_[le + 1]; t++) need = std::max(need, wire_level_[le_wire_[t]] + 1);
+    }
+    if (need > in.level) {
+      in.level = need;
+      for (uint32_t k = 0; k < in.nout; k++) wire_level_[in.out + k] = need;
+      if (need > max_level_) max_level_ = need;
+    }
+    tape_.push_back(in);
+  }
   return true;
 }
 

@@ -117,6 +117,45 @@ void* ct_compile_small(int kind) {
 void ct_schedule_alap(void* h) { ((Circuit*)h)->api.ScheduleALAP(); }
 void ct_schedule_spine_tail(void* h) { ((Circuit*)h)->api.ScheduleSpineAndTail(); }
 
+// Structural check of the (scheduled) tape the GPU executor runs: every input wire of an instruction is a circuit input
+// or is produced by an instruction of a strictly LOWER level; every wire has at most one producer; macro instructions
+// carry as many output wires as they claim. out3 = {level violations, doubly produced wires, macro instructions}.
+void ct_schedule_check(void* h, uint64_t* out3) {
+  Circuit* c = (Circuit*)h;
+  const API& api = c->api;
+  const auto& tape = api.Tape();
+  const auto& mo = api.MacroOuts();
+  const auto& off = api.LeOffsets();
+  const auto& wi = api.LeWires();
+  std::vector<uint32_t> producer_level(api.NumWires(), 0xffffffffu);
+  uint64_t bad_level = 0, dup = 0, macros = 0;
+  for (const auto& in : tape) {
+    if (in.outs_off != NO_LE) macros++;
+    for (uint32_t k = 0; k < in.nout; k++) {
+      const uint32_t w = in.out_wire(k, mo);
+      if (producer_level[w] != 0xffffffffu) dup++;
+      producer_level[w] = in.level;
+    }
+  }
+  for (const auto& in : tape) {
+    const uint32_t les[4] = {in.le[0], in.le[1], in.le[2], in.le3};
+    for (uint32_t le : les) {
+      if (le == NO_LE) continue;
+      for (uint32_t t = off[le]; t < off[le + 1]; t++) {
+        const uint32_t pl = producer_level[wi[t]];
+        if (pl != 0xffffffffu && pl >= in.level) {
+          if (bad_level < 8 && getenv("CT_DEBUG"))
+            fprintf(stderr, "violation: op %d level %u out %u reads wire %u produced at level %u\n", in.op, in.level, in.out, wi[t], pl);
+          bad_level++;
+        }
+      }
+    }
+  }
+  out3[0] = bad_level;
+  out3[1] = dup;
+  out3[2] = macros;
+}
+
 void ct_free(void* h) { delete (Circuit*)h; }
 
 // stats: [wires, public, secret, constraints, tape, levels, commit_level, limb_wires, muladd, reduce, glinv, split,

@@ -114,6 +114,33 @@ def test_poseidon_gl_macro_host(lib, kats):
     assert [int(x) for x in out] == [int(x) for x in kats["poseidon_gl_perm_zero"]]
 
 
+def _schedule_check(lib, h):
+    lib.ct_schedule_check.argtypes = [C.c_void_p, C.c_void_p]
+    out = np.zeros(3, dtype=np.uint64)
+    lib.ct_schedule_check(h, out.ctypes.data)
+    return [int(x) for x in out]
+
+
+def test_tape_schedule_is_consistent(lib, testdata_dir):
+    # the tape the GPU executor walks: after the ASAP levels of the builder, after ALAP and after the spine-and-tail
+    # schedule every operand comes from a strictly lower level and no wire has two producers; the verifier circuit of
+    # `step` carries one Poseidon-Goldilocks macro per permutation (129 challenger + 5 public-input hash) and one
+    # Poseidon-BN254 macro per Merkle / leaf hash permutation
+    lib.ct_schedule_spine_tail.argtypes = [C.c_void_p]
+    h = lib.ct_compile_small(0)
+    assert _schedule_check(lib, h)[:2] == [0, 0]
+    lib.ct_schedule_spine_tail(h)
+    assert _schedule_check(lib, h)[:2] == [0, 0]
+    lib.ct_free(h)
+    h = lib.ct_compile(open(os.path.join(testdata_dir, "step", "common_circuit_data.json"), "rb").read())
+    bad, dup, macros = _schedule_check(lib, h)
+    assert (bad, dup) == (0, 0) and macros == 134
+    lib.ct_schedule_spine_tail(h)
+    bad, dup, macros = _schedule_check(lib, h)
+    assert (bad, dup) == (0, 0) and macros == 134
+    lib.ct_free(h)
+
+
 def test_compile_rejects_unsupported_circuits(lib, testdata_dir):
     # types/common_data.go:121-124 panics on hiding = true; an unknown gate id is refused by GateInstanceFromId
     # (plonk/gates/gates.go:37-54); both must fail loudly here too, in the C++ frontend and in the oracle
