@@ -308,6 +308,52 @@ def test_msm_fixed_base_matches_windowed(ctx, window_bits):
     assert gpw.points_to_ints(1, row)[0] == ob.point_key(1, exp)
 
 
+def _dot_mod_r(scalars_u64x4, first_k):
+    """sum_i scalars[i] * (first_k + i) mod r for (n, 4) little-endian u64 limbs, exactly, with numpy: 16-bit pieces keep
+    every partial sum below 2^64 (piece < 2^16, multiplier < 2^24, n <= 2^23)."""
+    n = scalars_u64x4.shape[0]
+    ks = np.arange(first_k, first_k + n, dtype=np.uint64)
+    assert first_k + n < (1 << 24) and n <= (1 << 23)
+    total = 0
+    for limb in range(4):
+        col = scalars_u64x4[:, limb]
+        for piece in range(4):
+            part = (col >> np.uint64(16 * piece)) & np.uint64(0xffff)
+            total += int((part * ks).sum(dtype=np.uint64)) << (64 * limb + 16 * piece)
+    return total % ob.R
+
+
+def test_msm_full_size_windowed_and_fixed_base(ctx):
+    # BASELINE-scale MSM (n = 2^23 - 1 G1 points, the size of the Z MSM of testdata/step): exact check through the known
+    # discrete logs - points [k]G, k = 1..n, so the result must be [sum s_k k]G - for the windowed MSM on a witness-shaped
+    # scalar mix and for the fixed-base MSM (22-bit windows, one bucket set) on full-width scalars
+    import torch
+    n = (1 << 23) - 1
+    pts = torch.empty((n, 8), dtype=torch.int64, device="cuda")
+    ctx.generator_multiples_dev(1, 1, n, pts.data_ptr())
+    rng = np.random.default_rng(11)
+    s = rng.integers(0, 1 << 62, size=(n, 4), dtype=np.uint64)
+    s[:, 3] &= np.uint64((1 << 59) - 1)                    # < 2^251 < r
+    full = s.copy()
+    u = rng.random(n)
+    s[u < 0.80, 1:] = 0                                     # 80 % at most 64 bits ...
+    s[u < 0.35, 0] &= np.uint64(0xffff)                     # ... 35 % 16-bit limbs ...
+    s[u < 0.15, 0] &= np.uint64(1)                          # ... 15 % bits (the hot bucket)
+    for scalars, fixed in ((s, False), (full, True)):
+        ds = torch.from_numpy(scalars.view(np.int64)).cuda()
+        torch.cuda.synchronize()
+        if fixed:
+            W = ctx.msm_fixed_windows(22)
+            table = torch.empty((W * n, 8), dtype=torch.int64, device="cuda")
+            ctx.msm_g1_fixed_table(pts.data_ptr(), n, 22, table.data_ptr())
+            out = ctx.msm_g1_fixed_dev(ds.data_ptr(), table.data_ptr(), n, 22)
+            del table
+        else:
+            out = ctx.msm_dev(1, ds.data_ptr(), pts.data_ptr(), n)
+        exp = ob.ec_mul(1, ob.G1_GEN, _dot_mod_r(scalars, 1))
+        assert gpw.points_to_ints(1, out)[0] == ob.point_key(1, exp), "fixed-base" if fixed else "windowed"
+
+
 # ---- K8: NTT ------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("logn", [0, 1, 2, 3, 5, 8, 9, 10])
 def test_ntt_small_vs_definition(ctx, logn):
