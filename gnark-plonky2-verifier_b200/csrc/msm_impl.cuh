@@ -11,14 +11,16 @@
 //   3. k_msm_digits<1> counting-sort scatter of (point index | sign) by bucket (both passes warp-aggregate their atomics)
 //   4. k_msm_accumulate  THE hot kernel: the sorted entry array is cut into uniform tasks of
 //                      MSM_TASK entries; one thread walks one task doing XYZZ += affine mixed adds
-//                      (8M + 2S each, ~3000 IMADs) with 64 B / 128 B gathers of the affine points.
-//                      Uniform tasks make the work per thread identical even for the heavily skewed
-//                      scalar distribution of a gnark witness (most wires are 0/1 or < 2^64), where
-//                      thread-per-bucket schemes serialise on the hot buckets.
-//   5. k_msm_fixup     buckets that span several tasks: warp-parallel sum of their partials
-//   6. k_msm_window_partial / k_msm_window_final   sum_b (b+1) * B[w][b] per window
+//                      (8 multiplications + the dual-product Y3: ~1290 IMAD.WIDE) with 64 B / 128 B gathers of the
+//                      affine points, in ONE flat loop so the warp stays converged. Uniform tasks make the work per
+//                      thread identical even for the heavily skewed scalar distribution of a gnark witness (most
+//                      wires are 0/1 or < 2^64), where thread-per-bucket schemes serialise on the hot buckets.
+//   5. k_msm_fixup(_big)  buckets that span several tasks: their partials follow from the bucket offsets alone
+//   6. k_msm_window_partial (two levels) / k_msm_window_final   sum_b (b+1) * B[w][b] per window
 //   7. host: Horner over <= 16 window sums (270 group ops) and one inversion to affine.
 // Zero digits are skipped entirely, so a scalar < 2^64 costs 4-5 adds instead of 16.
+// Variants: fixed-base mode (precomputed 2^(c w) P_i, one bucket set, msm_dev_impl's fixed_windows) and shared sorts
+// (several MSMs over the same scalars, sort_tag / reuse_sort).
 #include "common.cuh"
 #include "ec.cuh"
 
