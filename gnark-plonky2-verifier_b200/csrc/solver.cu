@@ -69,7 +69,16 @@ struct Segment {
   std::vector<Part> parts;
 };
 
+// levels with at least this many instructions run as grid launches across all SMs, narrower ones on the proof's
+// persistent spine CTA (GPW_WIDE_THRESHOLD overrides it at circuit-compile time, for experiments). Measured on
+// testdata/step: 2048 -> solve phase 1 45.8 ms instead of 47.7 ms, 512 -> 69.7 ms: below a few thousand instructions the
+// staged spine (tape and operands in shared memory, no launch per level) beats a grid launch with cold operands.
 constexpr uint32_t WIDE_THRESHOLD = 8192;
+static uint32_t wide_threshold() {
+  const char* e = getenv("GPW_WIDE_THRESHOLD");
+  const long v = e ? atol(e) : 0;
+  return v >= 64 ? (uint32_t)v : WIDE_THRESHOLD;
+}
 constexpr int NARROW_THREADS = 256;  // upper bound (launch bounds); the spine launches spine_threads() of them
 
 __device__ __forceinline__ Fr ld_w(const Fr* p) {
@@ -662,7 +671,7 @@ static int finish_compile(gpw_circuit* c) {
   for (uint32_t l = 0; l < L; l++) {
     const uint32_t cnt = level_off[l + 1] - level_off[l];
     const bool special = (l == count_level || l == commit_level);
-    if (cnt >= WIDE_THRESHOLD || special) {
+    if (cnt >= wide_threshold() || special) {
       flush(l);
       if (cnt) {
         Segment w{SEG_WIDE, l, l + 1};
