@@ -1293,3 +1293,7 @@ extern "C" int gpw_circuit_compile_gadget(gpw_ctx* ctx, const char* name, gpw_ci
   *out = c;
   return GPW_OK;
 }
+
+// Internal (not part of the C ABI): the host-side compiled circuit, for the trusted setup (csrc/setup.cu) and the
+// circuit cache.
+const gpw::fe::API* gpw_circuit_api_internal(const gpw_circuit* c) { return c ? &c->api : nullptr; }

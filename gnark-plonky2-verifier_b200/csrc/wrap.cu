@@ -5,6 +5,8 @@
 //     proof, _   := groth16.Prove(r1cs, pk, witness)            (benchmark.go:240-249)
 // with the circuit from gpw_circuit_compile_verifier standing in for frontend.Compile (benchmark.go:55) and
 // gpw_wrap_key_synthetic for groth16.DummySetup (benchmark.go:214).
+#include <sys/random.h>
+
 #include <atomic>
 #include <cstring>
 #include <mutex>
@@ -92,6 +94,12 @@ struct Sha256 {
   }
 };
 
+void sha256_bytes(const uint8_t* msg, size_t len, uint8_t out[32]) {
+  Sha256 s;
+  s.update(msg, len);
+  s.final(out);
+}
+
 static void sha256(const std::vector<uint8_t>& m, uint8_t out[32]) {
   Sha256 s;
   s.update(m.data(), m.size());
@@ -155,59 +163,7 @@ int gpw_msm_g1_shared_dev(gpw_ctx* ctx, uint64_t s, uint64_t p, size_t n, int mo
 int gpw_msm_g2_shared_dev(gpw_ctx* ctx, uint64_t s, uint64_t p, size_t n, int mont, int c, const char* sort_tag, int reuse, uint64_t* out);
 }
 
-// Proving key for a compiled circuit. Bases are synthetic (known discrete logs, documented below) - the analogue of
-// groth16.DummySetup - but have exactly the shapes a real key has for THIS circuit: A / B bases only for wires that
-// occur in some L / R row (gnark's pk.InfinityA / InfinityB filtering), K bases for private non-committed wires, a
-// Pedersen commitment basis (+ its sigma-twin for the proof of knowledge) for the committed wires, Z for h.
-// A proving LANE = one proof in flight: its own context (stream + scratch memory), wire vector, evaluation vectors
-// and gathered scalars. Lane 0 lives on the key's context and serves the single-proof entry points; gpw_wrap_prove_many
-// runs one host thread per lane, so that the sequential solve spine of one proof (one SM), the host-side glue of another
-// (Horner over window sums, proof assembly) and the MSMs / NTTs of the others overlap on the device.
-struct WrapLane {
-  gpw_ctx* ctx = nullptr;
-  bool own_ctx = false;
-  Fr *wires = nullptr, *va = nullptr, *vb = nullptr, *vc = nullptr, *gathA = nullptr, *gathB = nullptr;
-  uint64_t* inputs_dev = nullptr;
-  cudaEvent_t done = nullptr;
-  cudaEvent_t tev[9] = {};  // phase timing events of a wrap ([0,1]: solve phase 1, [2..8]: stage 2), created once per lane
-  float t_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-};
-constexpr int WRAP_DEFAULT_LANES = 6, WRAP_MAX_LANES = 16;
-// window widths of the fixed-base tables: 22 bits (12 additions per scalar, 2^21 buckets) for the 8.4 M-point Z MSM; 20 bits
-// (13 additions, 2^19 buckets) for the 2.5 M-point quotient ranges of A and K, where the reduction of 2^21 buckets would
-// cost more than the thirteenth addition
-constexpr int FIXED_C = 22, FIXED_W = (254 + FIXED_C) / FIXED_C;
-constexpr int FIXED_CQ = 20, FIXED_WQ = (254 + FIXED_CQ) / FIXED_CQ;
-
-struct gpw_wrap_key {
-  gpw_ctx* ctx = nullptr;
-  gpw_circuit* circ = nullptr;
-  uint32_t m = 0, n_pub = 0, n_cons = 0;
-  int logN = 0;
-  uint32_t limb_start = 0, n_committed = 0, commit_wire = 0;
-  uint32_t nA = 0, nB = 0;
-  uint32_t *suppA = nullptr, *suppB = nullptr;  // device wire-id lists
-  G1Affine *A = nullptr, *B1 = nullptr, *K = nullptr, *Z = nullptr, *CK = nullptr, *CKs = nullptr;
-  G2Affine* B2 = nullptr;
-  // fixed-base tables (2^(22 w) P, 12 windows) for the two MSMs whose scalars are full-width field elements: Z (the
-  // quotient coefficients h) and the K range behind the committed wires (the log-derivative quotients). 12 instead of
-  // 16 bucket additions per scalar; 8.4 GB of HBM. GPW_FIXED_BASE=0 keeps the plain windowed MSMs.
-  G1Affine *Zt = nullptr, *K2t = nullptr, *At = nullptr;
-  // Behind the committed wires sit the commitment-challenge wire and then the log-derivative quotients. The challenge
-  // is a public input of the verifier (gnark appends commitment wires to the public witness, their bases live in vk.K),
-  // so it is not part of the prover's K MSM: the second K range starts at k2_lo, right behind it. That range is exactly
-  // the scalars of A's fixed-base suffix, whose bucket sort the K MSM then reuses.
-  uint32_t k2_lo = 0;
-  bool share_q_sort = false;
-  uint32_t nA_tail = 0;  // the last nA_tail wires of A's support are the log-derivative quotients too (they are the L side
-                         // of their own division constraints): that suffix of the A MSM also runs fixed-base
-  G1Affine alpha1, beta1, delta1;
-  G2Affine beta2, delta2;
-  uint32_t n_inputs = 0;
-  std::vector<WrapLane*> lanes;
-  int want_lanes = WRAP_DEFAULT_LANES;
-  uint64_t seed = 0;
-};
+#include "wrap_internal.cuh"
 
 static int wk_alloc(void** p, size_t bytes) {
   cudaError_t e = cudaMalloc(p, bytes ? bytes : 16);
@@ -282,10 +238,7 @@ static Affine<F> gen_mul_host(uint64_t k) {
   return to_affine(host_scalar_mul(generator<F>(), kw));
 }
 
-// Discrete logs (all bases are [k]G): A_j = [1 + j], B1_j = [2^32 + j], B2_j = [1 + j] (G2), K_i = [2^33 + i],
-// Z_j = [2^34 + j], CK_i = [2^35 + i], CKs_i = [2^36 + i]; alpha = [seed+1], beta = [seed+2], delta = [seed+3].
-// (j indexes the compacted A / B support lists, i is the wire id.)
-extern "C" int gpw_wrap_key_synthetic(gpw_ctx* ctx, gpw_circuit* circ, uint64_t seed, gpw_wrap_key** out) {
+int wrap_key_alloc(gpw_ctx* ctx, gpw_circuit* circ, gpw_wrap_key** out) {
   if (!ctx || !circ || !out) {
     set_error("wrap_key: null argument");
     return GPW_EINVAL;
@@ -296,7 +249,6 @@ extern "C" int gpw_wrap_key_synthetic(gpw_ctx* ctx, gpw_circuit* circ, uint64_t 
   gpw_wrap_key* k = new gpw_wrap_key();
   k->ctx = ctx;
   k->circ = circ;
-  k->seed = seed;
   k->m = (uint32_t)info[0];
   k->n_pub = (uint32_t)info[1];
   k->n_inputs = (uint32_t)(info[1] + info[2]);
@@ -307,70 +259,106 @@ extern "C" int gpw_wrap_key_synthetic(gpw_ctx* ctx, gpw_circuit* circ, uint64_t 
   k->logN = 1;
   while ((1ull << k->logN) < k->n_cons) k->logN++;
   const size_t N = (size_t)1 << k->logN;
-  std::vector<uint32_t> sa(k->m), sb(k->m);
+  std::vector<uint32_t>&sa = k->suppA_host, &sb = k->suppB_host;
+  sa.resize(k->m);
+  sb.resize(k->m);
   size_t na = 0, nb = 0;
-  GPW_TRY(gpw_circuit_supports(circ, 0, sa.data(), sa.size(), &na));
-  GPW_TRY(gpw_circuit_supports(circ, 1, sb.data(), sb.size(), &nb));
+  int rc = 0;
+  auto fail = [&](int code) {
+    gpw_wrap_key_free(k);
+    return code;
+  };
+  if ((rc = gpw_circuit_supports(circ, 0, sa.data(), sa.size(), &na)) || (rc = gpw_circuit_supports(circ, 1, sb.data(), sb.size(), &nb)))
+    return fail(rc);
+  sa.resize(na);
+  sb.resize(nb);
   k->nA = (uint32_t)na;
   k->nB = (uint32_t)nb;
-  int rc = 0;
   if ((rc = wk_alloc((void**)&k->suppA, na * 4)) || (rc = wk_alloc((void**)&k->suppB, nb * 4)) ||
       (rc = wk_alloc((void**)&k->A, na * sizeof(G1Affine))) || (rc = wk_alloc((void**)&k->B1, nb * sizeof(G1Affine))) ||
       (rc = wk_alloc((void**)&k->B2, nb * sizeof(G2Affine))) || (rc = wk_alloc((void**)&k->K, (size_t)k->m * sizeof(G1Affine))) ||
       (rc = wk_alloc((void**)&k->Z, N * sizeof(G1Affine))) || (rc = wk_alloc((void**)&k->CK, (size_t)k->n_committed * sizeof(G1Affine))) ||
-      (rc = wk_alloc((void**)&k->CKs, (size_t)k->n_committed * sizeof(G1Affine)))) {
-    gpw_wrap_key_free(k);
-    return rc;
-  }
+      (rc = wk_alloc((void**)&k->CKs, (size_t)k->n_committed * sizeof(G1Affine))))
+    return fail(rc);
   {
     WrapLane* l0 = nullptr;
-    if ((rc = lane_create(k, ctx, &l0))) {
-      gpw_wrap_key_free(k);
-      return rc;
-    }
+    if ((rc = lane_create(k, ctx, &l0))) return fail(rc);
     k->lanes.push_back(l0);
   }
   if (const char* e = getenv("GPW_WRAP_LANES")) k->want_lanes = std::max(1, std::min(WRAP_MAX_LANES, atoi(e)));
-  GPW_CUDA(cudaMemcpy(k->suppA, sa.data(), na * 4, cudaMemcpyHostToDevice));
-  GPW_CUDA(cudaMemcpy(k->suppB, sb.data(), nb * 4, cudaMemcpyHostToDevice));
-  GPW_TRY(gpw_ec_generator_multiples_dev(ctx, 1, 1, na, (uint64_t)k->A));
-  GPW_TRY(gpw_ec_generator_multiples_dev(ctx, 1, 1ull << 32, nb, (uint64_t)k->B1));
-  GPW_TRY(gpw_ec_generator_multiples_dev(ctx, 2, 1, nb, (uint64_t)k->B2));
-  GPW_TRY(gpw_ec_generator_multiples_dev(ctx, 1, 1ull << 33, k->m, (uint64_t)k->K));
-  GPW_TRY(gpw_ec_generator_multiples_dev(ctx, 1, 1ull << 34, N - 1, (uint64_t)k->Z));
-  GPW_TRY(gpw_ec_generator_multiples_dev(ctx, 1, (1ull << 35) + k->limb_start, k->n_committed, (uint64_t)k->CK));
-  GPW_TRY(gpw_ec_generator_multiples_dev(ctx, 1, (1ull << 36) + k->limb_start, k->n_committed, (uint64_t)k->CKs));
-  {
-    const char* e = getenv("GPW_FIXED_BASE");
-    const uint32_t c_hi = k->n_committed ? k->limb_start + k->n_committed : k->m;
-    // the challenge wire (if any) is the first wire behind the committed range
-    k->k2_lo = (k->n_committed && k->commit_wire == c_hi && c_hi < k->m) ? c_hi + 1 : c_hi;
-    if (!(e && atoi(e) == 0)) {
-      if ((rc = wk_alloc((void**)&k->Zt, (size_t)FIXED_W * (N - 1) * sizeof(G1Affine))) ||
-          (k->k2_lo < k->m && (rc = wk_alloc((void**)&k->K2t, (size_t)FIXED_WQ * (k->m - k->k2_lo) * sizeof(G1Affine))))) {
-        gpw_wrap_key_free(k);
-        return rc;
-      }
-      GPW_TRY(gpw_msm_g1_fixed_table(ctx, (uint64_t)k->Z, N - 1, FIXED_C, FIXED_W, (uint64_t)k->Zt));
-      if (k->K2t) GPW_TRY(gpw_msm_g1_fixed_table(ctx, (uint64_t)(k->K + k->k2_lo), k->m - k->k2_lo, FIXED_CQ, FIXED_WQ, (uint64_t)k->K2t));
-      while (k->nA_tail < na && sa[na - 1 - k->nA_tail] >= c_hi) k->nA_tail++;  // supports are sorted by wire id
-      // A's suffix is exactly the wires [k2_lo, m) iff it has that many entries and starts there (sorted, distinct)
-      k->share_q_sort = k->K2t && k->nA_tail == k->m - k->k2_lo && k->nA_tail > 0 && sa[na - k->nA_tail] == k->k2_lo;
-      if (k->nA_tail) {
-        if ((rc = wk_alloc((void**)&k->At, (size_t)FIXED_WQ * k->nA_tail * sizeof(G1Affine)))) {
-          gpw_wrap_key_free(k);
-          return rc;
-        }
-        GPW_TRY(gpw_msm_g1_fixed_table(ctx, (uint64_t)(k->A + (na - k->nA_tail)), k->nA_tail, FIXED_CQ, FIXED_WQ, (uint64_t)k->At));
-      }
+  if (cudaMemcpy(k->suppA, sa.data(), na * 4, cudaMemcpyHostToDevice) != cudaSuccess ||
+      cudaMemcpy(k->suppB, sb.data(), nb * 4, cudaMemcpyHostToDevice) != cudaSuccess) {
+    set_error("wrap_key: support upload failed: %s", cudaGetErrorString(cudaGetLastError()));
+    return fail(GPW_ECUDA);
+  }
+  const uint32_t c_hi = k->n_committed ? k->limb_start + k->n_committed : k->m;
+  // the challenge wire (if any) is the first wire behind the committed range
+  k->k2_lo = (k->n_committed && k->commit_wire == c_hi && c_hi < k->m) ? c_hi + 1 : c_hi;
+  *out = k;
+  return GPW_OK;
+}
+
+// Fixed-base tables over the filled-in bases (Z, the K range behind the commitment, A's quotient suffix).
+int wrap_key_finish(gpw_wrap_key* k) {
+  gpw_ctx* ctx = k->ctx;
+  const size_t N = (size_t)1 << k->logN;
+  const std::vector<uint32_t>& sa = k->suppA_host;
+  const size_t na = sa.size();
+  int rc = 0;
+  auto fail = [&](int code) {
+    gpw_wrap_key_free(k);
+    return code;
+  };
+  const char* e = getenv("GPW_FIXED_BASE");
+  const uint32_t c_hi = k->n_committed ? k->limb_start + k->n_committed : k->m;
+  if (!(e && atoi(e) == 0)) {
+    if ((rc = wk_alloc((void**)&k->Zt, (size_t)FIXED_W * (N - 1) * sizeof(G1Affine))) ||
+        (k->k2_lo < k->m && (rc = wk_alloc((void**)&k->K2t, (size_t)FIXED_WQ * (k->m - k->k2_lo) * sizeof(G1Affine)))))
+      return fail(rc);
+    if ((rc = gpw_msm_g1_fixed_table(ctx, (uint64_t)k->Z, N - 1, FIXED_C, FIXED_W, (uint64_t)k->Zt))) return fail(rc);
+    if (k->K2t && (rc = gpw_msm_g1_fixed_table(ctx, (uint64_t)(k->K + k->k2_lo), k->m - k->k2_lo, FIXED_CQ, FIXED_WQ, (uint64_t)k->K2t)))
+      return fail(rc);
+    while (k->nA_tail < na && sa[na - 1 - k->nA_tail] >= c_hi) k->nA_tail++;  // supports are sorted by wire id
+    // A's suffix is exactly the wires [k2_lo, m) iff it has that many entries and starts there (sorted, distinct)
+    k->share_q_sort = k->K2t && k->nA_tail == k->m - k->k2_lo && k->nA_tail > 0 && sa[na - k->nA_tail] == k->k2_lo;
+    if (k->nA_tail) {
+      if ((rc = wk_alloc((void**)&k->At, (size_t)FIXED_WQ * k->nA_tail * sizeof(G1Affine)))) return fail(rc);
+      if ((rc = gpw_msm_g1_fixed_table(ctx, (uint64_t)(k->A + (na - k->nA_tail)), k->nA_tail, FIXED_CQ, FIXED_WQ, (uint64_t)k->At)))
+        return fail(rc);
     }
+  }
+  if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) {
+    set_error("wrap_key: %s", cudaGetErrorString(cudaGetLastError()));
+    return fail(GPW_ECUDA);
+  }
+  return GPW_OK;
+}
+
+// Discrete logs (all bases are [k]G): A_j = [1 + j], B1_j = [2^32 + j], B2_j = [1 + j] (G2), K_i = [2^33 + i],
+// Z_j = [2^34 + j], CK_i = [2^35 + i], CKs_i = [2^36 + i]; alpha = [seed+1], beta = [seed+2], delta = [seed+3].
+// (j indexes the compacted A / B support lists, i is the wire id.)
+extern "C" int gpw_wrap_key_synthetic(gpw_ctx* ctx, gpw_circuit* circ, uint64_t seed, gpw_wrap_key** out) {
+  gpw_wrap_key* k = nullptr;
+  GPW_TRY(wrap_key_alloc(ctx, circ, &k));
+  k->seed = seed;
+  const size_t N = (size_t)1 << k->logN;
+  int rc = 0;
+  if ((rc = gpw_ec_generator_multiples_dev(ctx, 1, 1, k->nA, (uint64_t)k->A)) ||
+      (rc = gpw_ec_generator_multiples_dev(ctx, 1, 1ull << 32, k->nB, (uint64_t)k->B1)) ||
+      (rc = gpw_ec_generator_multiples_dev(ctx, 2, 1, k->nB, (uint64_t)k->B2)) ||
+      (rc = gpw_ec_generator_multiples_dev(ctx, 1, 1ull << 33, k->m, (uint64_t)k->K)) ||
+      (rc = gpw_ec_generator_multiples_dev(ctx, 1, 1ull << 34, N - 1, (uint64_t)k->Z)) ||
+      (rc = gpw_ec_generator_multiples_dev(ctx, 1, (1ull << 35) + k->limb_start, k->n_committed, (uint64_t)k->CK)) ||
+      (rc = gpw_ec_generator_multiples_dev(ctx, 1, (1ull << 36) + k->limb_start, k->n_committed, (uint64_t)k->CKs))) {
+    gpw_wrap_key_free(k);
+    return rc;
   }
   k->alpha1 = gen_mul_host<Fp>(seed + 1);
   k->beta1 = gen_mul_host<Fp>(seed + 2);
   k->delta1 = gen_mul_host<Fp>(seed + 3);
   k->beta2 = gen_mul_host<Fp2>(seed + 2);
   k->delta2 = gen_mul_host<Fp2>(seed + 3);
-  GPW_CUDA(cudaStreamSynchronize(ctx->stream));
+  GPW_TRY(wrap_key_finish(k));  // frees the key on failure
   *out = k;
   return GPW_OK;
 }
@@ -395,6 +383,22 @@ extern "C" int gpw_wrap_set_lanes(gpw_wrap_key* k, int n) {
   }
   k->want_lanes = n;
   return GPW_OK;
+}
+
+// uniform in [0, r): 254 random bits, rejection (gnark: fr.Element.SetRandom over crypto/rand)
+static int sample_fr(uint64_t out[4]) {
+  static const uint64_t RQ[4] = {0x43e1f593f0000001ull, 0x2833e84879b97091ull, 0xb85045b68181585dull, 0x30644e72e131a029ull};
+  for (;;) {
+    if (getrandom(out, 32, 0) != 32) {
+      set_error("getrandom failed");
+      return GPW_EINVAL;
+    }
+    out[3] &= 0x3fffffffffffffffull;
+    for (int i = 3; i >= 0; i--) {
+      if (out[i] < RQ[i]) return GPW_OK;
+      if (out[i] > RQ[i]) break;
+    }
+  }
 }
 
 static void ser_g1_be(const G1Affine& p, uint8_t out[64]) {
@@ -446,7 +450,7 @@ extern "C" int gpw_wrap_prove(gpw_wrap_key* k, const uint64_t* inputs, const uin
 // Same with the parsed inputs already resident on the device (n_inputs x 4 u64 canonical).
 extern "C" int gpw_wrap_prove_dev(gpw_wrap_key* k, uint64_t inputs_dev, const uint64_t* r_canon, const uint64_t* s_canon, int check,
                                   uint64_t* out_proof) {
-  if (!k || !inputs_dev || !r_canon || !s_canon || !out_proof) {
+  if (!k || !inputs_dev || !out_proof) {
     set_error("wrap_prove: null argument");
     return GPW_EINVAL;
   }
@@ -494,7 +498,10 @@ static int wrap_stage2(gpw_wrap_key* k, WrapLane* L, const uint64_t* r_canon, co
   GPW_CUDA(cudaMemsetAsync(L->vc, 0, N * sizeof(Fr), st));
   uint64_t n_bad = 0;
   int rc = gpw_r1cs_eval_on(k->circ, ctx, (uint64_t)wires, (uint64_t)L->va, (uint64_t)L->vb, (uint64_t)L->vc, &n_bad);
-  if (rc != GPW_OK && (check || rc != GPW_EUNSAT)) return rc;
+  (void)check;  // an unsatisfied system never yields a proof: with it, (A.B - C)/Z_H is not a polynomial and the output would
+                // be a well-formed but invalid proof. The count is reported in slot 52, the status is GPW_EUNSAT.
+  out_proof[52] = n_bad;
+  if (rc != GPW_OK) return rc;
   GPW_CUDA(cudaEventRecord(ev[4], st));
   GPW_TRY(gpw_groth16_compute_h_dev(ctx, (uint64_t)L->va, (uint64_t)L->vb, (uint64_t)L->vc, k->logN));
   GPW_CUDA(cudaEventRecord(ev[5], st));
@@ -545,7 +552,17 @@ static int wrap_stage2(gpw_wrap_key* k, WrapLane* L, const uint64_t* r_canon, co
   GPW_CUDA(cudaEventRecord(ev[6], st));
   GPW_CUDA(cudaStreamSynchronize(st));
   for (int i = 0; i < 6; i++) GPW_CUDA(cudaEventElapsedTime(&L->t_ms[i], ev[i], ev[i + 1]));
-  // assembly (gnark groth16.Prove)
+  // assembly (gnark groth16.Prove). r, s: the caller's (reproducible proofs, tests) or, as gnark does,
+  // fresh from the OS CSPRNG when NULL.
+  uint64_t r_own[4], s_own[4];
+  if (!r_canon) {
+    GPW_TRY(sample_fr(r_own));
+    r_canon = r_own;
+  }
+  if (!s_canon) {
+    GPW_TRY(sample_fr(s_own));
+    s_canon = s_own;
+  }
   uint32_t rw[8], sw[8];
   memcpy(rw, r_canon, 32);
   memcpy(sw, s_canon, 32);
@@ -597,7 +614,7 @@ extern "C" int gpw_wrap_last_stats(const gpw_wrap_key* k, float* ms6) {
 // inputs: n x n_inputs x 4 u64 canonical (host or device memory); r, s: n x 4 u64 each (host); out: n x 64 u64 (host).
 extern "C" int gpw_wrap_prove_many(gpw_wrap_key* k, const uint64_t* inputs, int n, const uint64_t* r_canon, const uint64_t* s_canon,
                                    int check, uint64_t* out_proofs) {
-  if (!k || !inputs || n < 1 || !r_canon || !s_canon || !out_proofs) {
+  if (!k || !inputs || n < 1 || !out_proofs) {
     set_error("wrap_prove_many: bad argument");
     return GPW_EINVAL;
   }
@@ -623,7 +640,8 @@ extern "C" int gpw_wrap_prove_many(gpw_wrap_key* k, const uint64_t* inputs, int 
         set_error("wrap_prove_many: input copy failed: %s", cudaGetErrorString(cudaGetLastError()));
         rc = GPW_ECUDA;
       }
-      if (rc == GPW_OK) rc = wrap_one(k, L, (uint64_t)L->inputs_dev, r_canon + 4 * i, s_canon + 4 * i, check, out_proofs + 64 * (size_t)i);
+      if (rc == GPW_OK) rc = wrap_one(k, L, (uint64_t)L->inputs_dev, r_canon ? r_canon + 4 * i : nullptr, s_canon ? s_canon + 4 * i : nullptr, check,
+                                     out_proofs + 64 * (size_t)i);
       if (rc == GPW_OK && getenv("GPW_DEBUG_LANES"))
         fprintf(stderr, "[gpw lanes] proof %2d: solve1 %6.1f | commit %5.1f solve2 %5.1f r1cs %5.1f H %5.1f msm %6.1f ms\n", i, L->t_ms[0],
                 L->t_ms[1], L->t_ms[2], L->t_ms[3], L->t_ms[4], L->t_ms[5]);

@@ -26,6 +26,11 @@ _NEW = {
     "gpw_circuit_hint_wires": (C.c_int, [_vp, C.c_int, _vp, C.c_size_t, C.POINTER(C.c_size_t)]),
     "gpw_wrap_key_synthetic": (C.c_int, [_vp, _vp, C.c_uint64, C.POINTER(_vp)]),
     "gpw_wrap_key_free": (None, [_vp]),
+    "gpw_wrap_key_setup": (C.c_int, [_vp, _vp, C.c_char_p, C.POINTER(_vp)]),
+    "gpw_wrap_key_save": (C.c_int, [_vp, C.c_char_p, C.c_char_p]),
+    "gpw_wrap_key_load": (C.c_int, [_vp, _vp, C.c_char_p, C.c_char_p, C.POINTER(_vp)]),
+    "gpw_wrap_key_vk_write_raw": (C.c_int, [_vp, _vp, C.c_size_t, C.POINTER(C.c_size_t)]),
+    "gpw_wrap_proof_write_raw": (C.c_int, [_vp, _vp, _vp, C.c_size_t, C.POINTER(C.c_size_t)]),
     "gpw_wrap_key_info": (C.c_int, [_vp, _vp]),
     "gpw_wrap_key_wires_dev": (C.c_uint64, [_vp]),
     "gpw_wrap_key_h_dev": (C.c_uint64, [_vp]),
@@ -129,13 +134,50 @@ class Circuit:
 class WrapKey:
     KEY_INFO = "m n_pub n_cons logN nA nB n_committed limb_start".split()
 
-    def __init__(self, ctx, circuit, seed=0x5EED):
-        h = _vp()
-        _check(_lib.gpw_wrap_key_synthetic(ctx._h, circuit._h, seed, C.byref(h)))
+    def __init__(self, ctx, circuit, seed=0x5EED, _handle=None):
+        """groth16.DummySetup analogue (synthetic bases with known discrete logs). Real keys: WrapKey.setup / WrapKey.load."""
+        h = _handle
+        if h is None:
+            h = _vp()
+            _check(_lib.gpw_wrap_key_synthetic(ctx._h, circuit._h, seed, C.byref(h)))
         self._h, self.ctx, self.circuit, self.seed = h, ctx, circuit, seed
         a = np.zeros(8, dtype=np.uint64)
         _check(_lib.gpw_wrap_key_info(self._h, _p(a)))
         self.info = dict(zip(self.KEY_INFO, map(int, a)))
+
+    @classmethod
+    def setup(cls, ctx, circuit, seed32=None):
+        """groth16.Setup (benchmark.go:217). seed32: 32 bytes (reproducible toxic waste, tests) or None (OS entropy)."""
+        assert seed32 is None or len(seed32) == 32
+        h = _vp()
+        _check(_lib.gpw_wrap_key_setup(ctx._h, circuit._h, seed32, C.byref(h)))
+        return cls(ctx, circuit, None, _handle=h)
+
+    @classmethod
+    def load(cls, ctx, circuit, pk_path, vk_path=None):
+        h = _vp()
+        _check(_lib.gpw_wrap_key_load(ctx._h, circuit._h, pk_path.encode(), vk_path.encode() if vk_path else None, C.byref(h)))
+        return cls(ctx, circuit, None, _handle=h)
+
+    def save(self, pk_path, vk_path=None):
+        _check(_lib.gpw_wrap_key_save(self._h, pk_path.encode(), vk_path.encode() if vk_path else None))
+
+    def vk_raw(self) -> bytes:
+        """vk.WriteRawTo bytes"""
+        n = C.c_size_t()
+        _check(_lib.gpw_wrap_key_vk_write_raw(self._h, None, 0, C.byref(n)))
+        buf = np.zeros(n.value, dtype=np.uint8)
+        _check(_lib.gpw_wrap_key_vk_write_raw(self._h, _p(buf), buf.size, C.byref(n)))
+        return buf.tobytes()
+
+    def proof_raw(self, proof) -> bytes:
+        """proof.WriteRawTo bytes of a proof dict returned by prove*()"""
+        raw = np.ascontiguousarray(proof["raw"] if isinstance(proof, dict) else proof, dtype=np.uint64)
+        n = C.c_size_t()
+        _check(_lib.gpw_wrap_proof_write_raw(self._h, _p(raw), None, 0, C.byref(n)))
+        buf = np.zeros(n.value, dtype=np.uint8)
+        _check(_lib.gpw_wrap_proof_write_raw(self._h, _p(raw), _p(buf), buf.size, C.byref(n)))
+        return buf.tobytes()
 
     def close(self):
         if self._h:
@@ -151,13 +193,13 @@ class WrapKey:
         """device address of the quotient coefficients h (N - 1 Fr, Montgomery) of the last prove()"""
         return int(_lib.gpw_wrap_key_h_dev(self._h))
 
-    def prove(self, inputs, r_int, s_int, check=True):
+    def prove(self, inputs, r_int=None, s_int=None, check=True):
         """inputs: (n_inputs, 4) u64 canonical, host. -> dict with Ar, Bs, Krs, commitment, pok (affine Montgomery limbs),
         challenge (int), n_unsatisfied"""
         inputs = np.ascontiguousarray(inputs, dtype=np.uint64)
         assert inputs.shape == (self.circuit.n_inputs, 4)
-        r = ints_to_limbs([r_int])[0]
-        s = ints_to_limbs([s_int])[0]
+        r = ints_to_limbs([r_int])[0] if r_int is not None else None     # None: sampled inside libgpw (CSPRNG)
+        s = ints_to_limbs([s_int])[0] if s_int is not None else None
         out = np.zeros(64, dtype=np.uint64)
         _check(_lib.gpw_wrap_prove(self._h, _p(inputs), _p(r), _p(s), int(check), _p(out)))
         return {"Ar": out[0:8].copy(), "Bs": out[8:24].copy(), "Krs": out[24:32].copy(), "commitment": out[32:40].copy(),
@@ -185,10 +227,10 @@ class WrapKey:
         """proofs gpw_wrap_prove_many keeps in flight (one host thread + stream + scratch each)"""
         _check(_lib.gpw_wrap_set_lanes(self._h, int(n)))
 
-    def prove_many(self, inputs_ptr, n, r_ints, s_ints, check=True):
+    def prove_many(self, inputs_ptr, n, r_ints=None, s_ints=None, check=True):
         """n independent proofs, several in flight (gpw_wrap_prove_many). inputs_ptr: host address of n x n_inputs x 4 u64."""
-        r = ints_to_limbs(list(r_ints))
-        s = ints_to_limbs(list(s_ints))
+        r = ints_to_limbs(list(r_ints)) if r_ints is not None else None
+        s = ints_to_limbs(list(s_ints)) if s_ints is not None else None
         out = np.zeros((n, 64), dtype=np.uint64)
         _check(_lib.gpw_wrap_prove_many(self._h, _vp(inputs_ptr), n, _p(r), _p(s), int(check), _p(out)))
         return [self._unpack(out[i]) for i in range(n)]

@@ -184,9 +184,30 @@ typedef struct gpw_wrap_key gpw_wrap_key;
 int gpw_wrap_key_synthetic(gpw_ctx* ctx, gpw_circuit* circ, uint64_t seed, gpw_wrap_key** out);
 void gpw_wrap_key_free(gpw_wrap_key* k);
 int gpw_wrap_key_info(const gpw_wrap_key* k, uint64_t* info8);
+/* groth16.Setup(r1cs) (benchmark.go:217): a REAL key for the compiled circuit - toxic waste tau, alpha, beta, gamma, delta
+ * (+ the Pedersen key of the range-check commitment), QAP polynomials at tau from the R1CS, every base a multiple of the
+ * generators (csrc/setup.cu). seed32: 32 bytes the toxic waste is derived from (reproducible keys for tests); NULL = fresh
+ * OS entropy. Proofs made with such a key satisfy gnark's Groth16 verification equation (oracle/pairing.py checks it). */
+int gpw_wrap_key_setup(gpw_ctx* ctx, gpw_circuit* circ, const uint8_t* seed32, gpw_wrap_key** out);
+/* pk.WriteRawTo + vk.WriteRawTo (benchmark.go:224-232) in gnark's field order with uncompressed big-endian points, and the
+ * inverse. The file describes THIS library's R1CS of the circuit (own wire numbering); shapes are checked on load.
+ * vk_path may be NULL.                                                                                              */
+int gpw_wrap_key_save(const gpw_wrap_key* k, const char* pk_path, const char* vk_path);
+int gpw_wrap_key_load(gpw_ctx* ctx, gpw_circuit* circ, const char* pk_path, const char* vk_path, gpw_wrap_key** out);
+/* vk.WriteRawTo into a caller buffer: alpha1 | beta1 | beta2 | gamma2 | delta1 | delta2 | u32 len(K) | K | u32 n_commitments |
+ * per commitment u32 n + n x u64 | Pedersen vk (G | GRootSigmaNeg). out == NULL: only *len is set.                  */
+int gpw_wrap_key_vk_write_raw(const gpw_wrap_key* k, uint8_t* out, size_t cap, size_t* len);
+/* proof.WriteRawTo (benchmark.go:272-274): the 64-word proof of gpw_wrap_prove* as gnark's raw proof bytes
+ * Ar (64) | Bs (128: X.A1 X.A0 Y.A1 Y.A0) | Krs (64) | u32 n_commitments | commitments | CommitmentPok (64), big-endian
+ * canonical coordinates - benchmark.go:283-290 reads a, b, c from the first 256 bytes. out == NULL: only *len is set. */
+int gpw_wrap_proof_write_raw(const gpw_wrap_key* k, const uint64_t* proof64, uint8_t* out, size_t cap, size_t* len);
 uint64_t gpw_wrap_key_wires_dev(const gpw_wrap_key* k);
 /* device address of the quotient coefficients h_0 .. h_{N-2} (Fr, Montgomery) left by the last gpw_wrap_prove (test aid) */
 uint64_t gpw_wrap_key_h_dev(const gpw_wrap_key* k);
+/* r_canonical / s_canonical: the prover's blinding scalars. NULL (the production path) = drawn from the OS CSPRNG inside
+ * the library for every proof, as gnark's Prove does (crypto/rand); non-NULL = caller-supplied, for reproducible proofs in
+ * tests. An unsatisfied constraint system never yields a proof: the call returns GPW_EUNSAT (count in slot 52) whatever
+ * `check` is.                                                                                                        */
 int gpw_wrap_prove(gpw_wrap_key* k, const uint64_t* inputs, const uint64_t* r_canonical, const uint64_t* s_canonical, int check,
                    uint64_t* out_proof);
 /* same, with the parsed inputs already resident on the device (n_inputs x 4 u64 canonical) */
