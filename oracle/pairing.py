@@ -11,7 +11,7 @@ vectors, so this file is pinned by mathematics, and the tests say so
     (tests/test_oracle_pairing.py) - any such map decides the verification equations below identically;
   * the equation checked is the published one (Groth16, EUROCRYPT 2016, with gnark's commitment extension):
         e(Ar, Bs) = e(alpha, beta) . e(sum_i x_i K_i + D, gamma) . e(Krs, delta)
-        e(D, GRootSigmaNeg) . e(PoK, G) = 1                         (Pedersen proof of knowledge)
+        e(D, G) . e(PoK, GRootSigmaNeg) = 1      (Pedersen proof of knowledge: PoK = sigma D, GRootSigmaNeg = -G/sigma)
     where the public vector x is (1, public inputs..., challenge) and challenge = hash_to_field(D).
 
 Construction (deliberately the plainest one): Fp12 = Fp2[w]/(w^6 - xi), xi = 9 + u, as six Fp2 coefficients with
@@ -210,7 +210,7 @@ def groth16_verify(vk, proof, public_inputs):
         ped = vk["pedersen"]
         if len(commitments) != 1:
             return False, "batched proofs of knowledge are not restated here"
-        if not pairing_product_is_one([(commitments[0], ped["g_root_sigma_neg"]), (proof["pok"], ped["g"])]):
+        if not pairing_product_is_one([(commitments[0], ped["g"]), (proof["pok"], ped["g_root_sigma_neg"])]):
             return False, "commitment proof of knowledge fails"
     ok = pairing_product_is_one([(proof["Ar"], proof["Bs"]), (ec_neg(1, vk["alpha1"]), vk["beta2"]),
                                  (ec_neg(1, ksum), vk["gamma2"]), (ec_neg(1, proof["Krs"]), vk["delta2"])])
