@@ -9,8 +9,8 @@ One "step" = one complete wrap of the real testdata/step Plonky2 proof (BASELINE
   parsed proof inputs -> witness synthesis on the GPU (449 k reference hints, 5.6 M constraints, 7.67 M wires) ->
   range-check commitment (2 MSMs) -> log-derivative argument -> R1CS evaluation -> computeH (7 NTTs of 2^23) ->
   MSM G1 {A, B1, K, Z} + MSM G2 {B2} -> Groth16 proof (Ar, Bs, Krs) + commitment + PoK on the host.
-Compile (frontend.Compile) and setup (groth16.DummySetup) are one-off per circuit and outside the timed region, as
-in BASELINE.md 5. Prints ONE JSON line (rank 0). See DESIGN.md "Measurement".
+Compile (frontend.Compile) and setup (groth16.Setup; --dummy-setup for the DummySetup analogue) are one-off per circuit
+and outside the timed region, as in BASELINE.md 5. Prints ONE JSON line (rank 0). See DESIGN.md "Measurement".
 """
 import argparse
 import json
@@ -64,95 +64,112 @@ class ClockSampler(threading.Thread):
                 "sm_max_mhz": int(self.samples[0][1]) if self.samples[0][1].isdigit() else None, "reasons": reasons}
 
 
-# sizes of the compiled step circuit (printed by the GPU arm; used by the CPU arm, which cannot compile without libgpw)
+# sizes of the compiled step circuit (printed by the GPU arm; the CPU arm reports its own from cw_shape and they must agree)
 STEP_SHAPE = {"wires": 7672120, "constraints": 5597007, "logN": 23, "nA": 7075007, "nB": 3861384, "n_committed": 2528029,
-              "n_k": 5144054}
+              "n_k": 5144053}
 
 
-def cpu_baseline(threads=None):
-    """The reference-equivalent CPU path timed on this box's host cores (oracle port; the only place bench.py runs
-    oracle/ code): (1) the Python oracle replays the verifier dataflow of the real step proof = the witness solve
-    (single thread, like one gnark solver level at a time); (2) the C/OpenMP port of gnark-crypto's Pippenger MSM and
-    radix-2 FFT is timed on a bounded sample and extrapolated linearly to the circuit's real MSM / FFT sizes."""
-    import ctypes as C
-    import numpy as np
-    import gpw
-    from oracle.verifier import verify_testdata
-    so = os.path.join(ROOT, "oracle", "c", "libbn254_ref.so")
-    if not os.path.exists(so):
-        subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle", "c")], stdout=subprocess.DEVNULL)
-    lib = C.CDLL(so)
-    # torchrun exports OMP_NUM_THREADS=1: ask for the box's cores explicitly
-    nthreads = threads or max(int(lib.ref_max_threads()), os.cpu_count() or 1)
-    vp = C.c_void_p
-    lib.ref_msm_g1.argtypes = [vp, vp, C.c_size_t, C.c_int, C.c_int, C.c_int, vp]
-    lib.ref_msm_g2.argtypes = [vp, vp, C.c_size_t, C.c_int, C.c_int, C.c_int, vp]
-    lib.ref_ntt_fr.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int]
-    t0 = time.perf_counter()
-    verify_testdata(TESTDATA, trace=False)
-    t_wit = time.perf_counter() - t0
-    rng = np.random.default_rng(1)
+class CpuWrap:
+    """The reference-equivalent CPU path (oracle/c/wrap_cpu.cc + bn254_ref.c, `kind: "port"`): the WHOLE wrap proof of the
+    real fixture at full size on the host cores - level-parallel witness solve with the four Goldilocks hints, commitment
+    MSMs, R1CS evaluation + check, computeH (7 FFTs of 2^23), MSM G1 x6 + MSM G2 - nothing sampled, nothing extrapolated.
+    The only place bench.py executes oracle/ code; it never imports gpw / libgpw.so."""
 
-    def scalars(n):   # wire-value mix of the real witness: mostly 16/32/64-bit values
-        s = rng.integers(0, 1 << 62, size=(n, 4), dtype=np.uint64)
-        s[:, 3] &= np.uint64((1 << 59) - 1)
-        u = rng.random(n)
-        s[u < 0.85, 1:] = 0
-        s[u < 0.45, 0] &= np.uint64(0xffff)
-        s[u < 0.15, 0] &= np.uint64(1)
-        return s
+    def __init__(self):
+        import ctypes as C
+        so = os.path.join(ROOT, "oracle", "c", "libwrap_cpu_ref.so")
+        if not os.path.exists(so):
+            subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle", "c")], stdout=subprocess.DEVNULL)
+        self.C = C
+        lib = self.lib = C.CDLL(so)
+        lib.cw_compile.restype = C.c_void_p
+        lib.cw_compile.argtypes = [C.c_char_p]
+        lib.cw_prove.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p, C.c_int, C.c_void_p, C.c_void_p]
+        lib.cw_shape.argtypes = [C.c_void_p, C.c_void_p]
+        lib.cw_last_error.restype = C.c_char_p
+        lib.cw_free.argtypes = [C.c_void_p]
+        # torchrun exports OMP_NUM_THREADS=1: ask for the box's cores explicitly
+        self.threads = max(int(lib.ref_max_threads()), os.cpu_count() or 1)
+        rd = lambda f: open(os.path.join(TESTDATA, f), "rb").read()
+        self.proof, self.vod = rd("proof_with_public_inputs.json"), rd("verifier_only_circuit_data.json")
+        t0 = time.perf_counter()
+        self.h = lib.cw_compile(rd("common_circuit_data.json"))       # frontend.Compile: untimed, as on the GPU arm
+        if not self.h:
+            raise RuntimeError("cw_compile: " + lib.cw_last_error().decode())
+        self.compile_s = time.perf_counter() - t0
+        shape = (C.c_uint64 * 8)()
+        lib.cw_shape(self.h, shape)
+        self.shape = dict(zip(("wires", "constraints", "logN", "nA", "nB", "n_committed", "n_k", "levels"), map(int, shape)))
 
-    n1, n2, ln = 1 << 18, 1 << 16, 18
-    p1 = np.ascontiguousarray(np.tile(gpw.host_ec_generator_multiples(1, 1, 4096), (n1 // 4096, 1)))
-    p2 = np.ascontiguousarray(np.tile(gpw.host_ec_generator_multiples(2, 1, 1024), (n2 // 1024, 1)))
-    s1, s2 = scalars(n1), scalars(n2)
-    out = np.zeros(16, dtype=np.uint64)
-    t0 = time.perf_counter()
-    lib.ref_msm_g1(s1.ctypes.data, p1.ctypes.data, n1, 0, 0, nthreads, out.ctypes.data)
-    t_g1 = time.perf_counter() - t0
-    t0 = time.perf_counter()
-    lib.ref_msm_g2(s2.ctypes.data, p2.ctypes.data, n2, 0, 0, nthreads, out.ctypes.data)
-    t_g2 = time.perf_counter() - t0
-    a = scalars(1 << ln)
-    t0 = time.perf_counter()
-    lib.ref_ntt_fr(a.ctypes.data, ln, 0, 1, nthreads)
-    t_ntt = time.perf_counter() - t0
-    S = STEP_SHAPE
-    N = 1 << S["logN"]
-    g1_points = S["nA"] + S["nB"] + S["n_k"] + (N - 1) + 2 * S["n_committed"]
-    t_proof = t_wit + t_g1 * g1_points / n1 + t_g2 * S["nB"] / n2 + 7 * t_ntt * (N * S["logN"]) / ((1 << ln) * ln)
-    return {"value": 1.0 / t_proof, "unit": "proofs/s", "cores": int(nthreads), "kind": "port",
-            "sample": "witness: Python oracle replay of the step proof %.1fs (1 thread); prover: C/OpenMP port of gnark-crypto "
-                      "Pippenger+FFT on %d threads: MSM G1 n=2^18 %.2fs, MSM G2 n=2^16 %.2fs, coset NTT 2^18 %.3fs, "
-                      "witness-shaped scalars, extrapolated linearly to %d G1 points, %d G2 points, 7 NTTs of 2^%d"
-                      % (t_wit, nthreads, t_g1, t_g2, t_ntt, g1_points, S["nB"], S["logN"]),
-            "t_proof_s": t_proof}
+    def prove(self):
+        """one full proof -> (seconds, phase seconds, status)"""
+        C = self.C
+        times, status = (C.c_double * 8)(), (C.c_uint64 * 4)()
+        rc = self.lib.cw_prove(self.h, self.proof, self.vod, self.threads, times, status)
+        if rc != 0:
+            raise RuntimeError("cw_prove rc=%d: %s" % (rc, self.lib.cw_last_error().decode()))
+        if status[0] != 0 or status[1] != 1:
+            raise RuntimeError("CPU proof is wrong: %d unsatisfied rows, A MSM == known dlog: %d" % (status[0], status[1]))
+        names = ("solve_phase1_s", "commitment_s", "solve_phase2_s", "r1cs_eval_s", "compute_h_s", "msm_s")
+        return times[6], dict(zip(names, [round(x, 3) for x in times[:6]])), (int(status[2]), int(status[3]))
+
+    def describe(self, t, phases, pts, n):
+        return {"value": 1.0 / t, "unit": "proofs/s", "cores": int(self.threads), "kind": "port",
+                "sample": "%d complete wrap proof(s) of testdata/%s at full size on %d host threads (C/OpenMP port of the gnark solver "
+                          "levels + gnark-crypto Pippenger / FFT, oracle/c/wrap_cpu.cc): %d G1 + %d G2 points, 7 FFTs of 2^%d per "
+                          "proof, every row of the R1CS checked, A MSM checked against its known discrete log; mean %.2f s per "
+                          "proof, phases of the last one %s; nothing extrapolated"
+                          % (n, os.path.basename(TESTDATA), self.threads, pts[0], pts[1], self.shape["logN"], t, json.dumps(phases)),
+                "compile_s": round(self.compile_s, 1)}
 
 
-def workload_config():
+def workload_config(key_kind="real Groth16 setup (gpw_wrap_key_setup)"):
     return {"workload": "wrap_prove(testdata/%s, Groth16): parsed Plonky2 proof -> GPU witness synthesis (tape) -> range-check "
-                        "commitment -> R1CS eval -> computeH (7 NTT 2^23) -> MSM G1 x6 + MSM G2 x1 -> proof; real proof, "
-                        "synthetic proving key (DummySetup analogue)" % os.path.basename(TESTDATA),
+                        "commitment -> R1CS eval -> computeH (7 NTT 2^23) -> MSM G1 x6 + MSM G2 x1 -> proof"
+                        % os.path.basename(TESTDATA),
+            "proving_key": key_kind,
             "circuit": STEP_SHAPE, "l2_policy": "inputs_exceed_l2 (7.67 M wires + 3 x 2^23 Fr vectors + >2 GB of bases per step)",
             "witness_synthesis_in_step": True}
 
 
 def run_reference(args):
+    """--impl reference: every step is ONE complete full-size CPU proof (no sampling). A CPU proof takes tens of seconds, so
+    the run is bounded in time instead: warm-up and timed steps stop when --ref-budget-s is used up (at least two timed
+    proofs when --steps allows); `steps` / `warmup` in the line are the numbers actually run, the requested ones are recorded."""
     if int(os.environ.get("RANK", 0)) != 0:
         return
-    vals, base = [], None
-    for i in range(args.warmup + args.steps):
-        base = cpu_baseline()
-        if i >= args.warmup:
-            vals.append(base["t_proof_s"])
+    cpu = CpuWrap()
+    t_start = time.perf_counter()
+    n_warm = 0
+    for _ in range(args.warmup):
+        cpu.prove()
+        n_warm += 1
+        if time.perf_counter() - t_start > 0.2 * args.ref_budget_s:
+            break
+    vals, phases, pts = [], None, None
+    for i in range(args.steps):
+        t, phases, pts = cpu.prove()
+        vals.append(t)
+        if i >= 1 and time.perf_counter() - t_start + t > args.ref_budget_s:
+            break
     t = sum(vals) / len(vals)
-    base["value"] = 1.0 / t
-    line = {"metric": "wrap_proofs_per_sec", "value": 1.0 / t, "unit": "proofs/s", "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "u32x8-montgomery", "data": "synthetic", "impl": "reference", "config": workload_config(),
-            "cpu_baseline": {k: v for k, v in base.items() if k != "t_proof_s"},
+    base = cpu.describe(t, phases, pts, len(vals))
+    line = {"metric": "wrap_proofs_per_sec", "value": 1.0 / t, "unit": "proofs/s", "n_gpus": args.gpus, "steps": len(vals),
+            "warmup": n_warm, "steps_requested": args.steps, "warmup_requested": args.warmup, "ms_per_step": t * 1e3,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u64x4-montgomery", "data": "synthetic", "impl": "reference",
+            "config": workload_config("synthetic bases with known discrete logs (Pippenger cost is independent of base values)"),
+            "cpu_baseline": base, "cpu_shape": cpu.shape,
             "e2e": {"value": 1.0 / t, "unit": "proofs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
     print(json.dumps(line), flush=True)
+
+
+def cpu_baseline():
+    """cpu_baseline of the GPU arm's line (rank 0, N = 1): one warm-up + one timed full-size CPU proof."""
+    cpu = CpuWrap()
+    cpu.prove()
+    t, phases, pts = cpu.prove()
+    return cpu.describe(t, phases, pts, 1)
 
 
 def main():
@@ -163,6 +180,9 @@ def main():
     ap.add_argument("--lanes", type=int, default=int(os.environ.get("GPW_WRAP_LANES", "6")),
                     help="proofs in flight per GPU (gpw_wrap_set_lanes)")
     ap.add_argument("--impl", default="gpw", choices=["gpw", "reference"])
+    ap.add_argument("--ref-budget-s", type=float, default=float(os.environ.get("GPW_REF_BUDGET_S", "200")),
+                    help="--impl reference: wall-clock budget for warm-up + timed full-size CPU proofs")
+    ap.add_argument("--dummy-setup", action="store_true", help="synthetic key (groth16.DummySetup analogue) instead of the real setup")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -187,8 +207,15 @@ def main():
     ctx.set_stream(side.cuda_stream)
 
     rd = lambda f: open(os.path.join(TESTDATA, f), "rb").read()
+    t_compile = time.perf_counter()
     circ = gpw.Circuit.compile_verifier(ctx, rd("common_circuit_data.json"))           # frontend.Compile (untimed)
-    key = gpw.WrapKey(ctx, circ, seed=0x5EED + rank)                                      # DummySetup (untimed)
+    t_compile = time.perf_counter() - t_compile
+    t_setup = time.perf_counter()
+    if args.dummy_setup:
+        key = gpw.WrapKey(ctx, circ, seed=0x5EED + rank)                                  # groth16.DummySetup (untimed)
+    else:
+        key = gpw.WrapKey.setup(ctx, circ, bytes([rank]) * 32)                           # groth16.Setup (untimed)
+    t_setup = time.perf_counter() - t_setup
     inputs = circ.parse_inputs(rd("proof_with_public_inputs.json"), rd("verifier_only_circuit_data.json"))
     host_inputs = torch.from_numpy(inputs.view(np.int64)).pin_memory()
     dev_inputs = host_inputs.to(dev)
@@ -289,7 +316,9 @@ def main():
     line = {
         "metric": "wrap_proofs_per_sec", "value": value, "unit": "proofs/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "u32x8-montgomery", "data": "synthetic", "config": workload_config(),
+        "dtype": "u32x8-montgomery", "data": "synthetic",
+        "config": workload_config("synthetic (DummySetup analogue)" if args.dummy_setup else "real Groth16 setup (gpw_wrap_key_setup)"),
+        "untimed_s": {"compile": round(t_compile, 2), "setup": round(t_setup, 2)},
         "e2e": {"value": e2e_value, "unit": "proofs/s", "h2d_bytes_per_step": int(inputs.nbytes), "d2h_bytes_per_step": 512},
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
@@ -322,7 +351,7 @@ def main():
     }
     if rank == 0:
         if world == 1:
-            line["cpu_baseline"] = {k: v for k, v in cpu_baseline().items() if k != "t_proof_s"}
+            line["cpu_baseline"] = cpu_baseline()
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

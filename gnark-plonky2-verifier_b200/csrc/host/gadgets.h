@@ -386,8 +386,10 @@ class VerifierChip {
 
 // ExampleVerifierCircuit.Define (verifier/util.go:19-24) with the proof and verifier-only data as SECRET inputs
 // (the reference's own test circuits use this form, fri/fri_test.go:17-21) and PublicInputs as public inputs.
-// Allocates the inputs in ParseProofInputs order, runs Verify and Finalize.
-void DefineVerifierCircuit(fe::API* api, const CommonCircuitData& cd);
+std::vector<std::array<uint64_t, 4>> ParseVerifierOnly(const CommonCircuitData& cd, const std::string& verifier_only_json);
+// Allocates the inputs in ParseProofInputs order, runs Verify and Finalize. `baked`: leading secret-input slots that
+// become compile-time constants instead (see the definition).
+void DefineVerifierCircuit(fe::API* api, const CommonCircuitData& cd, const std::vector<std::array<uint64_t, 4>>* baked = nullptr);
 
 }  // namespace gadgets
 }  // namespace gpw

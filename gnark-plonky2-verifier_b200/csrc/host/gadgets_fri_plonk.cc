@@ -907,11 +907,31 @@ void VerifierChip::Verify(const Proof& proof, const std::vector<Variable>& pis, 
   friChip.VerifyFriProof(friChip.GetInstance(ch.PlonkZeta), friChip.ToOpenings(proof.Openings), ch.Fri, caps, proof.OpeningProof);
 }
 
-// ---- ExampleVerifierCircuit with runtime inputs ------------------------------------------------------------------------
-void DefineVerifierCircuit(fe::API* api, const CommonCircuitData& cd) {
+// verifier_only_circuit_data.json alone, in ParseProofInputs order (cap, then digest): the values baked into a bound circuit
+std::vector<std::array<uint64_t, 4>> ParseVerifierOnly(const CommonCircuitData& cd, const std::string& vo_json) {
+  json::Value vo = json::parse(vo_json);
+  std::vector<std::array<uint64_t, 4>> out;
+  const auto& cap = vo["constants_sigmas_cap"];
+  if (cap.arr.size() != (1ull << cd.Fri.Config.CapHeight)) throw std::runtime_error("cap length mismatch");
+  for (const auto& h : cap.arr) out.push_back(limbs_dec(h.str));
+  out.push_back(limbs_dec(vo["circuit_digest"].str));
+  return out;
+}
+
+// ---- ExampleVerifierCircuit (verifier/util.go:10-24) ---------------------------------------------------------------------
+// baked == nullptr: proof and verifier-only data are runtime (secret) inputs. Otherwise the first baked->size() values of
+// the secret-input order (ParseProofInputs: verifier-only data first, then the proof) are compile-time CONSTANTS, which is
+// what the reference's `gnark:"-"` tags do: 2^cap_height + 1 values = VerifierOnlyCircuitData baked (the circuit then only
+// accepts proofs of THAT inner circuit); all of them = the reference's ExampleVerifierCircuit as benchmark.go compiles it.
+void DefineVerifierCircuit(fe::API* api, const CommonCircuitData& cd, const std::vector<std::array<uint64_t, 4>>* baked) {
   std::vector<Variable> pis;
   for (uint64_t i = 0; i < cd.NumPublicInputs; i++) pis.push_back(api->PublicInput());
-  auto sec = [&]() { return api->SecretInput(); };
+  size_t slot = 0;
+  auto sec = [&]() {
+    const size_t i = slot++;
+    if (baked && i < baked->size()) return api->ConstFr(fe::fr_from_limbs((*baked)[i].data()));
+    return api->SecretInput();
+  };
   auto sec_vec = [&](size_t n) {
     std::vector<Variable> v;
     for (size_t i = 0; i < n; i++) v.push_back(sec());

@@ -614,6 +614,9 @@ struct gpw_circuit {
   double ring_hit_rate = 0;
   uint32_t n_inputs = 0;
   float solve_ms = 0;
+  // leading secret-input values compiled in as constants (gpw_circuit_compile_verifier_bound): parse_inputs checks the
+  // documents against them and leaves them out of the input vector
+  std::vector<std::array<uint64_t, 4>> baked;
 };
 
 template <class T>
@@ -912,9 +915,19 @@ extern "C" void gpw_circuit_free(gpw_circuit* c) {
   delete c;
 }
 
+extern "C" int gpw_circuit_compile_verifier_bound(gpw_ctx* ctx, const char* common_circuit_data_json, const char* verifier_only_json,
+                                                  const char* proof_json, gpw_circuit** out);
 extern "C" int gpw_circuit_compile_verifier(gpw_ctx* ctx, const char* common_circuit_data_json, gpw_circuit** out) {
-  if (!ctx || !common_circuit_data_json || !out) {
-    set_error("circuit_compile: null argument");
+  return gpw_circuit_compile_verifier_bound(ctx, common_circuit_data_json, nullptr, nullptr, out);
+}
+
+// verifier_only_json != NULL: VerifierOnlyCircuitData (constants_sigmas_cap, circuit_digest) are compile-time constants, as
+// the reference's `gnark:"-"` tag makes them (verifier/util.go:13) - the compiled circuit then accepts only proofs of that
+// inner circuit. proof_json != NULL as well: the proof itself is baked in too, which is literally benchmark.go:33-55.
+extern "C" int gpw_circuit_compile_verifier_bound(gpw_ctx* ctx, const char* common_circuit_data_json, const char* verifier_only_json,
+                                                  const char* proof_json, gpw_circuit** out) {
+  if (!ctx || !common_circuit_data_json || !out || (proof_json && !verifier_only_json)) {
+    set_error("circuit_compile: null argument (a baked proof needs the verifier-only data too)");
     return GPW_EINVAL;
   }
   GPW_CUDA(cudaSetDevice(ctx->device));
@@ -922,7 +935,9 @@ extern "C" int gpw_circuit_compile_verifier(gpw_ctx* ctx, const char* common_cir
   c->ctx = ctx;
   try {
     c->cd = gadgets::ReadCommonCircuitData(common_circuit_data_json);
-    gadgets::DefineVerifierCircuit(&c->api, c->cd);
+    if (proof_json) c->baked = gadgets::ParseProofInputs(c->cd, proof_json, verifier_only_json).sec;
+    else if (verifier_only_json) c->baked = gadgets::ParseVerifierOnly(c->cd, verifier_only_json);
+    gadgets::DefineVerifierCircuit(&c->api, c->cd, c->baked.empty() ? nullptr : &c->baked);
     c->is_verifier = true;
   } catch (const std::exception& e) {
     set_error("circuit_compile: %s", e.what());
@@ -1171,6 +1186,15 @@ extern "C" int gpw_circuit_parse_inputs(const gpw_circuit* c, const char* proof_
   }
   try {
     gadgets::InputValues iv = gadgets::ParseProofInputs(c->cd, proof_with_public_inputs_json, verifier_only_circuit_data_json);
+    if (!c->baked.empty()) {
+      // a bound circuit: the baked values must be the documents' (else this proof belongs to another inner circuit / is
+      // another proof than the one compiled in) and are not inputs
+      if (iv.sec.size() < c->baked.size() || !std::equal(c->baked.begin(), c->baked.end(), iv.sec.begin())) {
+        set_error("parse_inputs: the documents do not match the values this circuit was compiled with (verifier-only data / proof)");
+        return GPW_EINVAL;
+      }
+      iv.sec.erase(iv.sec.begin(), iv.sec.begin() + c->baked.size());
+    }
     if (iv.pub.size() != c->api.NumPublic() || iv.sec.size() != c->api.NumSecret()) {
       set_error("parse_inputs: proof shape does not match the compiled circuit");
       return GPW_EINVAL;

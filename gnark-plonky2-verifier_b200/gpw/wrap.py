@@ -15,6 +15,7 @@ from . import _lib, _check, _p, _vp, ints_to_limbs, SYMBOLS
 
 _NEW = {
     "gpw_circuit_compile_verifier": (C.c_int, [_vp, C.c_char_p, C.POINTER(_vp)]),
+    "gpw_circuit_compile_verifier_bound": (C.c_int, [_vp, C.c_char_p, C.c_char_p, C.c_char_p, C.POINTER(_vp)]),
     "gpw_circuit_compile_gadget": (C.c_int, [_vp, C.c_char_p, C.POINTER(_vp)]),
     "gpw_circuit_free": (None, [_vp]),
     "gpw_circuit_info": (C.c_int, [_vp, _vp]),
@@ -73,11 +74,13 @@ class Circuit:
         self.n_wires = self.info["wires"]
 
     @classmethod
-    def compile_verifier(cls, ctx, common_circuit_data_json):
-        if isinstance(common_circuit_data_json, str):
-            common_circuit_data_json = common_circuit_data_json.encode()
+    def compile_verifier(cls, ctx, common_circuit_data_json, verifier_only_json=None, proof_json=None):
+        """verifier_only_json: bake VerifierOnlyCircuitData in as constants (the reference's form; binds the statement to
+        one inner circuit). proof_json: bake the proof in too (benchmark.go's ExampleVerifierCircuit)."""
+        enc = lambda x: x.encode() if isinstance(x, str) else x
         h = _vp()
-        _check(_lib.gpw_circuit_compile_verifier(ctx._h, common_circuit_data_json, C.byref(h)))
+        _check(_lib.gpw_circuit_compile_verifier_bound(ctx._h, enc(common_circuit_data_json), enc(verifier_only_json),
+                                                       enc(proof_json), C.byref(h)))
         return cls(ctx, h)
 
     @classmethod

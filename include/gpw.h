@@ -145,6 +145,14 @@ int gpw_groth16_last_stats(const gpw_pk* pk, float* h_ms, float* msm_ms5);
  * (secret) inputs as in the reference's own test circuits (fri/fri_test.go:17-21), PublicInputs are public.  */
 typedef struct gpw_circuit gpw_circuit;
 int gpw_circuit_compile_verifier(gpw_ctx* ctx, const char* common_circuit_data_json, gpw_circuit** out);
+/* The reference's own forms of ExampleVerifierCircuit (verifier/util.go:10-24, `gnark:"-"` = compile-time constant):
+ *   verifier_only_json != NULL: constants_sigmas_cap + circuit_digest are CONSTANTS of the circuit - the statement proven is
+ *     "a proof of THIS inner circuit verifies for these public inputs" (the runtime-input form above proves it for whatever
+ *     verifier data the prover supplies, so a key made from it must only be used where that is intended);
+ *   proof_json != NULL too: the proof is baked in as well - literally what benchmark.go:33-55 compiles.
+ * gpw_circuit_parse_inputs on such a circuit checks the documents against the baked values and omits them.          */
+int gpw_circuit_compile_verifier_bound(gpw_ctx* ctx, const char* common_circuit_data_json, const char* verifier_only_json,
+                                       const char* proof_json, gpw_circuit** out);
 /* Stand-alone gadget circuits shaped like the reference's unit-test circuits: "poseidon_gl", "poseidon_bn254",
  * "qe_mul_div", "range_check" (poseidon/goldilocks_test.go, poseidon/bn254_test.go, goldilocks/*_test.go).       */
 int gpw_circuit_compile_gadget(gpw_ctx* ctx, const char* name, gpw_circuit** out);

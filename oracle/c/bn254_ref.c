@@ -218,10 +218,40 @@ int ref_ntt_fr(uint64_t* data, int logn, int inverse, int coset, int nthreads) {
   }
   fe_pow(&w, &g, e, &FR);
   if (inverse) fe_inv(&w, &w, &FR);
-  fe* tw = (fe*)malloc((n / 2 + 1) * sizeof(fe));
-  if (!tw) return -2;
-  tw[0] = FR.one;
-  for (size_t i = 1; i < n / 2; i++) fe_mul(&tw[i], &tw[i - 1], &w, &FR);
+  /* twiddles, compacted per stage so that every stage reads them with stride 1: stage s uses w^(j << s), j < n >> (s+1),
+   * stored at ctw + (n - (n >> s)). Cached per (logn, direction): gnark-crypto's fft.Domain precomputes them once too. */
+  static fe* tw_cache[29][2];
+  fe* ctw;
+#pragma omp critical(ref_ntt_tw)
+  {
+    ctw = tw_cache[logn][inverse ? 1 : 0];
+    if (!ctw && n > 1) {
+      ctw = (fe*)malloc(n * sizeof(fe));
+      if (ctw) {
+        fe* tw = ctw; /* stage 0 = the plain table w^j, j < n/2 */
+        int nt = omp_get_max_threads();
+#pragma omp parallel for schedule(static) num_threads(nt)
+        for (int t = 0; t < nt; t++) {
+          size_t lo = (n / 2) * t / nt, hi = (n / 2) * (t + 1) / nt;
+          uint64_t ee[4] = {lo, 0, 0, 0};
+          fe cur;
+          fe_pow(&cur, &w, ee, &FR);
+          for (size_t j = lo; j < hi; j++) {
+            tw[j] = cur;
+            fe_mul(&cur, &cur, &w, &FR);
+          }
+        }
+        for (int st = 1; st < logn; st++) {
+          fe* dst = ctw + (n - (n >> st));
+          size_t half = n >> (st + 1);
+#pragma omp parallel for schedule(static)
+          for (size_t j = 0; j < half; j++) dst[j] = tw[j << st];
+        }
+        tw_cache[logn][inverse ? 1 : 0] = ctw;
+      }
+    }
+  }
+  if (!ctw && n > 1) return -2;
   if (!inverse && coset) {
     /* a_j *= g^j : per-thread chunks seeded by one exponentiation each */
 #pragma omp parallel
@@ -237,8 +267,13 @@ int ref_ntt_fr(uint64_t* data, int logn, int inverse, int coset, int nthreads) {
       }
     }
   }
-  for (int s = 0; s < logn; s++) {
+  /* DIF stages. The first stages (butterfly span > one cache block) sweep the whole vector; once the span fits a
+   * 2^14-element block (512 KB), every block finishes ALL its remaining stages while it is cache resident. */
+  const int BLK_LOG = 14;
+  int s_split = logn > BLK_LOG ? logn - BLK_LOG : 0;
+  for (int s = 0; s < s_split; s++) {
     size_t half = n >> (s + 1);
+    const fe* stw = ctw + (n - (n >> s));
 #pragma omp parallel for schedule(static)
     for (size_t bf = 0; bf < n / 2; bf++) {
       size_t blk = bf / half, j = bf % half;
@@ -246,7 +281,25 @@ int ref_ntt_fr(uint64_t* data, int logn, int inverse, int coset, int nthreads) {
       fe u = a[i0], v = a[i1], d;
       fe_add(&a[i0], &u, &v, &FR);
       fe_sub(&d, &u, &v, &FR);
-      fe_mul(&a[i1], &d, &tw[j << s], &FR);
+      fe_mul(&a[i1], &d, &stw[j], &FR);
+    }
+  }
+  {
+    size_t bsz = n >> s_split; /* block size */
+#pragma omp parallel for schedule(static)
+    for (size_t b0 = 0; b0 < n; b0 += bsz) {
+      for (int s = s_split; s < logn; s++) {
+        size_t half = n >> (s + 1);
+        const fe* stw = ctw + (n - (n >> s));
+        for (size_t g = b0; g < b0 + bsz; g += 2 * half)
+          for (size_t j = 0; j < half; j++) {
+            size_t i0 = g + j, i1 = i0 + half;
+            fe u = a[i0], v = a[i1], d;
+            fe_add(&a[i0], &u, &v, &FR);
+            fe_sub(&d, &u, &v, &FR);
+            fe_mul(&a[i1], &d, &stw[j], &FR);
+          }
+      }
     }
   }
 #pragma omp parallel for schedule(static)
@@ -280,7 +333,6 @@ int ref_ntt_fr(uint64_t* data, int logn, int inverse, int coset, int nthreads) {
       }
     }
   }
-  free(tw);
   return 0;
 }
 
@@ -289,3 +341,70 @@ void ref_fr_mul(const uint64_t* a, const uint64_t* b, uint64_t* o, size_t n) {
   for (size_t i = 0; i < n; i++) fe_mul((fe*)(o + 4 * i), (const fe*)(a + 4 * i), (const fe*)(b + 4 * i), &FR);
 }
 int ref_max_threads(void) { return omp_get_max_threads(); }
+
+/* ---- helpers for the full-size CPU run (oracle/c/wrap_cpu.cc) and the tests ---- */
+static const g1_aff G1_GEN = {{{0xd35d438dc58f0d9dull, 0x0a78eb28f5c70b3dull, 0x666ea36f7879462cull, 0x0e0a77c19a07df2full}},   /* 1 */
+                              {{0xa6ba871b8b1e1b3aull, 0x14f1d651eb8e167bull, 0xccdd46def0f28c58ull, 0x1c14ef83340fbe5eull}}};  /* 2 */
+
+/* out[i] = [k0 + i] base  (affine, Montgomery), n points, by repeated addition + one inversion each (setup-only) */
+void ref_g1_multiples(const uint64_t* base_or_null, uint64_t k0, size_t n, uint64_t* out) {
+  g1_aff b = base_or_null ? *(const g1_aff*)base_or_null : G1_GEN;
+  g1_xyzz cur;
+  g1_set_inf(&cur);
+  for (int bit = 63; bit >= 0; bit--) {
+    g1_dbl(&cur, &cur);
+    if ((k0 >> bit) & 1) g1_madd(&cur, &b, 0);
+  }
+  for (size_t i = 0; i < n; i++) {
+    g1_to_affine((g1_aff*)(out + 8 * i), &cur);
+    g1_madd(&cur, &b, 0);
+  }
+}
+void ref_g2_multiples(const uint64_t* base, uint64_t k0, size_t n, uint64_t* out) {
+  g2_aff b = *(const g2_aff*)base;
+  g2_xyzz cur;
+  g2_set_inf(&cur);
+  for (int bit = 63; bit >= 0; bit--) {
+    g2_dbl(&cur, &cur);
+    if ((k0 >> bit) & 1) g2_madd(&cur, &b, 0);
+  }
+  for (size_t i = 0; i < n; i++) {
+    g2_to_affine((g2_aff*)(out + 16 * i), &cur);
+    g2_madd(&cur, &b, 0);
+  }
+}
+/* out = [k] P, k canonical 256-bit (double-and-add) */
+void ref_g1_scalar_mul(const uint64_t* point, const uint64_t* k, uint64_t* out) {
+  g1_xyzz acc;
+  g1_set_inf(&acc);
+  for (int w = 3; w >= 0; w--)
+    for (int bit = 63; bit >= 0; bit--) {
+      g1_dbl(&acc, &acc);
+      if ((k[w] >> bit) & 1) g1_madd(&acc, (const g1_aff*)point, 0);
+    }
+  g1_to_affine((g1_aff*)out, &acc);
+}
+void ref_g2_scalar_mul(const uint64_t* point, const uint64_t* k, uint64_t* out) {
+  g2_xyzz acc;
+  g2_set_inf(&acc);
+  for (int w = 3; w >= 0; w--)
+    for (int bit = 63; bit >= 0; bit--) {
+      g2_dbl(&acc, &acc);
+      if ((k[w] >> bit) & 1) g2_madd(&acc, (const g2_aff*)point, 0);
+    }
+  g2_to_affine((g2_aff*)out, &acc);
+}
+/* Fr: o = a + b, o = a - b (Montgomery or canonical alike), o = to/from Montgomery */
+void ref_fr_add(const uint64_t* a, const uint64_t* b, uint64_t* o) { fe_add((fe*)o, (const fe*)a, (const fe*)b, &FR); }
+void ref_fr_to_mont(const uint64_t* a, uint64_t* o, size_t n) {
+  for (size_t i = 0; i < n; i++) fe_mul((fe*)(o + 4 * i), (const fe*)(a + 4 * i), &FR.r2, &FR);
+}
+void ref_fr_from_mont(const uint64_t* a, uint64_t* o, size_t n) {
+  for (size_t i = 0; i < n; i++) fe_from_mont((fe*)(o + 4 * i), (const fe*)(a + 4 * i), &FR);
+}
+void ref_fp_to_mont(const uint64_t* a, uint64_t* o, size_t n) {
+  for (size_t i = 0; i < n; i++) fe_mul((fe*)(o + 4 * i), (const fe*)(a + 4 * i), &FP.r2, &FP);
+}
+void ref_fp_from_mont(const uint64_t* a, uint64_t* o, size_t n) {
+  for (size_t i = 0; i < n; i++) fe_from_mont((fe*)(o + 4 * i), (const fe*)(a + 4 * i), &FP);
+}

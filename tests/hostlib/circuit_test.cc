@@ -24,6 +24,7 @@ struct Circuit {
   gadgets::CommonCircuitData cd;
   std::vector<Fr> w;
   std::string err;
+  size_t n_baked = 0;
 };
 
 static thread_local std::string g_err;
@@ -54,6 +55,22 @@ void* ct_compile(const char* common_json) {
     Circuit* c = new Circuit();
     c->cd = gadgets::ReadCommonCircuitData(common_json);
     gadgets::DefineVerifierCircuit(&c->api, c->cd);
+    return c;
+  } catch (const std::exception& e) {
+    g_err = e.what();
+    return nullptr;
+  }
+}
+
+// bound / baked circuit forms (verifier/util.go:10-24): mode 1 = verifier-only data constant, 2 = proof constant too
+void* ct_compile_baked(const char* common_json, const char* proof_json, const char* vo_json, int mode) {
+  try {
+    Circuit* c = new Circuit();
+    c->cd = gadgets::ReadCommonCircuitData(common_json);
+    std::vector<std::array<uint64_t, 4>> baked =
+        mode == 2 ? gadgets::ParseProofInputs(c->cd, proof_json, vo_json).sec : gadgets::ParseVerifierOnly(c->cd, vo_json);
+    c->n_baked = baked.size();
+    gadgets::DefineVerifierCircuit(&c->api, c->cd, &baked);
     return c;
   } catch (const std::exception& e) {
     g_err = e.what();
@@ -352,6 +369,7 @@ int ct_solve_testdata(void* h, const char* proof_json, const char* vo_json, cons
   Circuit* c = (Circuit*)h;
   try {
     gadgets::InputValues iv = gadgets::ParseProofInputs(c->cd, proof_json, vo_json);
+    iv.sec.erase(iv.sec.begin(), iv.sec.begin() + c->n_baked);
     return ct_solve_inputs(h, (const uint64_t*)iv.pub.data(), iv.pub.size(), (const uint64_t*)iv.sec.data(), iv.sec.size(), x_commit);
   } catch (const std::exception& e) {
     g_err = e.what();

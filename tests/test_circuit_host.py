@@ -189,3 +189,23 @@ def test_full_verifier_circuit_on_step(lib, testdata_dir):
     rc = lib.ct_solve_testdata(h, json.dumps(p).encode(), rd("verifier_only_circuit_data.json"), x.ctypes.data)
     assert rc == 0 and lib.ct_check(h, C.byref(fb)) > 0
     lib.ct_free(h)
+
+
+def test_baked_circuit_form_on_decode_block(lib, testdata_dir):
+    # verifier/util.go:10-24 as benchmark.go compiles it: proof + verifier-only data are compile-time constants. Same hint
+    # counts as the runtime-input form, no secret inputs left, every constraint satisfied. (Form 1 - only the verifier data
+    # baked - is exercised on the GPU, tests/test_gpu_setup_verify.py.)
+    d = os.path.join(testdata_dir, "decode_block")
+    rd = lambda f: open(os.path.join(d, f), "rb").read()
+    lib.ct_compile_baked.restype = C.c_void_p
+    lib.ct_compile_baked.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p, C.c_int]
+    h = lib.ct_compile_baked(rd("common_circuit_data.json"), rd("proof_with_public_inputs.json"), rd("verifier_only_circuit_data.json"), 2)
+    assert h, lib.ct_last_error()
+    st = stats(lib, h)
+    assert st["secret"] == 0 and st["muladd"] > 40000 and st["reduce"] > 140000
+    x = gpw.ints_to_limbs([0x1234567890abcdef1234567890abcdef])
+    rc = lib.ct_solve_testdata(h, rd("proof_with_public_inputs.json"), rd("verifier_only_circuit_data.json"), x.ctypes.data)
+    assert rc == 0, lib.ct_last_error()
+    fb = C.c_int64()
+    assert lib.ct_check(h, C.byref(fb)) == 0, "first unsatisfied constraint: %d" % fb.value
+    lib.ct_free(h)

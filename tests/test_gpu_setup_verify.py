@@ -123,3 +123,39 @@ def test_wrap_proof_of_reference_fixture_verifies(ctx, testdata_dir, name):
         assert _verify(key, p, public)[0][0]
     key.close()
     circ.close()
+
+
+def test_bound_and_baked_circuit_forms(ctx, testdata_dir):
+    # verifier/util.go:10-24: Proof and VerifierOnlyCircuitData are `gnark:"-"` (compile-time constants) in the reference.
+    # Form 1 bakes the verifier-only data (statement bound to one inner circuit), form 2 the proof too (benchmark.go:33-55).
+    # Both produce the same 449 k reference hints and proofs that verify; documents of another circuit / proof are refused.
+    import json
+    d = os.path.join(testdata_dir, "decode_block")
+    rd = lambda f: open(os.path.join(d, f), "rb").read()
+    common, proof_json, vod = rd("common_circuit_data.json"), rd("proof_with_public_inputs.json"), rd("verifier_only_circuit_data.json")
+    free = gpw.Circuit.compile_verifier(ctx, common)
+    counts = {k: free.info[k] for k in ("muladd", "reduce", "inverse", "split")}
+    cap = 1 << json.loads(common)["config"]["fri_config"]["cap_height"]
+    n_free_secret = free.info["secret"]
+    free.close()
+    for baked_proof in (False, True):
+        circ = gpw.Circuit.compile_verifier(ctx, common, vod, proof_json if baked_proof else None)
+        assert {k: circ.info[k] for k in counts} == counts
+        assert circ.info["secret"] == (0 if baked_proof else n_free_secret - cap - 1)
+        inputs = circ.parse_inputs(proof_json, vod)
+        assert inputs.shape[0] == circ.info["public"] + circ.info["secret"]
+        key = gpw.WrapKey.setup(ctx, circ, SEED)
+        proof = key.prove(inputs)
+        (ok, why), vk, pr = _verify(key, proof, _public_ints(circ, inputs))
+        assert ok, why
+        v2 = json.loads(vod)
+        v2["circuit_digest"] = str(int(v2["circuit_digest"]) ^ 1)
+        with pytest.raises(gpw.GpwError):
+            circ.parse_inputs(proof_json, json.dumps(v2))
+        if baked_proof:
+            p2 = json.loads(proof_json)
+            p2["proof"]["opening_proof"]["pow_witness"] ^= 1
+            with pytest.raises(gpw.GpwError):
+                circ.parse_inputs(json.dumps(p2), vod)
+        key.close()
+        circ.close()
