@@ -116,6 +116,22 @@ extern "C" int gpw_ctx_set_stream(gpw_ctx* ctx, void* cuda_stream) {
   return GPW_OK;
 }
 
+// Tunables of a context. "msm_affine_rounds": batch-affine pair-reduction rounds before the XYZZ bucket accumulation
+// (0 = off, the default; see csrc/msm_affine.cuh).
+extern "C" int gpw_ctx_set_option(gpw_ctx* ctx, const char* key, int64_t value) {
+  if (!ctx || !key) return GPW_EINVAL;
+  if (!strcmp(key, "msm_affine_rounds")) {
+    if (value < 0 || value > 8) {
+      set_error("msm_affine_rounds must be in [0, 8]");
+      return GPW_EINVAL;
+    }
+    ctx->msm_affine_rounds = (int)value;
+    return GPW_OK;
+  }
+  set_error("ctx_set_option: unknown option '%s'", key);
+  return GPW_EINVAL;
+}
+
 extern "C" int gpw_ctx_sync(gpw_ctx* ctx) {
   if (!ctx) return GPW_EINVAL;
   GPW_CUDA(cudaSetDevice(ctx->device));
@@ -198,6 +214,15 @@ extern "C" int gpw_host_ff_inv(int field, const uint64_t* a, uint64_t* out, size
   if ((!a || !out) && n) return GPW_EINVAL;
   if (field == 0) host_map<FrParams>(a, out, n, [](const Fr& x) { return inv(x); });
   else if (field == 1) host_map<FpParams>(a, out, n, [](const Fp& x) { return inv(x); });
+  else return GPW_EINVAL;
+  return GPW_OK;
+}
+
+// the shift-and-subtract inverse the batch-affine bucket accumulation uses on the device (ff.cuh inv_euclid)
+extern "C" int gpw_host_ff_inv_euclid(int field, const uint64_t* a, uint64_t* out, size_t n) {
+  if ((!a || !out) && n) return GPW_EINVAL;
+  if (field == 0) host_map<FrParams>(a, out, n, [](const Fr& x) { return inv_euclid(x); });
+  else if (field == 1) host_map<FpParams>(a, out, n, [](const Fp& x) { return inv_euclid(x); });
   else return GPW_EINVAL;
   return GPW_OK;
 }

@@ -62,6 +62,17 @@ struct gpw_ctx {
   // cumulative statistics of the G1 bucket-accumulation kernel (bench.py roofline): [0] G1, [1] G2
   double msm_acc_ms_sum[2] = {0, 0}, msm_total_ms_sum[2] = {0, 0};
   uint64_t msm_points_sum[2] = {0, 0}, msm_digits_sum[2] = {0, 0}, msm_calls[2] = {0, 0};
+  // what a shared bucket sort (msm_dev_impl's sort_tag) was built for: reuse by an MSM of any other shape is refused
+  struct SortDesc {
+    size_t n = 0;
+    int c = 0, win_lo = 0, win_hi = 0, fixed = 0, rounds = 0;
+    const void* scalars = nullptr;
+    bool operator==(const SortDesc& o) const {
+      return n == o.n && c == o.c && win_lo == o.win_lo && win_hi == o.win_hi && fixed == o.fixed && rounds == o.rounds && scalars == o.scalars;
+    }
+  };
+  std::map<std::string, SortDesc> sort_desc;
+  int msm_affine_rounds = -1;  // -1: environment / default (off); see msm_dev_impl
   bool poseidon_consts_loaded = false;
   // Pinned host staging for the small host<->device transfers of the proving path (window sums, status words,
   // challenges). A cudaMemcpyAsync to or from PAGEABLE memory blocks inside the driver until the stream has drained -

@@ -55,6 +55,10 @@ __device__ __forceinline__ uint32_t get_bits(const uint32_t* s, int lo, int c) {
   return (uint32_t)(v >> off) & ((1u << c) - 1u);
 }
 
+}  // namespace gpw
+#include "msm_affine.cuh"
+namespace gpw {
+
 // Signed-digit extraction shared by the histogram and the scatter pass. Every lane walks every window (uniform trip
 // count) so that the warp can aggregate its atomics: lanes that hit the same bucket - bit wires and small constants make
 // (window 0, digit 1) and its neighbours receive millions of entries - are found with match.any and served by ONE
@@ -184,7 +188,7 @@ static __global__ void __launch_bounds__(SCAN_THREADS) k_msm_scan_final(const ui
   for (uint32_t k = 0; k < SCAN_PER_THREAD; k++) {
     if (base + k < B) {
       offsets[base + k] = run;
-      cursor[base + k] = run;
+      if (cursor) cursor[base + k] = run;
     }
     run += v[k];
   }
@@ -272,7 +276,8 @@ __global__ void __launch_bounds__(MSM_ACC_THREADS, sizeof(F) == sizeof(Fp) ? MSM
 
   XYZZ<F> acc = XYZZ<F>::inf();
   uint32_t pos = pos0;
-  uint32_t e_next = sorted[pos0];
+  // sorted == nullptr: the entries ARE the points (the list left by the batch-affine rounds), in order, no signs
+  uint32_t e_next = sorted ? sorted[pos0] : pos0;
   Affine<F> p_next = ld_struct(points + (e_next & 0x7fffffffu));
 #pragma unroll 1
   while (pos < pos1) {
@@ -289,7 +294,7 @@ __global__ void __launch_bounds__(MSM_ACC_THREADS, sizeof(F) == sizeof(Fp) ? MSM
     pos++;
     if (pos < pos1) {  // prefetch the next point while this add runs (dropping the prefetch for G2, whose addition
                        // is register bound, was measured: no faster)
-      e_next = sorted[pos];
+      e_next = sorted ? sorted[pos] : pos;
       p_next = ld_struct(points + (e_next & 0x7fffffffu));
     }
     add_mixed_flat(acc, p, (e >> 31) != 0);
@@ -601,6 +606,45 @@ static int msm_dev_impl(gpw_ctx* ctx, const Fr* scalars, const Affine<F>* points
   // wsums: [0, nw) level-0 sums T_w | [nw, 2 nw) level-1 sums | intermediates of the two-round sums
   GPW_TRY(ctx->get_scratch((T + ".wsums").c_str(), (size_t)nw * (2 + ngroups + ngroups2) * sizeof(XYZZ<F>), (void**)&wsums));
 
+  // Batch-affine rounds (msm_affine.cuh) before the XYZZ accumulation. OFF by default: measured on B200 (profiles/
+  // r02_batch_affine.md) the pairwise-tree rounds are bit-exact but slower than the XYZZ kernel - 6.4 instead of 9.5
+  // multiplications per addition, yet 2 140 instead of ~1 700 instructions, one dependent multiplication chain per thread
+  // (XYZZ has 2-3 independent ones) and three passes over the operands. gpw_ctx_set_option(ctx, "msm_affine_rounds", r) or
+  // GPW_MSM_AFFINE_ROUNDS=r turn them on (r = 1..8) for experiments and for the parity tests of that path.
+  int rounds = ctx->msm_affine_rounds;
+  {
+    static const char* env = getenv("GPW_MSM_AFFINE_ROUNDS");
+    if (env && rounds < 0) rounds = atoi(env);
+    rounds = std::max(0, std::min(8, rounds));
+    if (max_entries < 2 * (uint64_t)MSM_TASK) rounds = 0;
+  }
+  uint32_t *offr = nullptr, *rcounts = nullptr;
+  Affine<F>*affA = nullptr, *affB = nullptr;
+  F* affPre = nullptr;  // prefix products of one round's denominators (one per output slot, rounded up to whole CTAs)
+  if (rounds > 0) {
+    GPW_TRY(ctx->get_scratch((ST + ".offr").c_str(), (size_t)rounds * (B + 1) * 4 + 16, (void**)&offr));
+    GPW_TRY(ctx->get_scratch("msm.rcounts", (size_t)(B + 1) * 4 + 16, (void**)&rcounts));
+    const uint64_t cap1 = (max_entries + 1) / 2 + B, cap2 = (cap1 + 1) / 2 + B;
+    const char* grp = sizeof(Affine<F>) == 64 ? "msm.aff1" : "msm.aff2";
+    GPW_TRY(ctx->get_scratch((std::string(grp) + "A").c_str(), (size_t)cap1 * sizeof(Affine<F>) + 16, (void**)&affA));
+    if (rounds > 1) GPW_TRY(ctx->get_scratch((std::string(grp) + "B").c_str(), (size_t)cap2 * sizeof(Affine<F>) + 16, (void**)&affB));
+    const size_t pre_slots = (size_t)div_up(cap1, (size_t)PAIR_THREADS * PairCfg<F>::P) * PAIR_THREADS * PairCfg<F>::P;
+    GPW_TRY(ctx->get_scratch((std::string(grp) + "P").c_str(), pre_slots * sizeof(F) + 16, (void**)&affPre));
+  }
+  // a shared sort may only be reused by an MSM of exactly the shape it was built for
+  if (sort_tag) {
+    gpw_ctx::SortDesc want{n, c, win_lo, win_hi, fixed_windows, rounds, (const void*)scalars};
+    gpw_ctx::SortDesc& have = ctx->sort_desc[ST];
+    if (reuse_sort) {
+      if (!(have == want)) {
+        set_error("msm: shared sort '%s' was built for a different MSM (n, window, range, mode, rounds or scalars differ)", sort_tag);
+        return GPW_EINVAL;
+      }
+    } else {
+      have = want;
+    }
+  }
+
   GPW_CUDA(cudaEventRecord(ctx->ev[0], st));
   GPW_CUDA(cudaMemsetAsync(buckets, 0, (size_t)B * sizeof(XYZZ<F>), st));
   if (reuse_sort) {
@@ -621,8 +665,52 @@ static int msm_dev_impl(gpw_ctx* ctx, const Fr* scalars, const Affine<F>* points
     ctx->launches += 5;
   }
   GPW_CUDA(cudaEventRecord(ctx->ev[1], st));
-  k_msm_accumulate<F><<<div_up(ntasks, MSM_ACC_THREADS), MSM_ACC_THREADS, MSM_ACC_THREADS * sizeof(XYZZ<F>), st>>>(
-      points, sorted, offsets, B, buckets, head, tail, tail_key, tail_list, ntail);
+  // ---- batch-affine rounds (msm_affine.cuh): pairwise tree over the sorted list, then XYZZ for what is left --------------
+  const Affine<F>* acc_points = points;
+  const uint32_t* acc_sorted = sorted;
+  const uint32_t* acc_offsets = offsets;
+  uint32_t acc_ntasks = ntasks;
+  if (rounds > 0) {
+    constexpr int PP = PairCfg<F>::P;
+    uint64_t cap = max_entries;
+    const Affine<F>* in = points;
+    const uint32_t* off_prev = offsets;
+    for (int r = 1; r <= rounds; r++) {
+      uint32_t* off_r = offr + (size_t)(r - 1) * (B + 1);
+      if (!reuse_sort) {
+        k_msm_round_counts<<<div_up(B, 256), 256, 0, st>>>(offsets, B, r, rcounts);
+        GPW_CHECK_LAUNCH();
+        k_msm_scan_sums<<<nscan_blocks, SCAN_THREADS, 0, st>>>(rcounts, B, block_sums);
+        GPW_CHECK_LAUNCH();
+        k_msm_scan_blocks<<<1, SCAN_THREADS, 0, st>>>(block_sums, nscan_blocks, off_r + B);
+        GPW_CHECK_LAUNCH();
+        k_msm_scan_final<<<nscan_blocks, SCAN_THREADS, 0, st>>>(rcounts, B, block_sums, off_r, nullptr);
+        GPW_CHECK_LAUNCH();
+        ctx->launches += 4;
+      }
+      cap = (cap + 1) / 2 + B;  // bucket b keeps ceil(k_b / 2) entries
+      Affine<F>* out = (r & 1) ? affA : affB;
+      const int grid = div_up(cap, (size_t)PAIR_THREADS * PP);
+      static bool smem_set = false;  // (per template instance)
+      if (!smem_set) {
+        GPW_CUDA(cudaFuncSetAttribute(k_msm_pair_round<F, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PairRing<F>::BYTES));
+        GPW_CUDA(cudaFuncSetAttribute(k_msm_pair_round<F, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PairRing<F>::BYTES));
+        smem_set = true;
+      }
+      if (r == 1) k_msm_pair_round<F, true><<<grid, PAIR_THREADS, PairRing<F>::BYTES, st>>>(in, sorted, off_prev, off_r, B, out, affPre);
+      else k_msm_pair_round<F, false><<<grid, PAIR_THREADS, PairRing<F>::BYTES, st>>>(in, nullptr, off_prev, off_r, B, out, affPre);
+      GPW_CHECK_LAUNCH();
+      ctx->launches += 1;
+      in = out;
+      off_prev = off_r;
+    }
+    acc_points = in;
+    acc_sorted = nullptr;
+    acc_offsets = off_prev;
+    acc_ntasks = (uint32_t)((cap + MSM_TASK - 1) / MSM_TASK);
+  }
+  k_msm_accumulate<F><<<div_up(acc_ntasks, MSM_ACC_THREADS), MSM_ACC_THREADS, MSM_ACC_THREADS * sizeof(XYZZ<F>), st>>>(
+      acc_points, acc_sorted, acc_offsets, B, buckets, head, tail, tail_key, tail_list, ntail);
   GPW_CHECK_LAUNCH();
   GPW_CUDA(cudaEventRecord(ctx->ev[2], st));
   // development aid (GPW_DEBUG_MSM=1): split of the tail into fix-up / window reduction / sums
@@ -630,11 +718,11 @@ static int msm_dev_impl(gpw_ctx* ctx, const Fr* scalars, const Affine<F>* points
   cudaEvent_t dbg_ev[3] = {nullptr, nullptr, nullptr};
   if (dbg_phases)
     for (auto& e : dbg_ev) cudaEventCreate(&e);
-  k_msm_fixup<F><<<ctx->sm_count * 8, 128, 0, st>>>(head, tail, offsets, tail_key, tail_list, ntail, big_list, nbig, buckets);
+  k_msm_fixup<F><<<ctx->sm_count * 8, 128, 0, st>>>(head, tail, acc_offsets, tail_key, tail_list, ntail, big_list, nbig, buckets);
   GPW_CHECK_LAUNCH();
   {
     const int fb_threads = sizeof(XYZZ<F>) > 128 ? 128 : 256;
-    k_msm_fixup_big<F><<<ctx->sm_count * 2, fb_threads, fb_threads * sizeof(XYZZ<F>), st>>>(head, tail, offsets, tail_key, big_list,
+    k_msm_fixup_big<F><<<ctx->sm_count * 2, fb_threads, fb_threads * sizeof(XYZZ<F>), st>>>(head, tail, acc_offsets, tail_key, big_list,
                                                                                           nbig, buckets);
   }
   GPW_CHECK_LAUNCH();

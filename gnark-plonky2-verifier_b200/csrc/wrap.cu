@@ -540,9 +540,9 @@ static int wrap_stage2(gpw_wrap_key* k, WrapLane* L, const uint64_t* r_canon, co
   mK2 = G1Affine{Fp::zero(), Fp::zero()};
   if (k->k2_lo < k->m) {
     const uint32_t n2 = k->m - k->k2_lo;
-    if (k->K2t)
-      GPW_TRY(gpw_msm_g1_shared_dev(ctx, (uint64_t)(wires + k->k2_lo), (uint64_t)k->K2t, n2, 1, FIXED_CQ, FIXED_WQ, "sortQ",
-                                    k->share_q_sort ? 1 : 0, (uint64_t*)&mK2));
+    if (k->K2t)  // share_q_sort: A's gathered suffix IS wires[k2_lo, m) - same scalars, same buffer, same sort
+      GPW_TRY(gpw_msm_g1_shared_dev(ctx, k->share_q_sort ? (uint64_t)(L->gathA + (k->nA - k->nA_tail)) : (uint64_t)(wires + k->k2_lo),
+                                    (uint64_t)k->K2t, n2, 1, FIXED_CQ, FIXED_WQ, "sortQ", k->share_q_sort ? 1 : 0, (uint64_t*)&mK2));
     else GPW_TRY(gpw_msm_g1_dev(ctx, (uint64_t)(wires + k->k2_lo), (uint64_t)(k->K + k->k2_lo), n2, 1, 0, 0, 0, (uint64_t*)&mK2));
     report("K2", n2);
   }

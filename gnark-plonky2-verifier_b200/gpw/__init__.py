@@ -43,12 +43,14 @@ SYMBOLS = {
     "gpw_ctx_destroy": (None, [_vp]),
     "gpw_ctx_set_stream": (C.c_int, [_vp, _vp]),
     "gpw_ctx_sync": (C.c_int, [_vp]),
+    "gpw_ctx_set_option": (C.c_int, [_vp, C.c_char_p, C.c_int64]),
     "gpw_ctx_launch_count": (C.c_uint64, [_vp]),
     "gpw_host_ff_mul": (C.c_int, [C.c_int, C.c_int, _vp, _vp, _vp, C.c_size_t]),
     "gpw_host_ff_mul_sub2": (C.c_int, [C.c_int, _vp, _vp, _vp, _vp, _vp, C.c_size_t]),
     "gpw_host_ff_to_mont": (C.c_int, [C.c_int, _vp, _vp, C.c_size_t]),
     "gpw_host_ff_from_mont": (C.c_int, [C.c_int, _vp, _vp, C.c_size_t]),
     "gpw_host_ff_inv": (C.c_int, [C.c_int, _vp, _vp, C.c_size_t]),
+    "gpw_host_ff_inv_euclid": (C.c_int, [C.c_int, _vp, _vp, C.c_size_t]),
     "gpw_host_ec_scalar_mul": (C.c_int, [C.c_int, _vp, _vp, _vp]),
     "gpw_host_ec_add": (C.c_int, [C.c_int, _vp, _vp, _vp]),
     "gpw_host_ec_is_on_curve": (C.c_int, [C.c_int, _vp]),
@@ -168,6 +170,13 @@ def host_ff_inv(field, a):
     return out
 
 
+def host_ff_inv_euclid(field, a):
+    a = _u64(a, (-1, 4))
+    out = np.empty_like(a)
+    _check(_lib.gpw_host_ff_inv_euclid(field, _p(a), _p(out), a.shape[0]))
+    return out
+
+
 def _pt_words(group):
     return 8 if group == 1 else 16
 
@@ -244,6 +253,9 @@ class Context:
 
     def sync(self):
         _check(_lib.gpw_ctx_sync(self._h))
+
+    def set_option(self, key, value):
+        _check(_lib.gpw_ctx_set_option(self._h, key.encode(), int(value)))
 
     @property
     def launches(self):

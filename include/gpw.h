@@ -46,6 +46,10 @@ void gpw_ctx_destroy(gpw_ctx* ctx);
 /* Use an externally owned cudaStream_t (e.g. torch.cuda.current_stream().cuda_stream); 0 = own stream. */
 int gpw_ctx_set_stream(gpw_ctx* ctx, void* cuda_stream);
 int gpw_ctx_sync(gpw_ctx* ctx);
+/* Tunables. "msm_affine_rounds" (0..8, default 0): rounds of batch-affine pairwise bucket reduction - gnark-crypto's
+ * batch-affine MultiExp restated for the GPU (csrc/msm_affine.cuh) - run before the extended-Jacobian accumulation.
+ * Same results bit for bit; measured slower than XYZZ alone on B200, hence off (profiles/r02_batch_affine.md).      */
+int gpw_ctx_set_option(gpw_ctx* ctx, const char* key, int64_t value);
 /* Number of gpw kernels launched through this ctx since creation (bench.py's gpu_launches). */
 uint64_t gpw_ctx_launch_count(const gpw_ctx* ctx);
 
@@ -58,6 +62,8 @@ int gpw_host_ff_mul_sub2(int field, const uint64_t* a_mont, const uint64_t* b_mo
 int gpw_host_ff_to_mont(int field, const uint64_t* a, uint64_t* out, size_t n);
 int gpw_host_ff_from_mont(int field, const uint64_t* a, uint64_t* out, size_t n);
 int gpw_host_ff_inv(int field, const uint64_t* a_mont, uint64_t* out_mont, size_t n);
+/* same result through the binary extended Euclid the device uses for its batched inversions (csrc/ff.cuh inv_euclid) */
+int gpw_host_ff_inv_euclid(int field, const uint64_t* a_mont, uint64_t* out_mont, size_t n);
 /* group: 1 = G1, 2 = G2. out = k * P with k a canonical 256-bit scalar; affine in/out, mont. */
 int gpw_host_ec_scalar_mul(int group, const uint64_t* point_affine, const uint64_t* scalar_canonical, uint64_t* out_affine);
 int gpw_host_ec_add(int group, const uint64_t* p_affine, const uint64_t* q_affine, uint64_t* out_affine);

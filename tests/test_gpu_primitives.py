@@ -308,6 +308,34 @@ def test_msm_fixed_base_matches_windowed(ctx, window_bits):
     assert gpw.points_to_ints(1, row)[0] == ob.point_key(1, exp)
 
 
+@pytest.mark.parametrize("rounds", [1, 3, 5])
+def test_msm_batch_affine_rounds_bit_identical(ctx, rounds):
+    # csrc/msm_affine.cuh (gnark-crypto's batch-affine bucket accumulation as a pairwise tree): the opt-in rounds must give
+    # the same group element as the XYZZ-only path on the witness mix, on hot buckets that span many CTAs, on buckets holding
+    # the same base several times (doubling), P + (-P) (cancellation), bases at infinity, and for G2
+    rng = random.Random(50 + rounds)
+    try:
+        ctx.set_option("msm_affine_rounds", rounds)
+        n = 40000
+        ks = list(range(1, n + 1))
+        mix = [rng.choice((rng.randrange(2), rng.randrange(1 << 16), rng.randrange(1 << 64), rng.randrange(ob.R))) for _ in range(n)]
+        _msm_case(ctx, 1, mix, ks)
+        _msm_case(ctx, 1, mix, ks, mont=True, window_bits=9)
+        _msm_case(ctx, 1, [7] * n, ks, window_bits=16)                                   # one hot bucket
+        _msm_case(ctx, 1, [7] * n, [1 + (i % 5) for i in range(n)], window_bits=16)      # equal points: doubling
+        _msm_case(ctx, 1, [3] * (n // 2) + [ob.R - 3] * (n // 2), [1 + (i % 7) for i in range(n)])  # cancellations
+        _msm_case(ctx, 2, mix[:6000], ks[:6000])
+        _msm_case(ctx, 2, [5] * 3000, [1 + (i % 3) for i in range(3000)], window_bits=12)
+        pts = gpw.host_ec_generator_multiples(1, 1, 5000)
+        pts[::7] = 0                                                                      # bases at infinity
+        sc = [rng.randrange(1 << 20) for _ in range(5000)]
+        out = ctx.msm(1, gpw.ints_to_limbs(sc), pts, window_bits=8)
+        exp = ob.ec_mul(1, ob.G1_GEN, sum(s * (i + 1) for i, s in enumerate(sc) if i % 7) % ob.R)
+        assert gpw.points_to_ints(1, out)[0] == ob.point_key(1, exp)
+    finally:
+        ctx.set_option("msm_affine_rounds", 0)
+
+
 def _dot_mod_r(scalars_u64x4, first_k):
     """sum_i scalars[i] * (first_k + i) mod r for (n, 4) little-endian u64 limbs, exactly, with numpy: 16-bit pieces keep
     every partial sum below 2^64 (piece < 2^16, multiplier < 2^24, n <= 2^23)."""
