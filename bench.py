@@ -172,6 +172,74 @@ def cpu_baseline():
     return cpu.describe(t, phases, pts, 1)
 
 
+def msm_split_record(ctx, dist, dev, side, rank, world, logn):
+    """BASELINE.json configs[4]: ONE large G1 MSM split over the N GPUs inside libgpw (gpw_comm_init + gpw_msm_g1_sharded:
+    windows or points, one NCCL all-gather of an affine point per rank, device-side sum) against the same MSM on one GPU.
+    Strong scaling: t(1 GPU) / (N t(N GPUs)), times = max over ranks of CUDA-event times on the launching stream."""
+    import numpy as np
+    import torch
+    import gpw
+    n = 1 << logn
+    idt = torch.zeros(128, dtype=torch.uint8, device=dev)
+    if rank == 0:
+        idt = torch.frombuffer(bytearray(gpw.comm_unique_id()), dtype=torch.uint8).to(dev)
+    dist.broadcast(idt, 0)
+    ctx.comm_init(world, rank, idt.cpu().numpy().tobytes())
+    pts = torch.empty((n, 8), dtype=torch.int64, device=dev)
+    ctx.generator_multiples_dev(1, 1, n, pts.data_ptr())
+    g = torch.Generator(device=dev).manual_seed(11)            # the same scalars on every rank
+    uni = torch.randint(0, 1 << 62, (n, 4), dtype=torch.int64, device=dev, generator=g)
+    uni[:, 3] &= (1 << 59) - 1                                  # < r
+    # witness-shaped mix (SURVEY 8d): 15 % bits, 20 % < 2^16, 45 % < 2^64, 20 % full width
+    wit = uni.clone()
+    u = torch.rand(n, device=dev, generator=g)
+    wit[u < 0.80, 1:] = 0
+    wit[u < 0.35, 0] &= 0xffff
+    wit[u < 0.15, 0] &= 1
+    del u
+    torch.cuda.synchronize()
+
+    def timed(fn, reps=3):
+        fn()                                                    # warm-up (scratch allocation)
+        ts = []
+        for _ in range(reps):
+            torch.cuda.synchronize()
+            dist.barrier()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(side)
+            out = fn()
+            e1.record(side)
+            torch.cuda.synchronize()
+            t = torch.tensor([e0.elapsed_time(e1)], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ts.append(float(t.item()))
+        return sum(ts) / len(ts), out
+
+    cases = []
+    for name, sc in (("uniform", uni), ("witness_mix", wit)):
+        t1, full = timed(lambda: ctx.msm_dev(1, sc.data_ptr(), pts.data_ptr(), n, window_bits=16))
+        rec = {"scalars": name, "one_gpu_ms": t1}
+        same = True
+        for split, key in ((1, "windows"), (2, "points")):
+            tn, res = timed(lambda: ctx.msm_sharded(1, sc.data_ptr(), pts.data_ptr(), n, window_bits=16, split=split))
+            rec[key + "_ms"] = tn
+            same = same and bool((res == full).all())
+        ok = torch.tensor([int(same)], device=dev)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        best = min(rec["windows_ms"], rec["points_ms"])
+        rec.update({"best_split": "windows" if rec["windows_ms"] <= rec["points_ms"] else "points", "best_ms": best,
+                    "speedup": t1 / best, "strong_scaling_efficiency": t1 / best / world, "bit_identical": bool(ok.item()),
+                    "GBps_algorithmic": 96.0 * n / (best * 1e-3) / 1e9})
+        cases.append(rec)
+    info = ctx.comm_info()
+    ctx.comm_destroy()
+    del pts, uni, wit
+    return {"what": "one G1 MSM of n = 2^%d points split over %d GPUs inside libgpw (NCCL %d all-gather of one affine point per "
+                    "rank + device-side sum); every rank ends with the full result" % (logn, world, info["nccl_version"]),
+            "n": n, "n_gpus": world, "cases": cases}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -182,6 +250,8 @@ def main():
     ap.add_argument("--impl", default="gpw", choices=["gpw", "reference"])
     ap.add_argument("--ref-budget-s", type=float, default=float(os.environ.get("GPW_REF_BUDGET_S", "200")),
                     help="--impl reference: wall-clock budget for warm-up + timed full-size CPU proofs")
+    ap.add_argument("--msm-split-logn", type=int, default=int(os.environ.get("GPW_MSM_SPLIT_LOGN", "25")),
+                    help="N > 1: size of the single MSM split over the GPUs (msm_split record)")
     ap.add_argument("--dummy-setup", action="store_true", help="synthetic key (groth16.DummySetup analogue) instead of the real setup")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -349,6 +419,8 @@ def main():
         "breakdown_ms": last,
         "circuit": {**circ.info, **key.info},
     }
+    if world > 1:
+        line["msm_split"] = msm_split_record(ctx, dist, dev, side, rank, world, args.msm_split_logn)
     if rank == 0:
         if world == 1:
             line["cpu_baseline"] = cpu_baseline()

@@ -82,8 +82,10 @@ extern "C" int gpw_ctx_create(int device, gpw_ctx** out) {
   return GPW_OK;
 }
 
+extern "C" int gpw_comm_destroy(gpw_ctx* ctx);
 extern "C" void gpw_ctx_destroy(gpw_ctx* ctx) {
   if (!ctx) return;
+  gpw_comm_destroy(ctx);
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
   for (auto& kv : ctx->scratch)

@@ -72,6 +72,9 @@ struct gpw_ctx {
     }
   };
   std::map<std::string, SortDesc> sort_desc;
+  // NCCL communicator of the sharded MSM (csrc/comm.cu); ncclComm_t kept opaque here
+  void* nccl_comm = nullptr;
+  int comm_size = 1, comm_rank = 0;
   int msm_affine_rounds = -1;  // -1: environment / default (off); see msm_dev_impl
   bool poseidon_consts_loaded = false;
   // Pinned host staging for the small host<->device transfers of the proving path (window sums, status words,

@@ -44,6 +44,14 @@ SYMBOLS = {
     "gpw_ctx_set_stream": (C.c_int, [_vp, _vp]),
     "gpw_ctx_sync": (C.c_int, [_vp]),
     "gpw_ctx_set_option": (C.c_int, [_vp, C.c_char_p, C.c_int64]),
+    "gpw_comm_unique_id": (C.c_int, [_vp]),
+    "gpw_comm_init": (C.c_int, [_vp, C.c_int, C.c_int, _vp]),
+    "gpw_comm_destroy": (C.c_int, [_vp]),
+    "gpw_comm_info": (C.c_int, [_vp, _vp]),
+    "gpw_msm_g1_sharded": (C.c_int, [_vp, C.c_uint64, C.c_uint64, C.c_size_t, C.c_int, C.c_int, C.c_int, _vp]),
+    "gpw_msm_g2_sharded": (C.c_int, [_vp, C.c_uint64, C.c_uint64, C.c_size_t, C.c_int, C.c_int, C.c_int, _vp]),
+    "gpw_msm_sharded_partial": (C.c_int, [_vp, C.c_int, C.c_uint64, C.c_uint64, C.c_size_t, C.c_int, C.c_int, C.c_int, C.c_int,
+                                          C.c_int, _vp]),
     "gpw_ctx_launch_count": (C.c_uint64, [_vp]),
     "gpw_host_ff_mul": (C.c_int, [C.c_int, C.c_int, _vp, _vp, _vp, C.c_size_t]),
     "gpw_host_ff_mul_sub2": (C.c_int, [C.c_int, _vp, _vp, _vp, _vp, _vp, C.c_size_t]),
@@ -89,6 +97,13 @@ for _name, (_res, _args) in SYMBOLS.items():
     _fn = getattr(_lib, _name)   # AttributeError here = header/library drift
     _fn.restype = _res
     _fn.argtypes = _args
+
+
+def comm_unique_id() -> bytes:
+    """ncclGetUniqueId (rank 0 calls it and ships the 128 bytes to the other ranks)"""
+    buf = np.zeros(128, dtype=np.uint8)
+    _check(_lib.gpw_comm_unique_id(_p(buf)))
+    return buf.tobytes()
 
 
 def last_error():
@@ -256,6 +271,33 @@ class Context:
 
     def set_option(self, key, value):
         _check(_lib.gpw_ctx_set_option(self._h, key.encode(), int(value)))
+
+    # ---- one MSM over several GPUs (csrc/comm.cu) ----
+    def comm_init(self, nranks, rank, unique_id: bytes):
+        assert len(unique_id) == 128
+        buf = np.frombuffer(unique_id, dtype=np.uint8).copy()
+        _check(_lib.gpw_comm_init(self._h, nranks, rank, _p(buf)))
+
+    def comm_destroy(self):
+        _check(_lib.gpw_comm_destroy(self._h))
+
+    def comm_info(self):
+        a = np.zeros(3, dtype=np.int32)
+        _check(_lib.gpw_comm_info(self._h, _p(a)))
+        return {"ranks": int(a[0]), "rank": int(a[1]), "nccl_version": int(a[2])}
+
+    def msm_sharded(self, group, scalars_ptr, points_ptr, n, scalars_mont=False, window_bits=0, split=0):
+        """collective: the whole MSM on every rank (split 1 = windows, 2 = points, 0 = choose)"""
+        out = np.zeros(_pt_words(group), dtype=np.uint64)
+        fn = _lib.gpw_msm_g1_sharded if group == 1 else _lib.gpw_msm_g2_sharded
+        _check(fn(self._h, scalars_ptr, points_ptr, n, int(scalars_mont), window_bits, split, _p(out)))
+        return out
+
+    def msm_sharded_partial(self, group, scalars_ptr, points_ptr, n, split, rank, nranks, scalars_mont=False, window_bits=0):
+        out = np.zeros(_pt_words(group), dtype=np.uint64)
+        _check(_lib.gpw_msm_sharded_partial(self._h, group, scalars_ptr, points_ptr, n, int(scalars_mont), window_bits, split,
+                                            rank, nranks, _p(out)))
+        return out
 
     @property
     def launches(self):

@@ -99,6 +99,26 @@ int gpw_msm_g1_fixed_dev(gpw_ctx* ctx, uint64_t scalars_dev, uint64_t table_dev,
                          int n_windows, uint64_t* out_affine);
 int gpw_msm_g2_dev(gpw_ctx* ctx, uint64_t scalars_dev, uint64_t points_dev, size_t n, int scalars_mont,
                    int window_bits, int win_lo, int win_hi, uint64_t* out_affine);
+/* ---- one MSM over several GPUs (BASELINE configs[4]; gnark-crypto's MultiExp splits its windows over CPU cores, this
+ * splits them - or the points - over B200s). One process per GPU; rank 0 gets an id from gpw_comm_unique_id and hands the
+ * 128 bytes to the other ranks through the host program's own channel; every rank then calls gpw_comm_init (collective,
+ * ncclCommInitRank on the context's device). libnccl.so.2 is loaded lazily; GPW_ENCCL if it is missing or a call fails.  */
+int gpw_comm_unique_id(uint8_t* out128);
+int gpw_comm_init(gpw_ctx* ctx, int nranks, int rank, const uint8_t* id128);
+int gpw_comm_destroy(gpw_ctx* ctx);
+int gpw_comm_info(const gpw_ctx* ctx, int* info3); /* {ranks (0 = no communicator), this rank, NCCL version code} */
+/* Collective over the context's communicator. split: 1 = every rank holds all n scalars / bases and computes its range of
+ * Pippenger windows; 2 = rank r computes the points [n r / N, n (r + 1) / N) (it only touches that slice); 0 = choose. One
+ * all-gather of one affine point per rank on the context's stream, the N points are added on the device; every rank
+ * receives the full result, bit-identical to gpw_msm_g{1,2}_dev on one GPU.                                              */
+int gpw_msm_g1_sharded(gpw_ctx* ctx, uint64_t scalars_dev, uint64_t points_dev, size_t n, int scalars_mont, int window_bits,
+                       int split, uint64_t* out_affine);
+int gpw_msm_g2_sharded(gpw_ctx* ctx, uint64_t scalars_dev, uint64_t points_dev, size_t n, int scalars_mont, int window_bits,
+                       int split, uint64_t* out_affine);
+/* The share rank `rank` of `nranks` contributes under split 1 / 2, computed on this context without a communicator (group:
+ * 1 = G1, 2 = G2): the shares of all ranks add up to the whole MSM.                                                      */
+int gpw_msm_sharded_partial(gpw_ctx* ctx, int group, uint64_t scalars_dev, uint64_t points_dev, size_t n, int scalars_mont,
+                            int window_bits, int split, int rank, int nranks, uint64_t* out_affine);
 /* Time (ms, CUDA events on the ctx stream) spent in the bucket-accumulation kernel of the most
  * recent MSM on this ctx, and the number of non-zero digits it processed. */
 int gpw_msm_last_stats(gpw_ctx* ctx, float* accumulate_ms, float* total_ms, uint64_t* nonzero_digits);

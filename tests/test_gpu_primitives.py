@@ -433,14 +433,58 @@ def test_ntt_large_roundtrip_and_linearity(ctx):
     assert got == [pow(w, k, ob.R) for k in ks]
 
 
-def test_sharded_msm_nccl_two_gpus():
-    # multi-GPU window split over NCCL (needs >= 2 GPUs on the box; the CPU logic is covered by the gloo test)
+def test_sharded_msm_shares_add_up_and_single_rank_communicator(ctx):
+    # csrc/comm.cu on ONE GPU: (1) for both splits the shares of N = 2, 3, 8 and 20 virtual ranks (20 > the 16 windows:
+    # empty shares) add up to the whole MSM, G1 and G2; (2) a real NCCL communicator of one rank runs the collective path
+    # end to end (ncclCommInitRank, all-gather on the context's stream, device-side sum) and returns the same point
+    import torch
+    rng = random.Random(77)
+    for group, n in ((1, 6000), (2, 1500)):
+        pts = gpw.host_ec_generator_multiples(group, 1, n)
+        sc = [rng.choice((rng.randrange(ob.R), rng.randrange(1 << 64), rng.randrange(2))) for _ in range(n)]
+        sl = gpw.ints_to_limbs(sc)
+        full = ctx.msm(group, sl, pts, window_bits=16)
+        ds = torch.from_numpy(sl.view(np.int64)).cuda()
+        dp = torch.from_numpy(pts.view(np.int64)).cuda()
+        torch.cuda.synchronize()
+        for split in (1, 2):
+            for N in (2, 3, 8, 20):
+                acc = np.zeros(8 if group == 1 else 16, dtype=np.uint64)
+                for r in range(N):
+                    acc = gpw.host_ec_add(group, acc, ctx.msm_sharded_partial(group, ds.data_ptr(), dp.data_ptr(), n, split, r, N,
+                                                                              window_bits=16))
+                assert (acc == full).all(), (group, split, N)
+    c2 = gpw.Context(0)
+    try:
+        with pytest.raises(gpw.GpwError) as e:
+            c2.msm_sharded(1, ds.data_ptr(), dp.data_ptr(), 10)
+        assert e.value.code == -7                       # GPW_ENCCL: no communicator yet
+        c2.comm_init(1, 0, gpw.comm_unique_id())
+        info = c2.comm_info()
+        assert info["ranks"] == 1 and info["rank"] == 0 and info["nccl_version"] > 20000
+        pts = gpw.host_ec_generator_multiples(1, 1, 6000)
+        sl = gpw.ints_to_limbs([rng.randrange(ob.R) for _ in range(6000)])
+        ds = torch.from_numpy(sl.view(np.int64)).cuda()
+        dp = torch.from_numpy(pts.view(np.int64)).cuda()
+        torch.cuda.synchronize()
+        full = c2.msm(1, sl, pts, window_bits=16)
+        for split in (0, 1, 2):
+            assert (c2.msm_sharded(1, ds.data_ptr(), dp.data_ptr(), 6000, window_bits=16, split=split) == full).all()
+        c2.comm_destroy()
+        assert c2.comm_info()["ranks"] == 0
+    finally:
+        c2.close()
+
+
+def test_sharded_msm_nccl_all_gpus():
+    # the in-library sharded MSM over every GPU of the box (NCCL over NVLink); the single-GPU test above covers the logic
     import subprocess, sys, torch
-    if torch.cuda.device_count() < 2:
-        pytest.skip("needs 2 GPUs")
+    ngpu = torch.cuda.device_count()
+    if ngpu < 2:
+        pytest.skip("needs >= 2 GPUs (the one-rank communicator path is covered above)")
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
-                          "--master-addr", "127.0.0.1", "--master-port", "29517", os.path.join(root, "tools", "sharded_msm_check.py"), "16"],
-                         capture_output=True, text=True, timeout=600)
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(ngpu),
+                          "--master-addr", "127.0.0.1", "--master-port", "29517", os.path.join(root, "tools", "sharded_msm_check.py"), "18"],
+                         capture_output=True, text=True, timeout=900)
     assert out.returncode == 0, out.stdout + out.stderr
-    assert out.stdout.count("bit-identical") == 2
+    assert out.stdout.count("bit-identical") == 4

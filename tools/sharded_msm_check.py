@@ -1,6 +1,8 @@
 #!/usr/bin/env python3
-"""torchrun target: window-split MSM over all ranks (NCCL all-gather of one affine point per rank) must equal the
-single-GPU MSM bit for bit. Usage: torchrun --nproc-per-node N tools/sharded_msm_check.py [log2 n]"""
+"""torchrun target: ONE MSM split over all ranks INSIDE libgpw (gpw_comm_init + gpw_msm_g{1,2}_sharded: NCCL all-gather of one
+affine point per rank on the context's stream, the points added on the device) must equal the single-GPU MSM bit for bit, for
+both splits (windows / points), G1 and G2. torch.distributed only ships the 128-byte NCCL id and times the barrier.
+Usage: torchrun --nproc-per-node N tools/sharded_msm_check.py [log2 n]"""
 import os, sys
 import numpy as np
 import torch
@@ -8,7 +10,15 @@ import torch.distributed as dist
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "gnark-plonky2-verifier_b200"))
 import gpw
-from gpw import sharded
+
+
+def init_comm(ctx, rank, world, dev):
+    idt = torch.zeros(128, dtype=torch.uint8, device=dev)
+    if rank == 0:
+        idt = torch.frombuffer(bytearray(gpw.comm_unique_id()), dtype=torch.uint8).to(dev)
+    dist.broadcast(idt, 0)
+    ctx.comm_init(world, rank, idt.cpu().numpy().tobytes())
+
 
 def main():
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
@@ -21,6 +31,8 @@ def main():
     side = torch.cuda.Stream(device=dev)
     torch.cuda.set_stream(side)
     ctx.set_stream(side.cuda_stream)
+    init_comm(ctx, rank, world, dev)
+    assert ctx.comm_info()["ranks"] == world
     for group, words in ((1, 8), (2, 16)):
         m = n if group == 1 else n // 4
         pts = torch.empty((m, words), dtype=torch.int64, device=dev)
@@ -32,24 +44,25 @@ def main():
         full = ctx.msm_dev(group, s.data_ptr(), pts.data_ptr(), m, window_bits=16)
         full = ctx.msm_dev(group, s.data_ptr(), pts.data_ptr(), m, window_bits=16)      # second call: scratch is allocated
         full_ms = ctx.msm_last_stats()["total_ms"]
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        dist.barrier(); torch.cuda.synchronize()
-        e0.record(side)
-        res = sharded.sharded_msm(ctx, group, s.data_ptr(), pts.data_ptr(), m, window_bits=16, dist=dist, device=dev)
-        e1.record(side); torch.cuda.synchronize()
-        t = torch.tensor([e0.elapsed_time(e1)], device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ok = bool((res == full).all())
-        oks = torch.tensor([int(ok)], device=dev)
-        dist.all_reduce(oks, op=dist.ReduceOp.MIN)
-        if rank == 0:
-            st = ctx.msm_last_stats()
-            print("sharded MSM G%d n=%d over %d GPUs: %s, %.2f ms incl. all-gather + combine (max over ranks; this rank's window "
-                  "share alone %.2f ms; the whole MSM on one GPU %.2f ms)"
-                  % (group, m, world, "bit-identical to single-GPU" if oks.item() else "MISMATCH", t.item(), st["total_ms"], full_ms),
-                  flush=True)
-        assert oks.item() == 1
+        for split, name in ((1, "windows"), (2, "points")):
+            ctx.msm_sharded(group, s.data_ptr(), pts.data_ptr(), m, window_bits=16, split=split)   # warm-up
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            dist.barrier(); torch.cuda.synchronize()
+            e0.record(side)
+            res = ctx.msm_sharded(group, s.data_ptr(), pts.data_ptr(), m, window_bits=16, split=split)
+            e1.record(side); torch.cuda.synchronize()
+            t = torch.tensor([e0.elapsed_time(e1)], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            oks = torch.tensor([int(bool((res == full).all()))], device=dev)
+            dist.all_reduce(oks, op=dist.ReduceOp.MIN)
+            if rank == 0:
+                print("sharded MSM G%d n=%d over %d GPUs, split by %s: %s, %.2f ms incl. all-gather + device adds (max over ranks; "
+                      "the whole MSM on one GPU %.2f ms)"
+                      % (group, m, world, name, "bit-identical to single-GPU" if oks.item() else "MISMATCH", t.item(), full_ms), flush=True)
+            assert oks.item() == 1
+    ctx.comm_destroy()
     dist.destroy_process_group()
+
 
 if __name__ == "__main__":
     main()
