@@ -386,6 +386,8 @@ class VerifierChip {
 
 // ExampleVerifierCircuit.Define (verifier/util.go:19-24) with the proof and verifier-only data as SECRET inputs
 // (the reference's own test circuits use this form, fri/fri_test.go:17-21) and PublicInputs as public inputs.
+// A single gate's EvalUnfiltered as a circuit (see the definition for the spec string and the input order).
+void DefineGateCircuit(fe::API* api, const std::string& spec);
 std::vector<std::array<uint64_t, 4>> ParseVerifierOnly(const CommonCircuitData& cd, const std::string& verifier_only_json);
 // Allocates the inputs in ParseProofInputs order, runs Verify and Finalize. `baked`: leading secret-input slots that
 // become compile-time constants instead (see the definition).

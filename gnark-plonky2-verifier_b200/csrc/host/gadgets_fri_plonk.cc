@@ -907,6 +907,43 @@ void VerifierChip::Verify(const Proof& proof, const std::vector<Variable>& pis, 
   friChip.VerifyFriProof(friChip.GetInstance(ch.PlonkZeta), friChip.ToOpenings(proof.Openings), ch.Fri, caps, proof.OpeningProof);
 }
 
+// ---- one gate as a circuit of its own -----------------------------------------------------------------------------------
+// spec = "<n_consts>:<n_wires>:<n_constraints>:<gate id as in common_circuit_data.json>". Secret inputs: the local constants,
+// the local wires (2 Goldilocks limbs each) and the 4-element public-inputs hash; public inputs: the expected value of every
+// constraint (2 limbs each). The circuit asserts Gate::EvalUnfiltered == the public values, so a gate gadget can be checked
+// against ANY independent evaluation of the gate's polynomial (tests/test_gate_vectors.py does that for the gates the
+// reference has no vectors for: plonk/gates/gates_test.go covers 11 of 14).
+void DefineGateCircuit(fe::API* api, const std::string& spec) {
+  size_t p1 = spec.find(':'), p2 = spec.find(':', p1 + 1), p3 = spec.find(':', p2 + 1);
+  if (p1 == std::string::npos || p2 == std::string::npos || p3 == std::string::npos) throw std::runtime_error("gate circuit spec: n_consts:n_wires:n_constraints:id");
+  const size_t n_consts = std::stoul(spec.substr(0, p1)), n_wires = std::stoul(spec.substr(p1 + 1, p2 - p1 - 1)),
+               n_out = std::stoul(spec.substr(p2 + 1, p3 - p2 - 1));
+  std::unique_ptr<Gate> gate = GateInstanceFromId(spec.substr(p3 + 1));
+  std::vector<Variable> expect;
+  for (size_t i = 0; i < 2 * n_out; i++) expect.push_back(api->PublicInput());
+  EvaluationVars vars;
+  for (size_t i = 0; i < n_consts; i++) {
+    Variable a = api->SecretInput();
+    Variable b = api->SecretInput();
+    vars.localConstants.push_back({a, b});
+  }
+  for (size_t i = 0; i < n_wires; i++) {
+    Variable a = api->SecretInput();
+    Variable b = api->SecretInput();
+    vars.localWires.push_back({a, b});
+  }
+  for (int i = 0; i < 4; i++) vars.publicInputsHash[i] = api->SecretInput();
+  api->EndInputs();
+  GlChip gl(api);
+  std::vector<QE> out = gate->EvalUnfiltered(api, &gl, vars);
+  if (out.size() != n_out) throw std::runtime_error("gate produced " + std::to_string(out.size()) + " constraints, spec says " + std::to_string(n_out));
+  for (size_t i = 0; i < n_out; i++) {
+    api->AssertIsEqual(gl.Reduce(out[i][0]), expect[2 * i]);
+    api->AssertIsEqual(gl.Reduce(out[i][1]), expect[2 * i + 1]);
+  }
+  api->Finalize();
+}
+
 // verifier_only_circuit_data.json alone, in ParseProofInputs order (cap, then digest): the values baked into a bound circuit
 std::vector<std::array<uint64_t, 4>> ParseVerifierOnly(const CommonCircuitData& cd, const std::string& vo_json) {
   json::Value vo = json::parse(vo_json);

@@ -1269,6 +1269,16 @@ extern "C" int gpw_circuit_compile_gadget(gpw_ctx* ctx, const char* name, gpw_ci
   try {
     gadgets::GlChip gl(api);
     std::vector<fe::Variable> pub, sec;
+    if (nm.rfind("gate:", 0) == 0) {  // one gate of plonk/gates as its own circuit (finalised by DefineGateCircuit)
+      gadgets::DefineGateCircuit(api, nm.substr(5));
+      int rc_gate = finish_compile(c);
+      if (rc_gate != GPW_OK) {
+        gpw_circuit_free(c);
+        return rc_gate;
+      }
+      *out = c;
+      return GPW_OK;
+    }
     if (nm == "poseidon_gl") {
       for (int i = 0; i < 12; i++) pub.push_back(api->PublicInput());
       for (int i = 0; i < 12; i++) sec.push_back(api->SecretInput());

@@ -182,6 +182,9 @@ int gpw_circuit_compile_verifier_bound(gpw_ctx* ctx, const char* common_circuit_
 /* Stand-alone gadget circuits shaped like the reference's unit-test circuits: "poseidon_gl", "poseidon_bn254",
  * "qe_mul_div", "range_check" (poseidon/goldilocks_test.go, poseidon/bn254_test.go, goldilocks/*_test.go).       */
 int gpw_circuit_compile_gadget(gpw_ctx* ctx, const char* name, gpw_circuit** out);
+/* also: "gate:<n_consts>:<n_wires>:<n_constraints>:<gate id>" - ONE gate of plonk/gates (gate id as in common_circuit_data.json)
+ * as a circuit: secret inputs = constants, wires (2 limbs each), public-inputs hash (4); public inputs = the expected value of
+ * every constraint (2 limbs each); satisfied iff Gate.EvalUnfiltered gives those values (plonk/gates/gates_test.go's check). */
 void gpw_circuit_free(gpw_circuit* c);
 /* info16: wires, public, secret, constraints, instructions, levels, limb_wires, limb_start, count_start, commit_wire,
  * narrow segments, wide segments, #MulAddHint, #ReduceHint, #InverseHint, #SplitLimbsHint                          */

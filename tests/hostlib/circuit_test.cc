@@ -62,6 +62,18 @@ void* ct_compile(const char* common_json) {
   }
 }
 
+// one gate as a circuit (gadgets::DefineGateCircuit): spec = "n_consts:n_wires:n_constraints:gate id"
+void* ct_compile_gate(const char* spec) {
+  try {
+    Circuit* c = new Circuit();
+    gadgets::DefineGateCircuit(&c->api, spec);
+    return c;
+  } catch (const std::exception& e) {
+    g_err = e.what();
+    return nullptr;
+  }
+}
+
 // bound / baked circuit forms (verifier/util.go:10-24): mode 1 = verifier-only data constant, 2 = proof constant too
 void* ct_compile_baked(const char* common_json, const char* proof_json, const char* vo_json, int mode) {
   try {

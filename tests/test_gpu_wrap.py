@@ -255,3 +255,22 @@ def test_poseidon_gl_macro_rejects_noncanonical_state(ctx):
         _solve(ctx, circ, circ.inputs_from_ints([0] * 12, [ogl.P] + [0] * 11))
     assert e.value.code == -5 and "MulAddHint" in str(e.value)
     circ.close()
+
+
+def test_gate_circuits_on_gpu(ctx):
+    # the three gates without a reference vector (Exponentiation, Constant, Noop) as one-gate circuits solved on the GPU, against
+    # the independent evaluation of their constraint polynomials (tests/test_gate_vectors.py); a perturbed expectation is rejected
+    from test_gate_vectors import gate_cases, gate_circuit_inputs, qadd, ONE
+    rng = random.Random(22)
+    for spec, expected, consts, wires in gate_cases(rng):
+        circ = gpw.Circuit.compile_gadget(ctx, "gate:" + spec)
+        pub, sec = gate_circuit_inputs(expected, consts, wires)
+        w = _solve(ctx, circ, circ.inputs_from_ints(pub, sec))
+        assert circ.r1cs_eval_dev(w.data_ptr()) == 0, spec
+        if expected:
+            pub2, _ = gate_circuit_inputs([qadd(expected[0], ONE)] + expected[1:], consts, wires)
+            w = _solve(ctx, circ, circ.inputs_from_ints(pub2, sec))
+            with pytest.raises(gpw.GpwError) as e:
+                circ.r1cs_eval_dev(w.data_ptr())
+            assert e.value.code == -6
+        circ.close()
