@@ -277,9 +277,34 @@ def main():
     ctx.set_stream(side.cuda_stream)
 
     rd = lambda f: open(os.path.join(TESTDATA, f), "rb").read()
-    t_compile = time.perf_counter()
-    circ = gpw.Circuit.compile_verifier(ctx, rd("common_circuit_data.json"))           # frontend.Compile (untimed)
-    t_compile = time.perf_counter() - t_compile
+    # frontend.Compile (untimed). The gadget code runs ONCE per job: rank 0 compiles and writes the compile cache
+    # (gpw_circuit_save - the r1cs.WriteTo the reference had to comment out, benchmark.go:94-99), the other ranks load it.
+    import hashlib
+    common = rd("common_circuit_data.json")
+    cache = os.path.join(os.environ.get("GPW_CACHE_DIR", "/tmp"), "gpw_%s_%d.circuit"
+                         % (hashlib.sha256(common).hexdigest()[:16], int(os.path.getmtime(gpw.LIB_PATH))))
+    t_compile, t_load = None, None
+    if rank == 0:
+        t0 = time.perf_counter()
+        circ = gpw.Circuit.compile_verifier(ctx, common)
+        t_compile = time.perf_counter() - t0
+        circ.save(cache + ".tmp%d" % os.getpid())
+        os.replace(cache + ".tmp%d" % os.getpid(), cache)
+    if world > 1:
+        dist.barrier()
+    if rank != 0 or world == 1:
+        t0 = time.perf_counter()
+        loaded = gpw.Circuit.load(ctx, cache)
+        t_load = time.perf_counter() - t0
+        if rank == 0:
+            assert loaded.info == circ.info
+            loaded.close()                                                               # (N = 1: only to report the load time)
+        else:
+            circ = loaded
+    if world > 1:   # the load time the line reports at N > 1 is the slowest rank's
+        tl = torch.tensor([t_load or 0.0], device=dev)
+        dist.all_reduce(tl, op=dist.ReduceOp.MAX)
+        t_load = float(tl.item())
     t_setup = time.perf_counter()
     if args.dummy_setup:
         key = gpw.WrapKey(ctx, circ, seed=0x5EED + rank)                                  # groth16.DummySetup (untimed)
@@ -388,7 +413,10 @@ def main():
         "warmup": args.warmup, "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "u32x8-montgomery", "data": "synthetic",
         "config": workload_config("synthetic (DummySetup analogue)" if args.dummy_setup else "real Groth16 setup (gpw_wrap_key_setup)"),
-        "untimed_s": {"compile": round(t_compile, 2), "setup": round(t_setup, 2)},
+        "untimed_s": {"compile": round(t_compile, 2) if t_compile is not None else None,
+                      "circuit_cache_load": round(t_load, 2) if t_load is not None else None,
+                      "circuit_cache_bytes": os.path.getsize(cache) if os.path.exists(cache) else None, "setup": round(t_setup, 2),
+                      "note": "rank 0 compiles once and saves the circuit; every other rank (and any later process) loads it"},
         "e2e": {"value": e2e_value, "unit": "proofs/s", "h2d_bytes_per_step": int(inputs.nbytes), "d2h_bytes_per_step": 512},
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,

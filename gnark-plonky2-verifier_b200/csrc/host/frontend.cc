@@ -1,6 +1,9 @@
 #include "frontend.h"
 
 #include <algorithm>
+#include <istream>
+#include <ostream>
+#include <type_traits>
 
 namespace gpw {
 namespace fe {
@@ -509,6 +512,8 @@ void API::ScheduleALAP() {
 }
 
 void API::ScheduleSpineAndTail() {
+  if (scheduled_) return;
+  scheduled_ = true;
   if (tape_.empty()) return;
   const size_t n = tape_.size();
   std::vector<uint32_t> producer(next_wire_, NO_LE);
@@ -576,6 +581,127 @@ void API::ScheduleSpineAndTail() {
     if (tape_[i].op == OP_COMMIT) commit_level_ = tape_[i].level;
   }
   max_level_ = max_level;
+}
+
+}  // namespace fe
+}  // namespace gpw
+
+// ---- compile cache ------------------------------------------------------------------------------------------------------
+namespace gpw {
+namespace fe {
+namespace {
+constexpr uint64_t CACHE_MAGIC = 0x3143575047ull;  // "GPWC1"
+template <class T>
+void put_vec(std::ostream& os, const std::vector<T>& v) {
+  static_assert(std::is_trivially_copyable<T>::value, "raw dump");
+  const uint64_t n = v.size();
+  os.write(reinterpret_cast<const char*>(&n), 8);
+  if (n) os.write(reinterpret_cast<const char*>(v.data()), (std::streamsize)(n * sizeof(T)));
+}
+template <class T>
+void get_vec(std::istream& is, std::vector<T>& v) {
+  uint64_t n = 0;
+  is.read(reinterpret_cast<char*>(&n), 8);
+  if (!is || n > (1ull << 33) / sizeof(T)) throw std::runtime_error("circuit cache: bad vector length");
+  v.resize(n);
+  if (n) is.read(reinterpret_cast<char*>(v.data()), (std::streamsize)(n * sizeof(T)));
+  if (!is) throw std::runtime_error("circuit cache: truncated");
+}
+// (std::pair is not trivially copyable for the type system although its layout is plain: go through two flat arrays)
+template <class A, class B>
+void put_pairs(std::ostream& os, const std::vector<std::pair<A, B>>& v) {
+  std::vector<A> a(v.size());
+  std::vector<B> b(v.size());
+  for (size_t i = 0; i < v.size(); i++) {
+    a[i] = v[i].first;
+    b[i] = v[i].second;
+  }
+  put_vec(os, a);
+  put_vec(os, b);
+}
+template <class A, class B>
+void get_pairs(std::istream& is, std::vector<std::pair<A, B>>& v) {
+  std::vector<A> a;
+  std::vector<B> b;
+  get_vec(is, a);
+  get_vec(is, b);
+  if (a.size() != b.size()) throw std::runtime_error("circuit cache: pair arrays differ in length");
+  v.resize(a.size());
+  for (size_t i = 0; i < a.size(); i++) v[i] = {a[i], b[i]};
+}
+template <class T>
+void put_pod(std::ostream& os, const T& v) {
+  os.write(reinterpret_cast<const char*>(&v), sizeof(T));
+}
+template <class T>
+void get_pod(std::istream& is, T& v) {
+  is.read(reinterpret_cast<char*>(&v), sizeof(T));
+  if (!is) throw std::runtime_error("circuit cache: truncated");
+}
+}  // namespace
+
+void API::Serialize(std::ostream& os) const {
+  put_pod(os, CACHE_MAGIC);
+  const uint32_t sizes[2] = {(uint32_t)sizeof(Instr), (uint32_t)sizeof(Fr)};
+  put_pod(os, sizes);
+  const uint32_t head[12] = {next_wire_, n_public_, n_secret_, max_level_, commit_level_, limb_wire_start_, n_limb_wires_,
+                             count_wire_start_, commit_wire_, le_one_, (uint32_t)finalized_, (uint32_t)scheduled_};
+  put_pod(os, head);
+  put_pod(os, counts_);
+  put_vec(os, tape_);
+  put_vec(os, cons_);
+  put_vec(os, le_off_);
+  put_vec(os, le_wire_);
+  put_vec(os, le_coeff_);
+  put_vec(os, coeffs_);
+  put_vec(os, macro_outs_);
+  put_pairs(os, hint_log_);
+  put_pairs(os, rc_);
+}
+
+void API::Deserialize(std::istream& is) {
+  uint64_t magic = 0;
+  get_pod(is, magic);
+  uint32_t sizes[2];
+  get_pod(is, sizes);
+  if (magic != CACHE_MAGIC || sizes[0] != sizeof(Instr) || sizes[1] != sizeof(Fr)) throw std::runtime_error("circuit cache: not a gpw circuit blob of this build");
+  uint32_t head[12];
+  get_pod(is, head);
+  next_wire_ = head[0];
+  n_public_ = head[1];
+  n_secret_ = head[2];
+  max_level_ = head[3];
+  commit_level_ = head[4];
+  limb_wire_start_ = head[5];
+  n_limb_wires_ = head[6];
+  count_wire_start_ = head[7];
+  commit_wire_ = head[8];
+  le_one_ = head[9];
+  finalized_ = head[10] != 0;
+  scheduled_ = head[11] != 0;
+  inputs_closed_ = true;
+  get_pod(is, counts_);
+  get_vec(is, tape_);
+  get_vec(is, cons_);
+  get_vec(is, le_off_);
+  get_vec(is, le_wire_);
+  get_vec(is, le_coeff_);
+  get_vec(is, coeffs_);
+  get_vec(is, macro_outs_);
+  get_pairs(is, hint_log_);
+  get_pairs(is, rc_);
+  // consistency: every index stays inside its table
+  if (le_off_.empty() || le_off_.back() != le_wire_.size() || le_wire_.size() != le_coeff_.size() || cons_.size() % 3)
+    throw std::runtime_error("circuit cache: inconsistent tables");
+  for (uint32_t le : cons_)
+    if (le + 1 >= le_off_.size()) throw std::runtime_error("circuit cache: constraint refers to a missing linear expression");
+  for (uint32_t w : le_wire_)
+    if (w >= next_wire_) throw std::runtime_error("circuit cache: wire id out of range");
+  for (uint32_t c : le_coeff_)
+    if (c >= coeffs_.size()) throw std::runtime_error("circuit cache: coefficient id out of range");
+  wire_level_.clear();
+  wire_bool_.clear();
+  coeff_ids_.clear();
 }
 
 }  // namespace fe

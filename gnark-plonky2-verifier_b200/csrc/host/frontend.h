@@ -14,6 +14,7 @@
 #pragma once
 #include <cstdint>
 #include <cstring>
+#include <iosfwd>
 #include <map>
 #include <stdexcept>
 #include <string>
@@ -171,6 +172,14 @@ class API {
   const std::vector<std::pair<uint32_t, int>>& RangeChecks() const { return rc_; }  // (LE id, bits)
   uint64_t NumRangeCheckedLimbs() const;
 
+  // Compile cache (the reference gave up on r1cs.WriteTo for this circuit, benchmark.go:94-99): everything a COMPILED circuit
+  // needs afterwards - R1CS, scheduled tape, macro output lists, hint log, range-check bookkeeping - as one binary blob
+  // (native endianness, versioned). The builder-only state (wire levels, interning maps, collected range checks) is not
+  // kept: a loaded API is read-only.
+  void Serialize(std::ostream& os) const;
+  void Deserialize(std::istream& is);  // throws std::runtime_error on a malformed / foreign blob
+  bool Scheduled() const { return scheduled_; }
+
   static constexpr uint32_t COEFF_ONE = 0, COEFF_NEG_ONE = 1;
 
  private:
@@ -186,6 +195,7 @@ class API {
   uint32_t n_public_ = 0, n_secret_ = 0;
   bool inputs_closed_ = false;
   bool finalized_ = false;
+  bool scheduled_ = false;  // ScheduleSpineAndTail has run (a circuit loaded from the cache is already scheduled)
   std::vector<uint32_t> wire_level_;
   std::vector<uint8_t> wire_bool_;  // known-boolean wires
   std::vector<Instr> tape_;

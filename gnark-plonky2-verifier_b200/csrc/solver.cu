@@ -617,6 +617,7 @@ struct gpw_circuit {
   // leading secret-input values compiled in as constants (gpw_circuit_compile_verifier_bound): parse_inputs checks the
   // documents against them and leaves them out of the input vector
   std::vector<std::array<uint64_t, 4>> baked;
+  std::string common_json;  // kept for the compile cache (gpw_circuit_save)
 };
 
 template <class T>
@@ -935,6 +936,7 @@ extern "C" int gpw_circuit_compile_verifier_bound(gpw_ctx* ctx, const char* comm
   c->ctx = ctx;
   try {
     c->cd = gadgets::ReadCommonCircuitData(common_circuit_data_json);
+    c->common_json = common_circuit_data_json;
     if (proof_json) c->baked = gadgets::ParseProofInputs(c->cd, proof_json, verifier_only_json).sec;
     else if (verifier_only_json) c->baked = gadgets::ParseVerifierOnly(c->cd, verifier_only_json);
     gadgets::DefineVerifierCircuit(&c->api, c->cd, c->baked.empty() ? nullptr : &c->baked);
@@ -1320,6 +1322,79 @@ extern "C" int gpw_circuit_compile_gadget(gpw_ctx* ctx, const char* name, gpw_ci
     return GPW_EINVAL;
   }
   int rc = finish_compile(c);
+  if (rc != GPW_OK) {
+    gpw_circuit_free(c);
+    return rc;
+  }
+  *out = c;
+  return GPW_OK;
+}
+
+// ---- compile cache (the r1cs.WriteTo the reference had to comment out, benchmark.go:94-99) -----------------------------
+// File = "GPWF" | is_verifier | common_circuit_data.json | baked input values | fe::API blob (R1CS + scheduled tape).
+extern "C" int gpw_circuit_save(const gpw_circuit* c, const char* path) {
+  if (!c || !path) {
+    set_error("circuit_save: null argument");
+    return GPW_EINVAL;
+  }
+  std::ofstream os(path, std::ios::binary | std::ios::trunc);
+  if (!os) {
+    set_error("circuit_save: cannot open %s", path);
+    return GPW_EINVAL;
+  }
+  const uint32_t magic = 0x46575047u, isv = c->is_verifier ? 1u : 0u;
+  const uint64_t jl = c->common_json.size(), nb = c->baked.size();
+  os.write((const char*)&magic, 4);
+  os.write((const char*)&isv, 4);
+  os.write((const char*)&jl, 8);
+  os.write(c->common_json.data(), (std::streamsize)jl);
+  os.write((const char*)&nb, 8);
+  if (nb) os.write((const char*)c->baked.data(), (std::streamsize)(nb * 32));
+  c->api.Serialize(os);
+  os.flush();
+  if (!os) {
+    set_error("circuit_save: write to %s failed", path);
+    return GPW_EINVAL;
+  }
+  return GPW_OK;
+}
+
+extern "C" int gpw_circuit_load(gpw_ctx* ctx, const char* path, gpw_circuit** out) {
+  if (!ctx || !path || !out) {
+    set_error("circuit_load: null argument");
+    return GPW_EINVAL;
+  }
+  GPW_CUDA(cudaSetDevice(ctx->device));
+  std::ifstream is(path, std::ios::binary);
+  if (!is) {
+    set_error("circuit_load: cannot open %s", path);
+    return GPW_EINVAL;
+  }
+  gpw_circuit* c = new gpw_circuit();
+  c->ctx = ctx;
+  try {
+    uint32_t magic = 0, isv = 0;
+    uint64_t jl = 0, nb = 0;
+    is.read((char*)&magic, 4);
+    is.read((char*)&isv, 4);
+    is.read((char*)&jl, 8);
+    if (!is || magic != 0x46575047u || jl > (1u << 28)) throw std::runtime_error("not a gpw circuit file");
+    c->common_json.resize(jl);
+    is.read(&c->common_json[0], (std::streamsize)jl);
+    is.read((char*)&nb, 8);
+    if (!is || nb > (1u << 24)) throw std::runtime_error("truncated header");
+    c->baked.resize(nb);
+    if (nb) is.read((char*)c->baked.data(), (std::streamsize)(nb * 32));
+    c->is_verifier = isv != 0;
+    if (c->is_verifier) c->cd = gadgets::ReadCommonCircuitData(c->common_json);
+    c->api.Deserialize(is);
+    if (!c->api.Scheduled()) throw std::runtime_error("the cached circuit was saved before scheduling");
+  } catch (const std::exception& e) {
+    set_error("circuit_load: %s", e.what());
+    delete c;
+    return GPW_EINVAL;
+  }
+  int rc = finish_compile(c);  // device upload; the tape keeps the schedule it was saved with
   if (rc != GPW_OK) {
     gpw_circuit_free(c);
     return rc;

@@ -18,6 +18,8 @@ _NEW = {
     "gpw_circuit_compile_verifier_bound": (C.c_int, [_vp, C.c_char_p, C.c_char_p, C.c_char_p, C.POINTER(_vp)]),
     "gpw_circuit_compile_gadget": (C.c_int, [_vp, C.c_char_p, C.POINTER(_vp)]),
     "gpw_circuit_free": (None, [_vp]),
+    "gpw_circuit_save": (C.c_int, [_vp, C.c_char_p]),
+    "gpw_circuit_load": (C.c_int, [_vp, C.c_char_p, C.POINTER(_vp)]),
     "gpw_circuit_info": (C.c_int, [_vp, _vp]),
     "gpw_circuit_parse_inputs": (C.c_int, [_vp, C.c_char_p, C.c_char_p, _vp, C.c_size_t]),
     "gpw_witness_solve_phase1_dev": (C.c_int, [_vp, C.c_uint64, C.c_int, C.c_uint64, C.c_size_t]),
@@ -81,6 +83,16 @@ class Circuit:
         h = _vp()
         _check(_lib.gpw_circuit_compile_verifier_bound(ctx._h, enc(common_circuit_data_json), enc(verifier_only_json),
                                                        enc(proof_json), C.byref(h)))
+        return cls(ctx, h)
+
+    def save(self, path):
+        """compile cache (the r1cs.WriteTo of benchmark.go:94-99)"""
+        _check(_lib.gpw_circuit_save(self._h, path.encode()))
+
+    @classmethod
+    def load(cls, ctx, path):
+        h = _vp()
+        _check(_lib.gpw_circuit_load(ctx._h, path.encode(), C.byref(h)))
         return cls(ctx, h)
 
     @classmethod

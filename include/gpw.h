@@ -186,6 +186,12 @@ int gpw_circuit_compile_gadget(gpw_ctx* ctx, const char* name, gpw_circuit** out
  * as a circuit: secret inputs = constants, wires (2 limbs each), public-inputs hash (4); public inputs = the expected value of
  * every constraint (2 limbs each); satisfied iff Gate.EvalUnfiltered gives those values (plonk/gates/gates_test.go's check). */
 void gpw_circuit_free(gpw_circuit* c);
+/* Compile cache: the compiled circuit (R1CS + scheduled solver tape + input codec state) as one file, so that every rank and
+ * every later process loads in a fraction of the compile time instead of re-running the gadget code. This is the
+ * `r1cs.WriteTo(fR1CS)` the reference had to comment out for this circuit ("takes up too much memory", benchmark.go:94-99,
+ * 204-209). The file belongs to this build of libgpw (layout-versioned); a foreign or damaged file is refused.          */
+int gpw_circuit_save(const gpw_circuit* c, const char* path);
+int gpw_circuit_load(gpw_ctx* ctx, const char* path, gpw_circuit** out);
 /* info16: wires, public, secret, constraints, instructions, levels, limb_wires, limb_start, count_start, commit_wire,
  * narrow segments, wide segments, #MulAddHint, #ReduceHint, #InverseHint, #SplitLimbsHint                          */
 int gpw_circuit_info(const gpw_circuit* c, uint64_t* info16);

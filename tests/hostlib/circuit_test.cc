@@ -62,6 +62,26 @@ void* ct_compile(const char* common_json) {
   }
 }
 
+// compile cache round trip of the host-side compiled circuit (fe::API::Serialize / Deserialize)
+int ct_save(void* h, const char* path) {
+  std::ofstream os(path, std::ios::binary | std::ios::trunc);
+  if (!os) return -1;
+  ((Circuit*)h)->api.Serialize(os);
+  return os ? 0 : -1;
+}
+void* ct_load(const char* path) {
+  try {
+    std::ifstream is(path, std::ios::binary);
+    if (!is) throw std::runtime_error("cannot open file");
+    Circuit* c = new Circuit();
+    c->api.Deserialize(is);
+    return c;
+  } catch (const std::exception& e) {
+    g_err = e.what();
+    return nullptr;
+  }
+}
+
 // one gate as a circuit (gadgets::DefineGateCircuit): spec = "n_consts:n_wires:n_constraints:gate id"
 void* ct_compile_gate(const char* spec) {
   try {

@@ -209,3 +209,34 @@ def test_baked_circuit_form_on_decode_block(lib, testdata_dir):
     fb = C.c_int64()
     assert lib.ct_check(h, C.byref(fb)) == 0, "first unsatisfied constraint: %d" % fb.value
     lib.ct_free(h)
+
+
+def test_compile_cache_round_trip(lib, kats, tmp_path):
+    # fe::API::Serialize / Deserialize (the compile cache behind gpw_circuit_save / _load; benchmark.go:94-99 is the
+    # r1cs.WriteTo the reference had to comment out): a reloaded circuit has the same shape, solves and is satisfied; a
+    # truncated or foreign file is refused. Scheduled and unscheduled tapes both survive.
+    lib.ct_save.argtypes = [C.c_void_p, C.c_char_p]
+    lib.ct_load.restype = C.c_void_p
+    lib.ct_load.argtypes = [C.c_char_p]
+    lib.ct_schedule_spine_tail.argtypes = [C.c_void_p]
+    out = [int(x) for x in kats["poseidon_gl_perm_zero"]]
+    for schedule in (False, True):
+        h = lib.ct_compile_small(0)
+        if schedule:
+            lib.ct_schedule_spine_tail(h)
+        path = str(tmp_path / ("circ%d.bin" % schedule)).encode()
+        assert lib.ct_save(h, path) == 0
+        h2 = lib.ct_load(path)
+        assert h2, lib.ct_last_error()
+        assert stats(lib, h2) == stats(lib, h)
+        assert _schedule_check(lib, h2) == _schedule_check(lib, h)
+        assert solve(lib, h2, out, [0] * 12) == (0, 0)
+        rc, bad = solve(lib, h2, [out[0] ^ 1] + out[1:], [0] * 12)
+        assert rc == 0 and bad == 1
+        lib.ct_free(h)
+        lib.ct_free(h2)
+    blob = open(path, "rb").read()
+    open(path, "wb").write(blob[:len(blob) // 2])
+    assert not lib.ct_load(path) and b"circuit cache" in lib.ct_last_error()
+    open(path, "wb").write(b"\0" * 64 + blob[64:])
+    assert not lib.ct_load(path)

@@ -274,3 +274,27 @@ def test_gate_circuits_on_gpu(ctx):
                 circ.r1cs_eval_dev(w.data_ptr())
             assert e.value.code == -6
         circ.close()
+
+
+def test_circuit_cache_round_trip_on_gpu(ctx, step, tmp_path):
+    # gpw_circuit_save / gpw_circuit_load: the reloaded step circuit has the same shape, parses the same inputs and produces the
+    # same proof bytes with the same key seed, without re-running the gadget code
+    import time
+    circ, inputs, d = step
+    path = str(tmp_path / "step.circuit")
+    circ.save(path)
+    t0 = time.perf_counter()
+    circ2 = gpw.Circuit.load(ctx, path)
+    t_load = time.perf_counter() - t0
+    assert circ2.info == circ.info
+    rd = lambda f: open(os.path.join(d, f), "rb").read()
+    assert (circ2.parse_inputs(rd("proof_with_public_inputs.json"), rd("verifier_only_circuit_data.json")) == inputs).all()
+    k1, k2 = gpw.WrapKey(ctx, circ, seed=3), gpw.WrapKey(ctx, circ2, seed=3)
+    p1, p2 = k1.prove(inputs, 5, 6), k2.prove(inputs, 5, 6)
+    assert (p1["raw"] == p2["raw"]).all()
+    print("circuit cache: %.1f MB, load %.2f s" % (os.path.getsize(path) / 1e6, t_load))
+    k1.close()
+    k2.close()
+    circ2.close()
+    with pytest.raises(gpw.GpwError):
+        gpw.Circuit.load(ctx, os.path.join(d, "common_circuit_data.json"))
