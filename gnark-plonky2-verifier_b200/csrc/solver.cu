@@ -1155,9 +1155,11 @@ extern "C" int gpw_r1cs_eval_on(gpw_circuit* c, gpw_ctx* lane, uint64_t wires_de
     GPW_CHECK_LAUNCH();
     ctx->launches++;
   }
-  k_r1cs_eval<<<div_up(dc.n_cons, 128), 128, 0, ctx->stream>>>(dc, (const Fr*)wires_dev, (Fr*)a_dev, (Fr*)b_dev, (Fr*)c_dev, bad, bad + 1);
-  GPW_CHECK_LAUNCH();
-  ctx->launches++;
+  if (dc.n_cons) {  // (a circuit without constraints - a NoopGate on its own - is trivially satisfied)
+    k_r1cs_eval<<<div_up(dc.n_cons, 128), 128, 0, ctx->stream>>>(dc, (const Fr*)wires_dev, (Fr*)a_dev, (Fr*)b_dev, (Fr*)c_dev, bad, bad + 1);
+    GPW_CHECK_LAUNCH();
+    ctx->launches++;
+  }
   const unsigned long long* res = (const unsigned long long*)ctx->pin_take(16);
   GPW_CUDA(cudaMemcpyAsync((void*)res, bad, 16, cudaMemcpyDeviceToHost, ctx->stream));
   GPW_CUDA(cudaStreamSynchronize(ctx->stream));
