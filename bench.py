@@ -184,7 +184,15 @@ def msm_split_record(ctx, dist, dev, side, rank, world, logn):
     if rank == 0:
         idt = torch.frombuffer(bytearray(gpw.comm_unique_id()), dtype=torch.uint8).to(dev)
     dist.broadcast(idt, 0)
-    ctx.comm_init(world, rank, idt.cpu().numpy().tobytes())
+    # (NCCL may print its version banner on stdout when a communicator is created: keep stdout for the one JSON line)
+    sys.stdout.flush()
+    saved = os.dup(1)
+    os.dup2(2, 1)
+    try:
+        ctx.comm_init(world, rank, idt.cpu().numpy().tobytes())
+    finally:
+        os.dup2(saved, 1)
+        os.close(saved)
     pts = torch.empty((n, 8), dtype=torch.int64, device=dev)
     ctx.generator_multiples_dev(1, 1, n, pts.data_ptr())
     g = torch.Generator(device=dev).manual_seed(11)            # the same scalars on every rank
