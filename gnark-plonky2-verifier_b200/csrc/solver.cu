@@ -331,8 +331,8 @@ __device__ __forceinline__ void exec_instr(const DevCircuit& c, Fr* W, const DIn
 //   records: op|nout<<8, out, nA, nB, nC, ring slot, nD, then (wire, coeff-id) pairs of A, B, C, D
 //   (a Poseidon-Goldilocks macro sits alone in its chunk, flag CHUNK_FLAG_GL_MACRO, its 1992 output wire ids after A)
 // so one contiguous copy brings everything an instruction needs except the wire values themselves. The CTA keeps
-// two chunk buffers in shared memory and prefetches chunk i+1 with cp.async while it executes chunk i: the only
-// exposed global-memory latency per level is the load of the operand wires.
+// two chunk buffers in shared memory and prefetches chunk i+1 with ONE TMA bulk copy (cp.async.bulk + mbarrier) while it
+// executes chunk i: the only exposed global-memory latency per level is the load of the operand wires.
 constexpr uint32_t CHUNK_MAX_WORDS = 6144;  // 24 KB per buffer
 // + the Poseidon-Goldilocks macro's trace (1992 integers of 192 bits) and its 2 x 12-word exchange buffers
 constexpr size_t GLM_TRACE_WORDS64 = (size_t)glm::N_OUT * 3 + 24;
@@ -355,12 +355,35 @@ static size_t spine_smem_bytes() {
   return v;
 }
 
-__device__ __forceinline__ void cp_async_16(void* smem_dst, const void* gmem_src) {
-  uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gmem_src));
+// ---- TMA (1-D bulk) + mbarrier: one elected thread starts the copy of a whole chunk (up to 24 KB, contiguous in the
+// stream), the copy engine moves it while all 256 threads work on the current chunk, and completion is signalled on a
+// shared-memory mbarrier by byte count - no thread spends instructions on the transfer (the 16-byte cp.async loop this
+// replaces cost every thread ~6 copies + a commit per chunk, ~1 000 chunks per proof on a latency-bound CTA).
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(count));
 }
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;"); }
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_bulk_load(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   (uint32_t)__cvta_generic_to_shared(smem_dst)),
+               "l"(gmem_src), "r"(bytes), "r"((uint32_t)__cvta_generic_to_shared(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  const uint32_t a = (uint32_t)__cvta_generic_to_shared(bar);
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(a), "r"(parity)
+        : "memory");
+  } while (!done);
+}
 
 __global__ void __launch_bounds__(NARROW_THREADS)
     k_tape_staged(DevCircuit c, const uint32_t* __restrict__ stream, uint32_t first_words, Fr* __restrict__ wires, size_t wire_stride,
@@ -375,8 +398,18 @@ __global__ void __launch_bounds__(NARROW_THREADS)
   uint32_t* h = hist + (size_t)blockIdx.x * 65536;
   const uint32_t* src = stream;
   uint32_t words = first_words;
-  for (uint32_t i = threadIdx.x * 4; i < words; i += blockDim.x * 4) cp_async_16(&buf[0][i], src + i);
-  cp_async_commit();
+  __shared__ __align__(8) uint64_t chunk_bar[2];  // one mbarrier per chunk buffer
+  uint32_t bar_parity[2] = {0, 0};
+  if (threadIdx.x == 0) {
+    mbar_init(&chunk_bar[0], 1);
+    mbar_init(&chunk_bar[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    mbar_expect_tx(&chunk_bar[0], words * 4);
+    tma_bulk_load(&buf[0][0], src, words * 4, &chunk_bar[0]);
+  }
   int cur = 0;
   // development profile (GPW_SPINE_PROFILE): cycles of thread 0 spent [0] waiting for the chunk, [1] in macro input fetch,
   // [2] in the native permutation, [3] in the macro's conversion + stores, [4] in ordinary chunks; [5] macros, [6] chunks
@@ -388,14 +421,17 @@ __global__ void __launch_bounds__(NARROW_THREADS)
     t_prev = now;
   };
   while (words) {
-    cp_async_wait_all();
-    __syncthreads();  // chunk `cur` is resident; wires written by the previous chunk are visible
+    mbar_wait(&chunk_bar[cur], bar_parity[cur]);  // chunk `cur` has landed (the TMA's byte count completed the phase)
+    bar_parity[cur] ^= 1u;
+    __syncthreads();  // wires written by the previous chunk are visible; everyone has left the buffer about to be refilled
     lap(0);
     const uint32_t* ch = buf[cur];
     const uint32_t n_instr = ch[0], next_words = ch[1];
     const uint32_t* next_src = src + words;
-    for (uint32_t i = threadIdx.x * 4; i < next_words; i += blockDim.x * 4) cp_async_16(&buf[cur ^ 1][i], next_src + i);
-    cp_async_commit();
+    if (threadIdx.x == 0 && next_words) {  // prefetch chunk i+1 into the other buffer while chunk i executes
+      mbar_expect_tx(&chunk_bar[cur ^ 1], next_words * 4);
+      tma_bulk_load(&buf[cur ^ 1][0], next_src, next_words * 4, &chunk_bar[cur ^ 1]);
+    }
     if (ch[3] == CHUNK_FLAG_GL_MACRO) {
       // One whole Poseidon-Goldilocks permutation, cooperatively: 12 threads fetch the state, warp 0 evaluates the
       // permutation natively (lane k owns element k) leaving the 1992 hint / product integers in shared memory, then
