@@ -336,7 +336,7 @@ __device__ __forceinline__ void exec_instr(const DevCircuit& c, Fr* W, const DIn
 constexpr uint32_t CHUNK_MAX_WORDS = 6144;  // 24 KB per buffer
 // + the Poseidon-Goldilocks macro's trace (1992 integers of 192 bits) and its 2 x 12-word exchange buffers
 constexpr size_t GLM_TRACE_WORDS64 = (size_t)glm::N_OUT * 3 + 24;
-constexpr size_t STAGED_SMEM_BYTES = 2 * CHUNK_MAX_WORDS * 4 + RING_SLOTS * sizeof(Fr) + GLM_TRACE_WORDS64 * 8;  // 48 + 64 + 47 KB
+constexpr size_t STAGED_SMEM_BYTES = 2 * CHUNK_MAX_WORDS * 4 + RING_SLOTS * sizeof(Fr) + GLM_TRACE_WORDS64 * 8 + 16;  // 48 + 64 + 47 KB + 2 mbarriers
 constexpr uint32_t CHUNK_FLAG_GL_MACRO = 1;  // chunk header word [3]: the chunk is ONE OP_POSEIDON_GL instruction
 // The spine CTA is latency bound and shares nothing: when other proofs' MSM / NTT kernels run next to it (several
 // proofs in flight, wrap.cu) their warps would saturate the SM's IMAD pipe and stretch every level of the spine. It
@@ -398,7 +398,8 @@ __global__ void __launch_bounds__(NARROW_THREADS)
   uint32_t* h = hist + (size_t)blockIdx.x * 65536;
   const uint32_t* src = stream;
   uint32_t words = first_words;
-  __shared__ __align__(8) uint64_t chunk_bar[2];  // one mbarrier per chunk buffer
+  uint64_t* chunk_bar = glm_trace + (size_t)glm::N_OUT * 3;  // one mbarrier per chunk buffer (dynamic shared memory: the kernel
+                                                             // asks for the SM's whole 227 KB, static storage would not fit on top)
   uint32_t bar_parity[2] = {0, 0};
   if (threadIdx.x == 0) {
     mbar_init(&chunk_bar[0], 1);

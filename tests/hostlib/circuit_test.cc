@@ -12,6 +12,7 @@
 #include "../../gnark-plonky2-verifier_b200/csrc/gl.cuh"
 #include "../../gnark-plonky2-verifier_b200/csrc/host/frontend.h"
 #include "../../gnark-plonky2-verifier_b200/csrc/host/gadgets.h"
+#include "../../gnark-plonky2-verifier_b200/csrc/host/scs.h"
 #include "../../gnark-plonky2-verifier_b200/csrc/poseidon_bn254_macro.cuh"
 #include "../../gnark-plonky2-verifier_b200/csrc/poseidon_gl_macro.cuh"
 #include "../../gnark-plonky2-verifier_b200/csrc/poseidon_constants.inc"
@@ -60,6 +61,42 @@ void* ct_compile(const char* common_json) {
     g_err = e.what();
     return nullptr;
   }
+}
+
+// PLONK lowering (host/scs.cc) of the solved circuit: out6 = {gates, variables, logN, unsatisfied gates, first bad row + 1,
+// permutation errors}. The witness is extended on the host, every gate equation evaluated, and sigma checked to be a
+// permutation of the 3 N slots that never leaves a variable's slots.
+void ct_scs_check(void* h, uint64_t* out6) {
+  Circuit* c = (Circuit*)h;
+  scs::System sys = scs::Build(c->api);
+  std::vector<Fr> v(c->w.begin(), c->w.end());
+  scs::ExtendWitness(sys, &v);
+  int64_t fb = -1;
+  const uint64_t bad = scs::CheckGates(sys, v, &fb);
+  std::vector<uint32_t> sigma;
+  scs::BuildPermutation(sys, &sigma);
+  const size_t N = (size_t)1 << sys.logN;
+  auto var_of = [&](size_t slot) -> uint32_t {
+    const size_t col = slot / N, row = slot % N;
+    if (row >= sys.n_gates) return 0;
+    return col == 0 ? sys.a[row] : col == 1 ? sys.b[row] : sys.c[row];
+  };
+  uint64_t perm_bad = 0;
+  std::vector<uint8_t> hit(3 * N, 0);
+  for (size_t t = 0; t < 3 * N; t++) {
+    if (sigma[t] >= 3 * N || hit[sigma[t]]) {
+      perm_bad++;
+      continue;
+    }
+    hit[sigma[t]] = 1;
+    if (var_of(sigma[t]) != var_of(t)) perm_bad++;
+  }
+  out6[0] = sys.n_gates;
+  out6[1] = sys.n_vars;
+  out6[2] = (uint64_t)sys.logN;
+  out6[3] = bad;
+  out6[4] = (uint64_t)(fb + 1);
+  out6[5] = perm_bad;
 }
 
 // compile cache round trip of the host-side compiled circuit (fe::API::Serialize / Deserialize)
