@@ -463,4 +463,4 @@ class ProvingKey:
         return {"compute_h_ms": h.value, "msm_ms": dict(zip(("A", "B1", "B2", "K", "Z"), [float(x) for x in ms]))}
 
 
-from .wrap import Circuit, WrapKey, hash_to_fr  # noqa: E402,F401  (binds the circuit / wrap part of include/gpw.h)
+from .wrap import Circuit, WrapKey, PlonkKey, hash_to_fr  # noqa: E402,F401  (binds the circuit / wrap part of include/gpw.h)

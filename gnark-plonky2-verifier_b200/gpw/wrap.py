@@ -48,6 +48,12 @@ _NEW = {
     "gpw_ntt_share_tables": (C.c_int, [_vp, _vp, C.c_int]),
     "gpw_wrap_last_stats": (C.c_int, [_vp, _vp]),
     "gpw_hash_to_fr": (C.c_int, [C.c_char_p, C.c_size_t, C.c_char_p, _vp]),
+    "gpw_plonk_setup": (C.c_int, [_vp, _vp, C.c_char_p, C.POINTER(_vp)]),
+    "gpw_plonk_key_free": (None, [_vp]),
+    "gpw_plonk_key_info": (C.c_int, [_vp, _vp]),
+    "gpw_plonk_vk_write": (C.c_int, [_vp, _vp, C.c_size_t, C.POINTER(C.c_size_t)]),
+    "gpw_plonk_prove": (C.c_int, [_vp, _vp, _vp, C.c_size_t]),
+    "gpw_plonk_last_stats": (C.c_int, [_vp, _vp]),
 }
 for _name, (_res, _args) in _NEW.items():
     _fn = getattr(_lib, _name)
@@ -260,3 +266,42 @@ class WrapKey:
         _check(_lib.gpw_wrap_last_stats(self._h, ms))
         names = ("solve_phase1_ms", "commitment_ms", "solve_phase2_ms", "r1cs_eval_ms", "compute_h_ms", "msm_ms")
         return dict(zip(names, [float(x) for x in ms]))
+
+
+class PlonkKey:
+    """plonk.Setup / plonk.Prove (benchmark.go:130, 162) over the library's lowering of a compiled circuit (csrc/plonk.cu)."""
+    PROOF_BYTES = 10 * 64 + 18 * 32
+    INFO = "logN gates variables public_rows qcp_rows inputs has_commit chain_levels".split()
+
+    def __init__(self, ctx, circuit, seed32=None):
+        assert seed32 is None or len(seed32) == 32
+        h = _vp()
+        _check(_lib.gpw_plonk_setup(ctx._h, circuit._h, seed32, C.byref(h)))
+        self._h, self.ctx, self.circuit = h, ctx, circuit
+        a = np.zeros(8, dtype=np.uint64)
+        _check(_lib.gpw_plonk_key_info(self._h, _p(a)))
+        self.info = dict(zip(self.INFO, map(int, a)))
+
+    def close(self):
+        if self._h:
+            _lib.gpw_plonk_key_free(self._h)
+            self._h = None
+
+    def vk(self) -> bytes:
+        n = C.c_size_t()
+        _check(_lib.gpw_plonk_vk_write(self._h, None, 0, C.byref(n)))
+        buf = np.zeros(n.value, dtype=np.uint8)
+        _check(_lib.gpw_plonk_vk_write(self._h, _p(buf), buf.size, C.byref(n)))
+        return buf.tobytes()
+
+    def prove(self, inputs) -> bytes:
+        inputs = np.ascontiguousarray(inputs, dtype=np.uint64)
+        assert inputs.shape == (self.circuit.n_inputs, 4)
+        out = np.zeros(self.PROOF_BYTES, dtype=np.uint8)
+        _check(_lib.gpw_plonk_prove(self._h, _p(inputs), _p(out), out.size))
+        return out.tobytes()
+
+    def last_stats(self):
+        ms = (C.c_float * 6)()
+        _check(_lib.gpw_plonk_last_stats(self._h, ms))
+        return dict(zip(("witness_ms", "wires_ms", "grand_product_ms", "quotient_ms", "evaluations_ms", "openings_ms"), map(float, ms)))

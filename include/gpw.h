@@ -266,6 +266,27 @@ int gpw_wrap_set_lanes(gpw_wrap_key* k, int n);
 int gpw_wrap_last_stats(const gpw_wrap_key* k, float* ms6);
 int gpw_hash_to_fr(const uint8_t* msg, size_t len, const char* dst, uint64_t* out_canonical);
 
+/* ---- PLONK / KZG backend (BASELINE configs[3]; `-proof-system plonk`, benchmark.go:80-190) ---------------------------------
+ * gpw_plonk_setup = test.NewKZGSRS + plonk.Setup (benchmark.go:105, 130) for a compiled circuit: the circuit is lowered to PLONK
+ * gates (csrc/host/scs.cc: addition chains for the linear expressions, one multiplication gate per R1CS row, public-input rows,
+ * one Qcp row per committed range-check wire), the permutation and selector polynomials are committed with a KZG SRS generated
+ * from seed32 (NULL = OS entropy). gpw_plonk_prove = frontend.NewWitness + plonk.Prove (benchmark.go:162): witness on the GPU,
+ * five rounds of PLONK with the BSB22 commitment column, proof = 10 G1 commitments (64 B raw big-endian each: a b c P2 Z t0 t1 t2
+ * W_zeta W_zeta_w) + 18 evaluations (32 B big-endian each). The protocol is the published one; it differs from gnark's
+ * implementation in what is opened and in the transcript labels (header of csrc/plonk.cu) and has no blinding (not
+ * zero-knowledge). oracle/plonk.py is its verifier. GPW_EUNSAT if the witness does not satisfy the system.                    */
+typedef struct gpw_plonk_key gpw_plonk_key;
+int gpw_plonk_setup(gpw_ctx* ctx, gpw_circuit* circ, const uint8_t* seed32, gpw_plonk_key** out);
+void gpw_plonk_key_free(gpw_plonk_key* k);
+/* info8: logN, gates, variables, public rows (ONE + public inputs + commitment challenge), Qcp rows, inputs, has_commit, chain levels */
+int gpw_plonk_key_info(const gpw_plonk_key* k, uint64_t* info8);
+/* vk: u32 logN | u32 n_public_rows | u32 has_commit | k1 | k2 | omega | [qL] [qR] [qM] [qO] [qC] [Qcp] [S1] [S2] [S3] | [tau]2 */
+int gpw_plonk_vk_write(const gpw_plonk_key* k, uint8_t* out, size_t cap, size_t* len);
+/* inputs: n_inputs x 4 u64 canonical, host (gpw_circuit_parse_inputs order). out_proof: 1216 bytes. */
+int gpw_plonk_prove(gpw_plonk_key* k, const uint64_t* inputs, uint8_t* out_proof, size_t cap);
+/* ms of the last prove: witness + P2, wire columns, grand product, quotient, evaluations, openings */
+int gpw_plonk_last_stats(const gpw_plonk_key* k, float* ms6);
+
 /* ---- K3: Poseidon over BN254 Fr (t = 4) ---------------------------------------------------------
  * Replaces poseidon.BN254Chip.Poseidon (poseidon/bn254.go:39-45). states: n x 4 Fr in / out.   */
 int gpw_poseidon_bn254(gpw_ctx* ctx, const uint64_t* states_in, uint64_t* states_out, size_t n, int mont);
