@@ -51,30 +51,36 @@ struct Builder {
     s.qcp.push_back(qcp);
   }
 
-  // one chain over (coefficient id, variable) terms at `level`; returns the variable holding the sum
-  uint32_t chain(const uint32_t* cs, const uint32_t* ws, uint32_t n, uint32_t level) {
+  // one chain konst + sum of (coefficient id, variable) terms at `level`; returns the variable holding the sum
+  uint32_t chain(const uint32_t* cs, const uint32_t* ws, uint32_t n, uint32_t level, uint32_t konst) {
     if (level_chains.size() <= level) level_chains.resize(level + 1);
     Chain ch;
     ch.term_off = (uint32_t)s.chain_wire.size();
     ch.n_terms = n;
     ch.out = s.n_vars;
+    ch.konst = konst;
     for (uint32_t j = 0; j < n; j++) {
       s.chain_wire.push_back(ws[j]);
       s.chain_coeff.push_back(cs[j]);
     }
-    if ((uint64_t)s.n_vars + n - 1 >= 0xfffffff0ull) throw std::runtime_error("scs: too many variables");
-    s.n_vars += n - 1;
+    const uint32_t n_out = n > 1 ? n - 1 : 1;
+    if ((uint64_t)s.n_vars + n_out >= 0xfffffff0ull) throw std::runtime_error("scs: too many variables");
+    s.n_vars += n_out;
     level_chains[level].push_back(ch);
-    gate(ws[0], ws[1], ch.out, cs[0], cs[1], System::C_ZERO, System::C_NEG_ONE, System::C_ZERO);
+    if (n == 1) {
+      gate(ws[0], 0, ch.out, cs[0], System::C_ZERO, System::C_ZERO, System::C_NEG_ONE, konst);
+      return ch.out;
+    }
+    gate(ws[0], ws[1], ch.out, cs[0], cs[1], System::C_ZERO, System::C_NEG_ONE, konst);
     for (uint32_t j = 2; j < n; j++)
       gate(ch.out + j - 2, ws[j], ch.out + j - 1, System::C_ONE, cs[j], System::C_ZERO, System::C_NEG_ONE, System::C_ZERO);
     return ch.out + n - 2;
   }
 
-  // sum of n terms as one variable: chunks of SCS_CHUNK at `level`, their sums chained one level up
-  uint32_t sum(std::vector<uint32_t>& cs, std::vector<uint32_t>& ws, uint32_t level) {
+  // konst + sum of n terms as one variable: chunks of SCS_CHUNK at `level`, their sums chained one level up
+  uint32_t sum(std::vector<uint32_t>& cs, std::vector<uint32_t>& ws, uint32_t level, uint32_t konst) {
     const uint32_t n = (uint32_t)ws.size();
-    if (n <= SCS_CHUNK) return chain(cs.data(), ws.data(), n, level);
+    if (n <= SCS_CHUNK) return chain(cs.data(), ws.data(), n, level, konst);
     std::vector<uint32_t> ncs, nws;
     for (uint32_t lo = 0; lo < n; lo += SCS_CHUNK) {
       const uint32_t m = std::min(SCS_CHUNK, n - lo);
@@ -82,11 +88,11 @@ struct Builder {
         ncs.push_back(cs[lo]);
         nws.push_back(ws[lo]);
       } else {
-        nws.push_back(chain(cs.data() + lo, ws.data() + lo, m, level));
+        nws.push_back(chain(cs.data() + lo, ws.data() + lo, m, level, lo == 0 ? konst : System::C_ZERO));
         ncs.push_back(System::C_ONE);
       }
     }
-    return sum(ncs, nws, level + 1);
+    return sum(ncs, nws, level + 1, System::C_ZERO);
   }
 
   Side lower(uint32_t le) {
@@ -99,12 +105,18 @@ struct Builder {
     if (k == 1) {
       r = {api_coeff[lc[off[le]]], lw[off[le]]};
     } else if (k >= 2) {
-      std::vector<uint32_t> cs(k), ws(k);
-      for (uint32_t t = 0; t < k; t++) {
-        cs[t] = api_coeff[lc[off[le] + t]];
-        ws[t] = lw[off[le] + t];
+      // terms are sorted by wire id: a constant term (wire 0 = ONE) comes first and rides on qC
+      uint32_t t0 = 0, konst = System::C_ZERO;
+      if (lw[off[le]] == 0) {
+        konst = api_coeff[lc[off[le]]];
+        t0 = 1;
       }
-      r = {System::C_ONE, sum(cs, ws, 0)};
+      std::vector<uint32_t> cs(k - t0), ws(k - t0);
+      for (uint32_t t = t0; t < k; t++) {
+        cs[t - t0] = api_coeff[lc[off[le] + t]];
+        ws[t - t0] = lw[off[le] + t];
+      }
+      r = {System::C_ONE, sum(cs, ws, 0, konst)};
     }
     le_side[le] = r;
     le_done[le] = 1;
@@ -190,7 +202,8 @@ void ExtendWitness(const System& s, std::vector<Fr>* vp) {
   std::vector<Fr>& v = *vp;
   v.resize(s.n_vars, Fr::zero());
   for (const Chain& ch : s.chains) {
-    Fr acc = mul(s.coeffs[s.chain_coeff[ch.term_off]], v[s.chain_wire[ch.term_off]]);
+    Fr acc = add(s.coeffs[ch.konst], mul(s.coeffs[s.chain_coeff[ch.term_off]], v[s.chain_wire[ch.term_off]]));
+    if (ch.n_terms == 1) v[ch.out] = acc;
     for (uint32_t j = 1; j < ch.n_terms; j++) {
       acc = add(acc, mul(s.coeffs[s.chain_coeff[ch.term_off + j]], v[s.chain_wire[ch.term_off + j]]));
       v[ch.out + j - 1] = acc;

@@ -28,11 +28,14 @@ namespace scs {
 
 constexpr uint32_t SCS_CHUNK = 256;
 
-// v[out + j] = (j ? v[out + j - 1] : coeff[c[0]] v[w[0]]) + coeff[c[j + 1]] v[w[j + 1]],  j < n_terms - 1
+// v[out] = konst + c[0] v[w[0]] + c[1] v[w[1]],  v[out + j] = v[out + j - 1] + c[j + 1] v[w[j + 1]]   (j < n_terms - 1)
+// konst: coefficient id of the expression's constant term (C_ZERO if none) - it rides on the first gate's qC, which saves the
+// gate a term on the ONE wire would cost. n_terms == 1 (a constant plus one scaled wire): v[out] = konst + c[0] v[w[0]].
 struct Chain {
   uint32_t term_off;  // into chain_wire / chain_coeff
-  uint32_t n_terms;   // >= 2
-  uint32_t out;       // first of the n_terms - 1 new variables
+  uint32_t n_terms;   // >= 1
+  uint32_t out;       // first of the max(n_terms - 1, 1) new variables
+  uint32_t konst;
 };
 
 struct System {

@@ -78,6 +78,8 @@ __global__ void k_scs_chains(const scs::Chain* __restrict__ chains, uint32_t n, 
     return ci == scs::System::C_ONE ? x : ci == scs::System::C_NEG_ONE ? neg(x) : mul(ldf(coeffs + ci), x);
   };
   Fr acc = term(0);
+  if (ch.konst != scs::System::C_ZERO) acc = add(acc, ldf(coeffs + ch.konst));
+  if (ch.n_terms == 1) stf(v + ch.out, acc);
   for (uint32_t j = 1; j < ch.n_terms; j++) {
     acc = add(acc, term(j));
     stf(v + ch.out + j - 1, acc);

@@ -81,9 +81,11 @@ def test_plonk_circuit_with_range_check_commitment(ctx, kats):
     circ.close()
 
 
-def test_plonk_wrap_of_decode_block(ctx, testdata_dir):
-    # BASELINE configs[3] on the reference's fixture: the whole verifier circuit under PLONK (2^25 rows)
-    d = os.path.join(testdata_dir, "decode_block")
+@pytest.mark.parametrize("name", ["decode_block", "step"])
+def test_plonk_wrap_of_reference_fixture(ctx, testdata_dir, name):
+    # BASELINE configs[3] on the reference's fixtures: the whole verifier circuit under PLONK (2^25 rows each; step fits with
+    # 92 k rows to spare thanks to the constant folding into qC)
+    d = os.path.join(testdata_dir, name)
     rd = lambda f: open(os.path.join(d, f), "rb").read()
     circ = gpw.Circuit.compile_verifier(ctx, rd("common_circuit_data.json"), rd("verifier_only_circuit_data.json"))
     inputs = circ.parse_inputs(rd("proof_with_public_inputs.json"), rd("verifier_only_circuit_data.json"))
@@ -92,6 +94,9 @@ def test_plonk_wrap_of_decode_block(ctx, testdata_dir):
     public = [int(x) for x in gpw.limbs_to_ints(inputs[:circ.info["public"]])]
     ok, why = _check(key, proof, public)
     assert ok, why
-    print("plonk decode_block:", key.info, key.last_stats())
+    assert key.info["logN"] == 25
+    if public:
+        assert not _check(key, proof, public[:-1] + [public[-1] ^ 1])[0]
+    print("plonk %s:" % name, key.info, key.last_stats())
     key.close()
     circ.close()
