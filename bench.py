@@ -250,7 +250,7 @@ def msm_split_record(ctx, dist, dev, side, rank, world, logn):
 
 def run_plonk(args, ctx, circ, rd, side, dev, rank, world, t_compile, t_load):
     """BASELINE.json configs[3]: testdata/step under the PLONK / KZG backend (csrc/plonk.cu). One proof at a time per GPU (a
-    2^25-row proof keeps the whole device busy: 68 NTTs of 2^25 and 10 MSMs of 2^25 points), K proofs back to back."""
+    2^25-row proof keeps the whole device busy: 41 NTTs of 2^25 and 10 MSMs of 2^25 points), K proofs back to back."""
     import numpy as np
     import torch
     import gpw
@@ -293,9 +293,10 @@ def run_plonk(args, ctx, circ, rd, side, dev, rank, world, t_compile, t_load):
     assert proof == first, "PLONK proof not reproducible (no blinding: same inputs -> same bytes)"
     N = 1 << key.info["logN"]
     mean = {k: sum(p[k] for p in phases) / len(phases) for k in phases[0]}
-    # the quotient round: 4 cosets x 17 transforms of N points (64 N algorithmic bytes each) + as many scaling passes
+    # the quotient round: 4 cosets x (6 forward + 1 inverse) transforms of N points (64 N algorithmic bytes each), 28 scaling
+    # passes, and the quotient kernel itself reading 17 arrays and writing one
     peak, peak_kind = measured_peak_gbs()
-    q_bytes = 68 * 64.0 * N + 72 * 64.0 * N
+    q_bytes = 28 * 64.0 * N + 28 * 64.0 * N + 4 * 18 * 32.0 * N
     achieved = q_bytes / (mean["quotient_ms"] * 1e-3) / 1e9
     value = world * args.steps / (ms * 1e-3)
     line = {"metric": "wrap_proofs_per_sec", "value": value, "unit": "proofs/s", "n_gpus": world, "steps": args.steps,
@@ -312,8 +313,8 @@ def run_plonk(args, ctx, circ, rd, side, dev, rank, world, t_compile, t_load):
                     "note": "the timed call IS the host-buffer call (gpw_plonk_prove takes host inputs and returns host bytes)"},
             "gpu_launches": int(ctx.launches - l0),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
-                         "peak_source": peak_kind, "kernel": "k_ntt_pass + k_scale_pow in the quotient round (68 transforms + 72 scaling "
-                         "passes of 2^%d Fr per proof)" % key.info["logN"],
+                         "peak_source": peak_kind, "kernel": "k_ntt_pass + k_scale_pow + k_quotient in the quotient round (28 transforms + 28 scaling "
+                         "passes of 2^%d Fr per proof; the fixed polynomials' coset evaluations are precomputed)" % key.info["logN"],
                          "note": "integer-pipe bound like every kernel here (11.5 Montgomery multiplications per element and transform)"},
             "clocks": sampler.summary(), "breakdown_ms": mean,
             "untimed_s": {"compile": round(t_compile, 2) if t_compile is not None else None,

@@ -11,7 +11,8 @@
 //            the Groth16 path); solve phase 2; chain variables (k_scs_chains)
 //   round 1  a, b, c = the three wire columns, [a], [b], [c]
 //   round 2  beta, gamma; Z = grand product of (w + beta k_col w^i + gamma) / (w + beta S_col + gamma), [Z]
-//   round 3  alpha; quotient t = (gate + alpha perm + alpha^2 (Z - 1) L_0) / Z_H on four cosets of size N, split into
+//   round 3  alpha; quotient t = (gate + alpha perm + alpha^2 (Z - 1) L_0) / Z_H on four cosets of size N (the selectors',
+//            sigmas' and L_0's coset evaluations are precomputed at setup: 6 transforms per coset and proof), split into
 //            t_0, t_1, t_2 of degree < N, [t_0], [t_1], [t_2]
 //   round 4  zeta; all 17 polynomials evaluated at zeta, Z at zeta w
 //   round 5  nu; ONE batched opening at zeta and one at zeta w (W evaluated on H, interpolated, committed)
@@ -409,6 +410,9 @@ struct gpw_plonk_key {
   Fr* sig_c[3] = {};   // S1 S2 S3, coefficient form
   Fr* sig_e[3] = {};
   Fr* l0_c = nullptr;  // L_0 = (1/N) sum X^k
+  // the ten proof-independent polynomials (selectors, sigmas, L_0) evaluated on the four quotient cosets at setup:
+  // fixed_ce[j * 10 + p], 40 N-sized arrays (43 GB at 2^25) that save 40 of the 68 transforms of every proof
+  Fr* fixed_ce[40] = {};
   G1Affine* srs = nullptr;  // [tau^i] G1, i < N
   G2Affine tau2;            // [tau] G2
   G1Affine vk_com[9];       // [qL] [qR] [qM] [qO] [qC] [Qcp] [S1] [S2] [S3]
@@ -614,6 +618,21 @@ extern "C" int gpw_plonk_setup(gpw_ctx* ctx, gpw_circuit* circ, const uint8_t* s
     if (cudaMemcpyAsync(k->sig_c[i], k->sig_e[i], (size_t)N * sizeof(Fr), cudaMemcpyDeviceToDevice, st) != cudaSuccess) return fail(GPW_ECUDA);
     if ((rc = intt(k, k->sig_c[i]))) return fail(rc);
   }
+  {  // coset evaluations of the fixed polynomials
+    const Fr g = fr_u64(5), rho = root_of_unity(k->logN + 2);
+    const Fr* fixed_c[10] = {k->sel_c[0], k->sel_c[1], k->sel_c[2], k->sel_c[3], k->sel_c[4], k->sel_c[5], k->sig_c[0], k->sig_c[1], k->sig_c[2], k->l0_c};
+    for (int j = 0; j < 4; j++) {
+      const Fr shift = mul(g, pow_u64(rho, (uint64_t)j));
+      for (int p = 0; p < 10; p++) {
+        Fr*& dst = k->fixed_ce[j * 10 + p];
+        if ((rc = dalloc(k, (void**)&dst, (size_t)N * sizeof(Fr)))) return fail(rc);
+        if (cudaMemcpyAsync(dst, fixed_c[p], (size_t)N * sizeof(Fr), cudaMemcpyDeviceToDevice, st) != cudaSuccess) return fail(GPW_ECUDA);
+        k_scale_pow<<<GP, 128, 0, st>>>(dst, N, shift, Fr::one());
+        if ((rc = ntt(k, dst))) return fail(rc);
+      }
+    }
+    ctx->launches += 40;
+  }
   // SRS: tau^i G1 (i < N), tau G2
   uint8_t seed[64];
   memset(seed, 0, sizeof(seed));
@@ -814,21 +833,12 @@ extern "C" int gpw_plonk_prove(gpw_plonk_key* k, const uint64_t* inputs, uint8_t
   tr.g1(com[4]);
   const Fr alpha = tr.challenge("gpw-plonk-alpha");
   const Fr g = fr_u64(5), rho = root_of_unity(k->logN + 2);
-  const Fr* srcs[16] = {a_c, b_c, c_c, z_c, p2_c, pi_c, k->sel_c[0], k->sel_c[1], k->sel_c[2], k->sel_c[3], k->sel_c[4], k->sel_c[5],
-                        k->sig_c[0], k->sig_c[1], k->sig_c[2], k->l0_c};
-  // sixteen coset-evaluation buffers: buf[15..23] (9) + the seven that are free now
-  Fr* ce[16];
-  {
-    int n = 0;
-    for (int i = 15; i < 24; i++) ce[n++] = k->buf[i];
-    // d[0..3] are outputs; nothing else is free: allocate the remaining 7 from scratch memory
-    Fr* extra = nullptr;
-    GPW_TRY(ctx->get_scratch("plonk.coset", (size_t)7 * N * sizeof(Fr), (void**)&extra));
-    for (int i = 0; i < 7; i++) ce[n++] = extra + (size_t)i * N;
-  }
+  const Fr* srcs[6] = {a_c, b_c, c_c, z_c, p2_c, pi_c};
+  Fr* ce[9];  // six coset-evaluation buffers of the proof's own polynomials (+ three more work arrays used by round 5)
+  for (int i = 0; i < 9; i++) ce[i] = k->buf[15 + i];
   for (int j = 0; j < 4; j++) {
     const Fr shift = mul(g, pow_u64(rho, (uint64_t)j));
-    for (int p = 0; p < 16; p++) {
+    for (int p = 0; p < 6; p++) {
       GPW_CUDA(cudaMemcpyAsync(ce[p], srcs[p], (size_t)N * sizeof(Fr), cudaMemcpyDeviceToDevice, st));
       k_scale_pow<<<GP, 128, 0, st>>>(ce[p], N, shift, Fr::one());
       GPW_CHECK_LAUNCH();
@@ -837,13 +847,14 @@ extern "C" int gpw_plonk_prove(gpw_plonk_key* k, const uint64_t* inputs, uint8_t
     Fr sN = shift;
     for (int i = 0; i < k->logN; i++) sN = sqr(sN);
     const Fr zh_inv = inv(sub(sN, Fr::one()));
-    CosetEvals e{ce[0], ce[1], ce[2], ce[3], ce[4], ce[5], ce[6], ce[7], ce[8], ce[9], ce[10], ce[11], ce[12], ce[13], ce[14], ce[15]};
+    Fr* const* f = k->fixed_ce + j * 10;
+    CosetEvals e{ce[0], ce[1], ce[2], ce[3], ce[4], ce[5], f[0], f[1], f[2], f[3], f[4], f[5], f[6], f[7], f[8], f[9]};
     k_quotient<<<G, 256, 0, st>>>(e, N, k->omega_pow, shift, beta, gamma, alpha, k->k1, k->k2, zh_inv, d[j]);
     GPW_CHECK_LAUNCH();
     GPW_TRY(intt(k, d[j]));
     k_scale_pow<<<GP, 128, 0, st>>>(d[j], N, inv(shift), Fr::one());
     GPW_CHECK_LAUNCH();
-    ctx->launches += 34;
+    ctx->launches += 14;
   }
   {
     Fr gN = g;
