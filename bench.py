@@ -308,7 +308,7 @@ def run_plonk(args, ctx, circ, rd, side, dev, rank, world, t_compile, t_load):
                                    % (os.path.basename(TESTDATA), key.info["gates"], key.info["logN"], key.info["logN"]),
                        "plonk": key.info, "l2_policy": "inputs_exceed_l2 (every polynomial is 1 GB)", "witness_synthesis_in_step": True,
                        "protocol_note": "published PLONK with gnark's BSB22 column; all 17 polynomials opened at zeta (no linearisation), "
-                                        "no blinding; verified by oracle/plonk.py in tests/test_gpu_plonk.py"},
+                                        "no blinding; verified by oracle/plonk_verify.py in tests/test_gpu_plonk.py"},
             "e2e": {"value": value, "unit": "proofs/s", "h2d_bytes_per_step": int(inputs.nbytes), "d2h_bytes_per_step": 1216,
                     "note": "the timed call IS the host-buffer call (gpw_plonk_prove takes host inputs and returns host bytes)"},
             "gpu_launches": int(ctx.launches - l0),

@@ -19,7 +19,7 @@
 // Differences from gnark's implementation, stated because proof bytes cannot be compared with gnark here anyway (no Go
 // toolchain): every polynomial is opened at zeta (no linearisation polynomial - 18 field elements instead of 7), no blinding
 // factors (the proof is not zero-knowledge), own transcript labels (SHA-256 / RFC 9380 hash-to-field, the library's
-// gpw_hash_to_fr). oracle/plonk.py is the verifier the tests check every proof with.
+// gpw_hash_to_fr). oracle/plonk_verify.py is the verifier the tests check every proof with.
 //
 // All polynomial work is device resident: NTTs through gpw_ntt_fr_dev, commitments through gpw_msm_g1_dev with the SRS as
 // bases, batched inversions with Montgomery's trick (8 per thread).
@@ -696,7 +696,7 @@ extern "C" int gpw_plonk_key_info(const gpw_plonk_key* k, uint64_t* info8) {
   return GPW_OK;
 }
 
-// vk bytes (own layout, documented in oracle/plonk.py): u32 logN | u32 n_public_rows | u32 has_commit | k1 | k2 | omega (32 B BE
+// vk bytes (own layout, documented in oracle/plonk_verify.py): u32 logN | u32 n_public_rows | u32 has_commit | k1 | k2 | omega (32 B BE
 // each) | 9 commitments (64 B raw each: qL qR qM qO qC Qcp S1 S2 S3) | [tau] G2 (128 B raw: X.A1 X.A0 Y.A1 Y.A0)
 extern "C" int gpw_plonk_vk_write(const gpw_plonk_key* k, uint8_t* out, size_t cap, size_t* len) {
   if (!k) return GPW_EINVAL;

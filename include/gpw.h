@@ -274,7 +274,7 @@ int gpw_hash_to_fr(const uint8_t* msg, size_t len, const char* dst, uint64_t* ou
  * five rounds of PLONK with the BSB22 commitment column, proof = 10 G1 commitments (64 B raw big-endian each: a b c P2 Z t0 t1 t2
  * W_zeta W_zeta_w) + 18 evaluations (32 B big-endian each). The protocol is the published one; it differs from gnark's
  * implementation in what is opened and in the transcript labels (header of csrc/plonk.cu) and has no blinding (not
- * zero-knowledge). oracle/plonk.py is its verifier. GPW_EUNSAT if the witness does not satisfy the system.                    */
+ * zero-knowledge). oracle/plonk_verify.py is its verifier. GPW_EUNSAT if the witness does not satisfy the system.                    */
 typedef struct gpw_plonk_key gpw_plonk_key;
 int gpw_plonk_setup(gpw_ctx* ctx, gpw_circuit* circ, const uint8_t* seed32, gpw_plonk_key** out);
 void gpw_plonk_key_free(gpw_plonk_key* k);

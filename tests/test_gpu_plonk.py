@@ -1,5 +1,5 @@
 """PLONK / KZG backend (BASELINE.json configs[3]; benchmark.go:80-190: NewKZGSRS, plonk.Setup, plonk.Prove, plonk.Verify):
-proofs made on the GPU are checked by the independent verifier oracle/plonk.py (field arithmetic on Python integers, the
+proofs made on the GPU are checked by the independent verifier oracle/plonk_verify.py (field arithmetic on Python integers, the
 pairing of oracle/pairing.py)."""
 import os
 
@@ -8,7 +8,7 @@ import pytest
 
 import gpw
 from oracle import goldilocks as ogl
-from oracle import plonk as oplonk
+from oracle import plonk_verify as oplonk
 from oracle.engine import Api
 from oracle.poseidon import BN254Chip
 
