@@ -240,3 +240,33 @@ def test_compile_cache_round_trip(lib, kats, tmp_path):
     assert not lib.ct_load(path) and b"circuit cache" in lib.ct_last_error()
     open(path, "wb").write(b"\0" * 64 + blob[64:])
     assert not lib.ct_load(path)
+
+
+def test_plonk_lowering_of_small_circuits(lib, kats):
+    # csrc/host/scs.cc (the scs.NewBuilder counterpart, benchmark.go:44-45): the compiled circuit lowered to PLONK gates. On the
+    # solved witness every gate equation holds (addition chains with the constant on qC, multiplication rows, public rows, Qcp
+    # rows for the committed range-check wires), sigma is a permutation of the 3 N slots that stays inside each variable's slots,
+    # and a wrong witness breaks gates. (The full verifier circuits are checked the same way by hand - 33.46 M gates for step,
+    # 2^25 rows - and end to end on the GPU, tests/test_gpu_plonk.py.)
+    lib.ct_scs_check.argtypes = [C.c_void_p, C.c_void_p]
+    out = [int(x) for x in kats["poseidon_gl_perm_zero"]]
+    h = lib.ct_compile_small(0)
+    assert solve(lib, h, out, [0] * 12) == (0, 0)
+    o = np.zeros(6, dtype=np.uint64)
+    lib.ct_scs_check(h, o.ctypes.data)
+    gates, nvars, logn, bad, first_bad, perm_bad = map(int, o)
+    st = stats(lib, h)
+    assert bad == 0 and perm_bad == 0
+    assert (1 << (logn - 1)) < gates <= (1 << logn) and nvars > st["wires"]
+    assert gates >= st["constraints"] + st["limb_wires"] + 65536            # one row per R1CS row and per committed wire at least
+    rc, r1cs_bad = solve(lib, h, [out[0] ^ 1] + out[1:], [0] * 12)
+    assert rc == 0 and r1cs_bad == 1
+    lib.ct_scs_check(h, o.ctypes.data)
+    assert int(o[3]) >= 1 and int(o[5]) == 0
+    lib.ct_free(h)
+    h = lib.ct_compile_small(1)                                             # Poseidon-BN254: no range checks, no Qcp rows
+    case = kats["poseidon_bn254"][0]
+    assert solve(lib, h, [int(x) for x in case["out"]], [int(x) for x in case["in"]]) == (0, 0)
+    lib.ct_scs_check(h, o.ctypes.data)
+    assert int(o[3]) == 0 and int(o[5]) == 0
+    lib.ct_free(h)
