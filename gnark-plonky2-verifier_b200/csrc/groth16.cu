@@ -192,17 +192,24 @@ extern "C" int gpw_groth16_pk_synthetic(gpw_ctx* ctx, size_t m, size_t n_pub, in
     gpw_groth16_pk_free(pk);
     return rc;
   }
-  GPW_TRY(gpw_ec_generator_multiples_dev(ctx, 1, 1, m, (uint64_t)pk->A));
-  GPW_TRY(gpw_ec_generator_multiples_dev(ctx, 1, 1 + m, m, (uint64_t)pk->B1));
-  GPW_TRY(gpw_ec_generator_multiples_dev(ctx, 1, 1 + 2 * m, m, (uint64_t)pk->K));
-  GPW_TRY(gpw_ec_generator_multiples_dev(ctx, 1, 1 + 3 * m, N - 1, (uint64_t)pk->Z));
-  GPW_TRY(gpw_ec_generator_multiples_dev(ctx, 2, 1, m, (uint64_t)pk->B2));
+  if ((rc = gpw_ec_generator_multiples_dev(ctx, 1, 1, m, (uint64_t)pk->A)) ||
+      (rc = gpw_ec_generator_multiples_dev(ctx, 1, 1 + m, m, (uint64_t)pk->B1)) ||
+      (rc = gpw_ec_generator_multiples_dev(ctx, 1, 1 + 2 * m, m, (uint64_t)pk->K)) ||
+      (rc = gpw_ec_generator_multiples_dev(ctx, 1, 1 + 3 * m, N - 1, (uint64_t)pk->Z)) ||
+      (rc = gpw_ec_generator_multiples_dev(ctx, 2, 1, m, (uint64_t)pk->B2))) {
+    gpw_groth16_pk_free(pk);  // every failure after the allocations releases the key
+    return rc;
+  }
   pk->alpha1 = host_gen_mul<Fp>(seed + 1);
   pk->beta1 = host_gen_mul<Fp>(seed + 2);
   pk->delta1 = host_gen_mul<Fp>(seed + 3);
   pk->beta2 = host_gen_mul<Fp2>(seed + 2);
   pk->delta2 = host_gen_mul<Fp2>(seed + 3);
-  GPW_CUDA(cudaStreamSynchronize(ctx->stream));
+  if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) {
+    set_error("pk_synthetic: %s", cudaGetErrorString(cudaGetLastError()));
+    gpw_groth16_pk_free(pk);
+    return GPW_ECUDA;
+  }
   *out = pk;
   return GPW_OK;
 }
