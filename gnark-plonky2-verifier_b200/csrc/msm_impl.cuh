@@ -570,7 +570,13 @@ static int msm_dev_impl(gpw_ctx* ctx, const Fr* scalars, const Affine<F>* points
     return GPW_EINVAL;
   }
   const uint32_t ntasks = (uint32_t)((max_entries + MSM_TASK - 1) / MSM_TASK);
-  const uint32_t chunk = half < 16u ? half : 16u;
+  // buckets per thread of the window reduction's first level (power of two; GPW_MSM_CHUNK overrides for experiments)
+  static const uint32_t chunk_pref = [] {
+    const char* e = getenv("GPW_MSM_CHUNK");
+    const uint32_t v = e ? (uint32_t)atoi(e) : 16u;
+    return (v >= 2 && v <= 64 && (v & (v - 1)) == 0) ? v : 16u;
+  }();
+  const uint32_t chunk = half < chunk_pref ? half : chunk_pref;
   const uint32_t nchunks = half / chunk;
 
   uint32_t *counts, *offsets, *cursor, *sorted, *tail_key, *tail_list, *ntail, *nbig, *big_list, *block_sums;
