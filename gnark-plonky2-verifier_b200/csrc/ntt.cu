@@ -318,7 +318,12 @@ static int ntt_dev_impl(gpw_ctx* ctx, Fr* data, int L, int inverse, int coset, i
   const bool dit = in_bitrev != 0;
   // split L stages into passes of <= NTT_MAX_K, avoiding a pass with lobits == 1 (needs >= 2 columns in lo)
   std::vector<int> ks;
-  {
+  if (L > 3 * NTT_MAX_K) {
+    // more than three passes: balance them (2^25: 7, 6, 6, 6) - the greedy split would end in a 2-stage pass (8, 8, 7, 2)
+    // whose 16-element tiles pay a whole trip through HBM for two butterfly stages in nearly empty CTAs
+    const int np = (L + NTT_MAX_K - 1) / NTT_MAX_K;
+    for (int i = 0; i < np; i++) ks.push_back(L / np + (i < L % np ? 1 : 0));
+  } else {
     int rem = L;
     while (rem > 0) {
       int k = rem > NTT_MAX_K ? NTT_MAX_K : rem;

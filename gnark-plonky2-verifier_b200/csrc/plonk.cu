@@ -414,6 +414,11 @@ struct gpw_plonk_key {
   // fixed_ce[j * 10 + p], 40 N-sized arrays (43 GB at 2^25) that save 40 of the 68 transforms of every proof
   Fr* fixed_ce[40] = {};
   G1Affine* srs = nullptr;  // [tau^i] G1, i < N
+  // the same SRS in the Lagrange basis, [L_i(tau)] G1: polynomials known by their values on H (the wire columns, P2) are
+  // committed from those values directly - witness values are mostly small (bits, 16-bit limbs, 64-bit field elements), so the
+  // MSM skips most digits, whereas their coefficient forms are full-width. (Generated from tau like the monomial SRS; for a
+  // ceremony SRS it would come from an inverse FFT "in the exponent".)
+  G1Affine* srs_lagrange = nullptr;
   G2Affine tau2;            // [tau] G2
   G1Affine vk_com[9];       // [qL] [qR] [qM] [qO] [qC] [Qcp] [S1] [S2] [S3]
   Fr k1, k2, omega;
@@ -498,6 +503,10 @@ struct Transcript {
 
 int commit(gpw_plonk_key* k, const Fr* coef, G1Affine* out) {
   return gpw_msm_g1_dev(k->ctx, (uint64_t)coef, (uint64_t)k->srs, k->N, 1, 0, 0, 0, (uint64_t*)out);
+}
+// the same commitment from the polynomial's values on H (Lagrange-basis SRS)
+int commit_evals(gpw_plonk_key* k, const Fr* evals, G1Affine* out) {
+  return gpw_msm_g1_dev(k->ctx, (uint64_t)evals, (uint64_t)k->srs_lagrange, k->N, 1, 0, 0, 0, (uint64_t*)out);
 }
 int intt(gpw_plonk_key* k, Fr* a) { return gpw_ntt_fr_dev(k->ctx, (uint64_t)a, k->logN, 1, 0, 0, 0); }
 int ntt(gpw_plonk_key* k, Fr* a) { return gpw_ntt_fr_dev(k->ctx, (uint64_t)a, k->logN, 0, 0, 0, 0); }
@@ -587,7 +596,7 @@ extern "C" int gpw_plonk_setup(gpw_ctx* ctx, gpw_circuit* circ, const uint8_t* s
     return fail(rc);
   std::vector<uint32_t>().swap(sigma);
   if ((rc = dalloc(k, (void**)&k->omega_pow, (size_t)N * sizeof(Fr))) || (rc = dalloc(k, (void**)&k->l0_c, (size_t)N * sizeof(Fr))) ||
-      (rc = dalloc(k, (void**)&k->srs, (size_t)N * sizeof(G1Affine))) || (rc = dalloc(k, (void**)&k->v, (size_t)k->n_vars * sizeof(Fr))) ||
+      (rc = dalloc(k, (void**)&k->srs, (size_t)N * sizeof(G1Affine))) || (rc = dalloc(k, (void**)&k->srs_lagrange, (size_t)N * sizeof(G1Affine))) || (rc = dalloc(k, (void**)&k->v, (size_t)k->n_vars * sizeof(Fr))) ||
       (rc = dalloc(k, (void**)&k->inputs_dev, (size_t)(k->n_inputs ? k->n_inputs : 1) * 32)))
     return fail(rc);
   for (int i = 0; i < 6; i++)
@@ -657,6 +666,17 @@ extern "C" int gpw_plonk_setup(gpw_ctx* ctx, gpw_circuit* circ, const uint8_t* s
     Fr* pw = k->buf[0];
     k_pow_table<<<GP, 128, 0, st>>>(pw, N, tau, Fr::one());
     k_srs_points<<<div_up(N, 128), 128, 0, st>>>(table, pw, N, k->srs);
+    {  // L_i(tau) = w^i (tau^N - 1) / (N (tau - w^i))
+      Fr tN = tau;
+      for (int i = 0; i < k->logN; i++) tN = sqr(tN);
+      const Fr c = mul(sub(tN, Fr::one()), inv(fr_u64(N)));
+      Fr* den = k->buf[1];
+      k_open_denominators<<<G, 256, 0, st>>>(k->omega_pow, N, tau, den);  // w^i - tau
+      k_batch_inv<<<div_up(div_up(N, 8), 128), 128, 0, st>>>(den, N);
+      k_mul_arrays<<<G, 256, 0, st>>>(den, k->omega_pow, N);
+      k_scale_pow<<<GP, 128, 0, st>>>(den, N, Fr::one(), neg(c));          // * -(tau^N - 1) / N
+      k_srs_points<<<div_up(N, 128), 128, 0, st>>>(table, den, N, k->srs_lagrange);
+    }
     if (cudaStreamSynchronize(st) != cudaSuccess) {
       set_error("plonk_setup: SRS generation failed: %s", cudaGetErrorString(cudaGetLastError()));
       return fail(GPW_ECUDA);
@@ -771,7 +791,7 @@ extern "C" int gpw_plonk_prove(gpw_plonk_key* k, const uint64_t* inputs, uint8_t
   GPW_CUDA(cudaMemcpyAsync(p2_c, p2_e, (size_t)N * sizeof(Fr), cudaMemcpyDeviceToDevice, st));
   GPW_TRY(intt(k, p2_c));
   if (k->has_commit) {
-    GPW_TRY(commit(k, p2_c, &com[3]));
+    GPW_TRY(commit_evals(k, p2_e, &com[3]));
     uint8_t ser[64];
     g1_be(com[3], ser);
     hash_to_fr(ser, 64, "bsb22-commitment", X);
@@ -794,7 +814,7 @@ extern "C" int gpw_plonk_prove(gpw_plonk_key* k, const uint64_t* inputs, uint8_t
   for (int i = 0; i < 3; i++) {
     GPW_CUDA(cudaMemcpyAsync(ev_c[i][1], ev_c[i][0], (size_t)N * sizeof(Fr), cudaMemcpyDeviceToDevice, st));
     GPW_TRY(intt(k, ev_c[i][1]));
-    GPW_TRY(commit(k, ev_c[i][1], &com[i]));
+    GPW_TRY(commit_evals(k, ev_c[i][0], &com[i]));
   }
   // public-input polynomial: -x_i on the public rows
   GPW_CUDA(cudaMemsetAsync(pi_c, 0, (size_t)N * sizeof(Fr), st));
