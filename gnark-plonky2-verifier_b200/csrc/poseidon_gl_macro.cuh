@@ -179,56 +179,80 @@ GPW_HD void trace_seq(uint64_t st[12], const uint64_t* T, Emit emit) {
 }
 
 #ifdef __CUDACC__
-// Warp form: lane k < 12 owns state element k; sh[12] is a shared-memory exchange buffer. Called by all 32 lanes of one
-// warp (lanes >= 12 only take part in the barriers). emit(slot, U192) must be callable concurrently from the lanes.
+// Warp form: lane k < 12 owns state element k in a register; the MDS layers mix the state with WARP SHUFFLES (the circulant
+// row of lane r reads lane (i + r) mod 12 for i = 0..11; the partial rounds broadcast lanes 1..11 to lane 0 and s0 back),
+// no shared-memory exchange and no __syncwarp. Called by all 32 lanes of one warp (lanes >= 12 only take part in the
+// shuffles). emit(slot, U192) must be callable concurrently from the lanes. `sh` is unused (kept for the callers' layout).
+__device__ __forceinline__ uint64_t shfl64(uint64_t v, int src) { return (uint64_t)__shfl_sync(0xffffffffu, (unsigned long long)v, src); }
+
 template <class Emit>
 __device__ void trace_warp(uint64_t x, uint64_t* sh, const uint64_t* __restrict__ T, Emit emit) {
+  (void)sh;
   const int lane = (int)(threadIdx.x & 31u);
   const bool on = lane < 12;
+  const int r = on ? lane : 0;
+  // sum_i st[(i + r) % 12] C[i] + st[r] D[r] with the state spread over lanes 0..11
+  auto mds_row_shfl = [&](uint64_t own) {
+    U192 acc = {{0, 0, 0}};
+    uint64_t v[12];
+#pragma unroll
+    for (int i = 0; i < 12; i++) {  // twelve independent shuffles in flight, then the multiply-accumulate chain
+      int src = i + r;
+      src = src >= 12 ? src - 12 : src;
+      v[i] = shfl64(own, src);
+    }
+#pragma unroll
+    for (int i = 0; i < 12; i++) mac(acc, v[i], T[T_CIRC + i]);
+    mac(acc, own, T[T_DIAG + r]);
+    return acc;
+  };
   auto full_round = [&](int f) {
     const uint32_t B = full_base(f);
     if (on) {
       x = addconst_emit(x, T[T_RC + lane + 12 * full_rc(f)], B + 2 * lane, emit);
       x = sbox_emit(x, B + 24 + 8 * lane, emit);
-      sh[lane] = x;
     }
-    __syncwarp();
-    if (on) x = reduce_emit(mds_row(lane, sh, T), B + 120 + 2 * lane, emit);
-    __syncwarp();
+    const U192 row = mds_row_shfl(x);
+    if (on) x = reduce_emit(row, B + 120 + 2 * lane, emit);
   };
 #pragma unroll 1
   for (int f = 0; f < 4; f++) full_round(f);
   {
     const uint32_t B = PARTIAL_BASE;
-    if (on) {
-      x = addconst_emit(x, T[T_FIRST + lane], B + 2 * lane, emit);
-      sh[lane] = x;
+    if (on) x = addconst_emit(x, T[T_FIRST + lane], B + 2 * lane, emit);
+    {  // partial_init_row(lane): lane 0 keeps st[0], lane d sums st[r] INIT[(r - 1) 11 + d - 1] over r = 1..11
+      U192 acc = {{0, 0, 0}};
+#pragma unroll 1
+      for (int rr = 1; rr < 12; rr++) {
+        const uint64_t v = shfl64(x, rr);
+        if (on && lane > 0) mac(acc, v, T[T_INIT + (rr - 1) * 11 + (lane - 1)]);
+      }
+      if (on) x = reduce_emit(lane == 0 ? u192(x) : acc, B + 24 + 2 * lane, emit);
     }
-    __syncwarp();
-    if (on) x = reduce_emit(partial_init_row(lane, sh, T), B + 24 + 2 * lane, emit);
-    __syncwarp();
 #pragma unroll 1
     for (int i = 0; i < 22; i++) {
       const uint32_t Bi = B + 48 + 36 * i;
-      if (on && lane > 0) sh[lane] = x;
-      __syncwarp();
+      U192 d = {{0, 0, 0}};
+      uint64_t vs[11];
+#pragma unroll
+      for (int j = 1; j < 12; j++) vs[j - 1] = shfl64(x, j);
       if (lane == 0) {
-        uint64_t s0 = sbox_emit(x, Bi, emit);
+#pragma unroll
+        for (int j = 1; j < 12; j++) mac(d, vs[j - 1], T[T_WHATS + i * 11 + j - 1]);
+      }
+      uint64_t s0 = 0;
+      if (lane == 0) {
+        s0 = sbox_emit(x, Bi, emit);
         s0 = addconst_emit(s0, T[T_PRC + i], Bi + 8, emit);
-        U192 d = {{0, 0, 0}};
-#pragma unroll 1
-        for (int j = 1; j < 12; j++) mac(d, sh[j], T[T_WHATS + i * 11 + j - 1]);
         mac(d, s0, MDS0TO0);
         x = reduce_emit(d, Bi + 10, emit);
-        sh[0] = s0;
       }
-      __syncwarp();
+      s0 = shfl64(s0, 0);
       if (on) {
         U192 v = u192(x);  // lane 0: d (already reduced: q = 0)
-        if (lane > 0) mac(v, sh[0], T[T_VS + i * 11 + lane - 1]);
+        if (lane > 0) mac(v, s0, T[T_VS + i * 11 + lane - 1]);
         x = reduce_emit(v, Bi + 12 + 2 * lane, emit);
       }
-      __syncwarp();
     }
   }
 #pragma unroll 1
