@@ -150,7 +150,8 @@ static void host_mul(int impl, const uint64_t* a, const uint64_t* b, uint64_t* o
     Fe<P> x, y;
     memcpy(&x, a + 4 * i, 32);
     memcpy(&y, b + 4 * i, 32);
-    Fe<P> z = impl == 0 ? mont_mul_wide(x, y) : mont_mul_portable(x, y);
+    // impl 0: even/odd IMAD.WIDE schedule (host emulation), 1: plain CIOS, 2: dedicated squaring of a (b ignored)
+    Fe<P> z = impl == 0 ? mont_mul_wide(x, y) : impl == 2 ? mont_sqr_wide(x) : mont_mul_portable(x, y);
     memcpy(o + 4 * i, &z, 32);
   }
 }
@@ -314,6 +315,8 @@ __global__ void k_selftest_mul(const Fe<P>* a, const Fe<P>* b, Fe<P>* o_wide, Fe
   o_wide[i] = mont_mul_wide(a[i], b[i]);
   o_port[i] = mont_mul_portable(a[i], b[i]);
   o_addsub[i] = sub(add(a[i], b[i]), neg(b[i]));  // a + 2b
+  // dedicated squaring against the general multiplication (both operands): a mismatch poisons the wide result
+  if (mont_sqr_wide(a[i]) != mont_mul_wide(a[i], a[i]) || mont_sqr_wide(b[i]) != mont_mul_wide(b[i], b[i])) o_wide[i] = Fe<P>::zero();
 }
 
 template <class P>

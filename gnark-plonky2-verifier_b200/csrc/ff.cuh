@@ -429,6 +429,18 @@ GPW_HD void mul_acc(uint32_t* e, uint32_t* o, const uint32_t* a, uint32_t bi) {
 #endif
 }
 
+// lo, hi = a * b as ONE 32 x 32 -> 64 multiplication (mul.wide.u32 -> IMAD.WIDE.U32; a separate a * b and __umulhi(a, b)
+// compile to an IMAD plus an IMAD.HI.U32 - two trips through the pipe that bounds every kernel of the path)
+GPW_HD void mulwide32(uint32_t a, uint32_t b, uint32_t& lo, uint32_t& hi) {
+#ifdef __CUDA_ARCH__
+  asm("{\n\t.reg .u64 t;\n\tmul.wide.u32 t, %2, %3;\n\tmov.b64 {%0, %1}, t;\n\t}" : "=r"(lo), "=r"(hi) : "r"(a), "r"(b));
+#else
+  const uint64_t p = (uint64_t)a * b;
+  lo = (uint32_t)p;
+  hi = (uint32_t)(p >> 32);
+#endif
+}
+
 GPW_HD uint32_t mulhi32(uint32_t a, uint32_t b) {
 #ifdef __CUDA_ARCH__
   return __umulhi(a, b);
@@ -445,10 +457,8 @@ GPW_HD Fe<P> mont_mul_wide(const Fe<P>& a, const Fe<P>& b) {
   // iteration 0: plain products, no accumulation
 #pragma unroll
   for (int j = 0; j < 8; j += 2) {
-    ev[j] = a.l[j] * b.l[0];
-    ev[j + 1] = detail::mulhi32(a.l[j], b.l[0]);
-    od[j] = a.l[j + 1] * b.l[0];
-    od[j + 1] = detail::mulhi32(a.l[j + 1], b.l[0]);
+    detail::mulwide32(a.l[j], b.l[0], ev[j], ev[j + 1]);
+    detail::mulwide32(a.l[j + 1], b.l[0], od[j], od[j + 1]);
   }
   detail::redc_step<P>(ev, od, ev[0] * P::M0);
 #pragma unroll
@@ -498,10 +508,8 @@ GPW_HD Fe<P> mont_mul2(const Fe<P>& a, const Fe<P>& b, const Fe<P>& c, const Fe<
   uint32_t ev[8], od[8];
 #pragma unroll
   for (int j = 0; j < 8; j += 2) {
-    ev[j] = a.l[j] * b.l[0];
-    ev[j + 1] = detail::mulhi32(a.l[j], b.l[0]);
-    od[j] = a.l[j + 1] * b.l[0];
-    od[j + 1] = detail::mulhi32(a.l[j + 1], b.l[0]);
+    detail::mulwide32(a.l[j], b.l[0], ev[j], ev[j + 1]);
+    detail::mulwide32(a.l[j + 1], b.l[0], od[j], od[j + 1]);
   }
   detail::mul_acc(ev, od, c.l, d.l[0]);
   detail::redc_step<P>(ev, od, ev[0] * P::M0);
@@ -543,6 +551,327 @@ GPW_HD Fe<P> mont_mul2(const Fe<P>& a, const Fe<P>& b, const Fe<P>& c, const Fe<
   return reduce_once(r);
 }
 
+
+// ---- Montgomery squaring -------------------------------------------------------------------------------------------
+// a^2 = D + 2 S with D = sum a_i^2 2^(64 i) and S = sum_{i<j} a_i a_j 2^(32 (i+j)): 28 + 8 = 36 IMAD.WIDE for the 512-bit
+// square instead of 64, then a plain REDC of the 16 limbs with the same even/odd reduction rows as mont_mul_wide
+// (8 x 8 = 64 IMAD.WIDE): 100 instead of 128 IMAD.WIDE per squaring. The extra work (merging the even / odd cross sums,
+// doubling by funnel shifts, feeding the upper limbs into the reduction window) is ~110 carry-chain additions on the ALU
+// pipe, which the IMAD-bound group-addition kernels have to spare.
+// S is split like the products of mont_mul_wide: cross products a_i a_j with i + j odd (one even, one odd limb: the 4 x 4
+// product of the even limbs by the odd limbs) live at odd limb offsets (array o16), those with i + j even at even offsets
+// (array e16). Every row below is ordered so that its last pair is fresh (zero) or its carry lands on a fresh limb: no
+// carry ever has to ripple further.
+namespace detail {
+
+// o-row: x[0..5] += (a0, a2, a4) * m (three pairs), x[6..7] = a6 * m + carry   (x = o16 + 2 v)
+GPW_HD void sqr_row4(uint32_t* x, uint32_t a0, uint32_t a2, uint32_t a4, uint32_t a6, uint32_t m) {
+#ifdef __CUDA_ARCH__
+  asm("mad.lo.cc.u32   %0, %8,  %12, %0;\n\t"
+      "madc.hi.cc.u32  %1, %8,  %12, %1;\n\t"
+      "madc.lo.cc.u32  %2, %9,  %12, %2;\n\t"
+      "madc.hi.cc.u32  %3, %9,  %12, %3;\n\t"
+      "madc.lo.cc.u32  %4, %10, %12, %4;\n\t"
+      "madc.hi.cc.u32  %5, %10, %12, %5;\n\t"
+      "madc.lo.cc.u32  %6, %11, %12, 0;\n\t"
+      "madc.hi.u32     %7, %11, %12, 0;"
+      : "+r"(x[0]), "+r"(x[1]), "+r"(x[2]), "+r"(x[3]), "+r"(x[4]), "+r"(x[5]), "=r"(x[6]), "=r"(x[7])
+      : "r"(a0), "r"(a2), "r"(a4), "r"(a6), "r"(m));
+#else
+  CC k;
+  x[0] = k.mad_lo_cc(a0, m, x[0]);
+  x[1] = k.madc_hi_cc(a0, m, x[1]);
+  x[2] = k.madc_lo_cc(a2, m, x[2]);
+  x[3] = k.madc_hi_cc(a2, m, x[3]);
+  x[4] = k.madc_lo_cc(a4, m, x[4]);
+  x[5] = k.madc_hi_cc(a4, m, x[5]);
+  x[6] = k.madc_lo_cc(a6, m, 0);
+  x[7] = k.madc_hi(a6, m, 0);
+#endif
+}
+
+// x[0..3] += (b0, b1) * m, x[4..5] = b2 * m + carry
+GPW_HD void sqr_row3(uint32_t* x, uint32_t b0, uint32_t b1, uint32_t b2, uint32_t m) {
+#ifdef __CUDA_ARCH__
+  asm("mad.lo.cc.u32   %0, %6, %9, %0;\n\t"
+      "madc.hi.cc.u32  %1, %6, %9, %1;\n\t"
+      "madc.lo.cc.u32  %2, %7, %9, %2;\n\t"
+      "madc.hi.cc.u32  %3, %7, %9, %3;\n\t"
+      "madc.lo.cc.u32  %4, %8, %9, 0;\n\t"
+      "madc.hi.u32     %5, %8, %9, 0;"
+      : "+r"(x[0]), "+r"(x[1]), "+r"(x[2]), "+r"(x[3]), "=r"(x[4]), "=r"(x[5])
+      : "r"(b0), "r"(b1), "r"(b2), "r"(m));
+#else
+  CC k;
+  x[0] = k.mad_lo_cc(b0, m, x[0]);
+  x[1] = k.madc_hi_cc(b0, m, x[1]);
+  x[2] = k.madc_lo_cc(b1, m, x[2]);
+  x[3] = k.madc_hi_cc(b1, m, x[3]);
+  x[4] = k.madc_lo_cc(b2, m, 0);
+  x[5] = k.madc_hi(b2, m, 0);
+#endif
+}
+
+// x[0..3] += (b0, b1) * m, x[4] = carry
+GPW_HD void sqr_row2c(uint32_t* x, uint32_t b0, uint32_t b1, uint32_t m) {
+#ifdef __CUDA_ARCH__
+  asm("mad.lo.cc.u32   %0, %5, %7, %0;\n\t"
+      "madc.hi.cc.u32  %1, %5, %7, %1;\n\t"
+      "madc.lo.cc.u32  %2, %6, %7, %2;\n\t"
+      "madc.hi.cc.u32  %3, %6, %7, %3;\n\t"
+      "addc.u32        %4, 0, 0;"
+      : "+r"(x[0]), "+r"(x[1]), "+r"(x[2]), "+r"(x[3]), "=r"(x[4])
+      : "r"(b0), "r"(b1), "r"(m));
+#else
+  CC k;
+  x[0] = k.mad_lo_cc(b0, m, x[0]);
+  x[1] = k.madc_hi_cc(b0, m, x[1]);
+  x[2] = k.madc_lo_cc(b1, m, x[2]);
+  x[3] = k.madc_hi_cc(b1, m, x[3]);
+  x[4] = k.addc(0, 0);
+#endif
+}
+
+// x[0..2] += (b0, b1) * m with x[3] fresh: x[0..1] += b0 m, x[2] = lo(b1 m) + x[2] + carry, x[3] = hi(b1 m) + carry
+GPW_HD void sqr_row2f(uint32_t* x, uint32_t b0, uint32_t b1, uint32_t m) {
+#ifdef __CUDA_ARCH__
+  asm("mad.lo.cc.u32   %0, %4, %6, %0;\n\t"
+      "madc.hi.cc.u32  %1, %4, %6, %1;\n\t"
+      "madc.lo.cc.u32  %2, %5, %6, %2;\n\t"
+      "madc.hi.u32     %3, %5, %6, 0;"
+      : "+r"(x[0]), "+r"(x[1]), "+r"(x[2]), "=r"(x[3])
+      : "r"(b0), "r"(b1), "r"(m));
+#else
+  CC k;
+  x[0] = k.mad_lo_cc(b0, m, x[0]);
+  x[1] = k.madc_hi_cc(b0, m, x[1]);
+  x[2] = k.madc_lo_cc(b1, m, x[2]);
+  x[3] = k.madc_hi(b1, m, 0);
+#endif
+}
+
+// x[0..1] += b0 * m, x[2] = carry
+GPW_HD void sqr_row1c(uint32_t* x, uint32_t b0, uint32_t m) {
+#ifdef __CUDA_ARCH__
+  asm("mad.lo.cc.u32   %0, %3, %4, %0;\n\t"
+      "madc.hi.cc.u32  %1, %3, %4, %1;\n\t"
+      "addc.u32        %2, 0, 0;"
+      : "+r"(x[0]), "+r"(x[1]), "=r"(x[2])
+      : "r"(b0), "r"(m));
+#else
+  CC k;
+  x[0] = k.mad_lo_cc(b0, m, x[0]);
+  x[1] = k.madc_hi_cc(b0, m, x[1]);
+  x[2] = k.addc(0, 0);
+#endif
+}
+
+// x[0] += lo(b0 m), x[1] = hi(b0 m) + carry   (x[1] fresh)
+GPW_HD void sqr_row1f(uint32_t* x, uint32_t b0, uint32_t m) {
+#ifdef __CUDA_ARCH__
+  asm("mad.lo.cc.u32   %0, %2, %3, %0;\n\t"
+      "madc.hi.u32     %1, %2, %3, 0;"
+      : "+r"(x[0]), "=r"(x[1])
+      : "r"(b0), "r"(m));
+#else
+  CC k;
+  x[0] = k.mad_lo_cc(b0, m, x[0]);
+  x[1] = k.madc_hi(b0, m, 0);
+#endif
+}
+
+// s[1..15] = e[1..15] + o[0..14] (the odd-offset sum shifted up by one limb); e[0] = e[1] = 0, o[14] = 0 on entry.
+// Two asm statements of 7 limbs (operand-count limit); the carry between them is re-created by c + 0xffffffff.
+GPW_HD void sqr_merge(uint32_t* s, const uint32_t* e, const uint32_t* o) {
+  s[0] = 0;
+  s[1] = o[0];
+#ifdef __CUDA_ARCH__
+  uint32_t c;
+  asm("add.cc.u32   %0, %8,  %15;\n\t"
+      "addc.cc.u32  %1, %9,  %16;\n\t"
+      "addc.cc.u32  %2, %10, %17;\n\t"
+      "addc.cc.u32  %3, %11, %18;\n\t"
+      "addc.cc.u32  %4, %12, %19;\n\t"
+      "addc.cc.u32  %5, %13, %20;\n\t"
+      "addc.cc.u32  %6, %14, %21;\n\t"
+      "addc.u32     %7, 0, 0;"
+      : "=r"(s[2]), "=r"(s[3]), "=r"(s[4]), "=r"(s[5]), "=r"(s[6]), "=r"(s[7]), "=r"(s[8]), "=r"(c)
+      : "r"(e[2]), "r"(e[3]), "r"(e[4]), "r"(e[5]), "r"(e[6]), "r"(e[7]), "r"(e[8]),
+        "r"(o[1]), "r"(o[2]), "r"(o[3]), "r"(o[4]), "r"(o[5]), "r"(o[6]), "r"(o[7]));
+  asm("add.cc.u32   %0, %7,  0xffffffff;\n\t"
+      "addc.cc.u32  %0, %8,  %14;\n\t"
+      "addc.cc.u32  %1, %9,  %15;\n\t"
+      "addc.cc.u32  %2, %10, %16;\n\t"
+      "addc.cc.u32  %3, %11, %17;\n\t"
+      "addc.cc.u32  %4, %12, %18;\n\t"
+      "addc.cc.u32  %5, %13, %19;\n\t"
+      "addc.u32     %6, 0, 0;"
+      : "=&r"(s[9]), "=&r"(s[10]), "=&r"(s[11]), "=&r"(s[12]), "=&r"(s[13]), "=&r"(s[14]), "=&r"(s[15])
+      : "r"(c), "r"(e[9]), "r"(e[10]), "r"(e[11]), "r"(e[12]), "r"(e[13]), "r"(e[14]),
+        "r"(o[8]), "r"(o[9]), "r"(o[10]), "r"(o[11]), "r"(o[12]), "r"(o[13]));
+#else
+  CC k;
+  s[2] = k.add_cc(e[2], o[1]);
+  for (int i = 3; i <= 14; i++) {
+    uint64_t v = (uint64_t)e[i] + o[i - 1] + k.c;
+    s[i] = (uint32_t)v;
+    k.c = (uint32_t)(v >> 32);
+  }
+  s[15] = k.c;
+#endif
+}
+
+// t[0..15] += sum a_i^2 2^(64 i)   (t = 2 S < 2^512 - a^2: the top carry is zero)
+GPW_HD void sqr_diag(uint32_t* t, const uint32_t* a) {
+#ifdef __CUDA_ARCH__
+  asm("mad.lo.cc.u32   %0,  %16, %16, %0;\n\t"
+      "madc.hi.cc.u32  %1,  %16, %16, %1;\n\t"
+      "madc.lo.cc.u32  %2,  %17, %17, %2;\n\t"
+      "madc.hi.cc.u32  %3,  %17, %17, %3;\n\t"
+      "madc.lo.cc.u32  %4,  %18, %18, %4;\n\t"
+      "madc.hi.cc.u32  %5,  %18, %18, %5;\n\t"
+      "madc.lo.cc.u32  %6,  %19, %19, %6;\n\t"
+      "madc.hi.cc.u32  %7,  %19, %19, %7;\n\t"
+      "madc.lo.cc.u32  %8,  %20, %20, %8;\n\t"
+      "madc.hi.cc.u32  %9,  %20, %20, %9;\n\t"
+      "madc.lo.cc.u32  %10, %21, %21, %10;\n\t"
+      "madc.hi.cc.u32  %11, %21, %21, %11;\n\t"
+      "madc.lo.cc.u32  %12, %22, %22, %12;\n\t"
+      "madc.hi.cc.u32  %13, %22, %22, %13;\n\t"
+      "madc.lo.cc.u32  %14, %23, %23, %14;\n\t"
+      "madc.hi.u32     %15, %23, %23, %15;"
+      : "+r"(t[0]), "+r"(t[1]), "+r"(t[2]), "+r"(t[3]), "+r"(t[4]), "+r"(t[5]), "+r"(t[6]), "+r"(t[7]), "+r"(t[8]), "+r"(t[9]),
+        "+r"(t[10]), "+r"(t[11]), "+r"(t[12]), "+r"(t[13]), "+r"(t[14]), "+r"(t[15])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(a[4]), "r"(a[5]), "r"(a[6]), "r"(a[7]));
+#else
+  CC k;
+  for (int i = 0; i < 8; i++) {
+    t[2 * i] = i == 0 ? k.mad_lo_cc(a[i], a[i], t[0]) : k.madc_lo_cc(a[i], a[i], t[2 * i]);
+    t[2 * i + 1] = i == 7 ? k.madc_hi(a[i], a[i], t[15]) : k.madc_hi_cc(a[i], a[i], t[2 * i + 1]);
+  }
+#endif
+}
+
+// Reduction window moves up by one limb: e[0] += o[1]; o = (o >> 64) with the next limb `tn` of the square entering at
+// window position 7 (o[6]) and the last carry at position 8 (o[7]).  (e, o) = (previous odd, previous even) accumulator.
+GPW_HD void redc_shift_in(uint32_t* e, uint32_t* o, uint32_t tn) {
+#ifdef __CUDA_ARCH__
+  asm("add.cc.u32   %0, %0, %2;\n\t"
+      "addc.cc.u32  %1, %3, 0;\n\t"
+      "addc.cc.u32  %2, %4, 0;\n\t"
+      "addc.cc.u32  %3, %5, 0;\n\t"
+      "addc.cc.u32  %4, %6, 0;\n\t"
+      "addc.cc.u32  %5, %7, 0;\n\t"
+      "addc.cc.u32  %6, %8, 0;\n\t"
+      "addc.cc.u32  %7, %9, 0;\n\t"
+      "addc.u32     %8, 0, 0;"
+      : "+r"(e[0]), "+r"(o[0]), "+r"(o[1]), "+r"(o[2]), "+r"(o[3]), "+r"(o[4]), "+r"(o[5]), "+r"(o[6]), "+r"(o[7])
+      : "r"(tn));
+#else
+  CC k;
+  e[0] = k.add_cc(e[0], o[1]);
+  for (int i = 0; i < 6; i++) {
+    uint64_t v = (uint64_t)o[i + 2] + k.c;
+    o[i] = (uint32_t)v;
+    k.c = (uint32_t)(v >> 32);
+  }
+  uint64_t v = (uint64_t)tn + k.c;
+  o[6] = (uint32_t)v;
+  o[7] = (uint32_t)(v >> 32);
+#endif
+}
+
+}  // namespace detail
+
+template <class P>
+GPW_HD Fe<P> mont_sqr_wide(const Fe<P>& a) {
+  const uint32_t* x = a.l;
+  // odd-offset cross sum: (a0, a2, a4, a6) x (a1, a3, a5, a7); o16[k] has weight 2^(32 (k + 1))
+  uint32_t o16[14];
+#pragma unroll
+  for (int j = 0; j < 4; j++) {
+    detail::mulwide32(x[2 * j], x[1], o16[2 * j], o16[2 * j + 1]);
+  }
+  detail::sqr_row4(o16 + 2, x[0], x[2], x[4], x[6], x[3]);
+  detail::sqr_row4(o16 + 4, x[0], x[2], x[4], x[6], x[5]);
+  detail::sqr_row4(o16 + 6, x[0], x[2], x[4], x[6], x[7]);
+  // even-offset cross sum: even limbs among themselves, odd limbs among themselves; e16[k] has weight 2^(32 k)
+  uint32_t e16[15];
+  e16[0] = e16[1] = 0;
+  e16[14] = 0;
+#pragma unroll
+  for (int j = 1; j < 4; j++) {  // a0 x (a2, a4, a6) at pairs 1..3
+    detail::mulwide32(x[0], x[2 * j], e16[2 * j], e16[2 * j + 1]);
+  }
+  detail::sqr_row3(e16 + 4, x[3], x[5], x[7], x[1]);  // a1 x (a3, a5, a7) at pairs 2..4   (8, 9 fresh)
+  detail::sqr_row2c(e16 + 6, x[4], x[6], x[2]);       // a2 x (a4, a6) at pairs 3, 4       (carry -> 10)
+  detail::sqr_row2f(e16 + 8, x[5], x[7], x[3]);       // a3 x (a5, a7) at pairs 4, 5       (11 fresh)
+  detail::sqr_row1c(e16 + 10, x[6], x[4]);            // a4 x a6 at pair 5                 (carry -> 12)
+  detail::sqr_row1f(e16 + 12, x[7], x[5]);            // a5 x a7 at pair 6                 (13 fresh)
+  // S = e16 + (o16 << 32), T = 2 S + D
+  uint32_t s[16], t[16];
+  {
+    uint32_t o15[15];
+#pragma unroll
+    for (int i = 0; i < 14; i++) o15[i] = o16[i];
+    o15[14] = 0;
+    detail::sqr_merge(s, e16, o15);
+  }
+  t[0] = 0;
+#pragma unroll
+  for (int i = 1; i < 16; i++) {
+#ifdef __CUDA_ARCH__
+    t[i] = __funnelshift_l(s[i - 1], s[i], 1);
+#else
+    t[i] = (s[i] << 1) | (s[i - 1] >> 31);
+#endif
+  }
+  detail::sqr_diag(t, x);
+  // REDC: window (ev, od) as in mont_mul_wide; t[8] starts at window position 8 (od[7])... see redc_shift_in
+  uint32_t ev[8], od[8];
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    ev[i] = t[i];
+    od[i] = 0;
+  }
+  detail::redc_step<P>(ev, od, ev[0] * P::M0);
+#pragma unroll
+  for (int i = 1; i < 8; i += 2) {
+    detail::redc_shift_in(od, ev, t[7 + i]);
+    detail::redc_step<P>(od, ev, od[0] * P::M0);
+    if (i + 1 < 8) {
+      detail::redc_shift_in(ev, od, t[8 + i]);
+      detail::redc_step<P>(ev, od, ev[0] * P::M0);
+    }
+  }
+  // (E, O) = (od, ev): result[k] = O[k] + E[k + 1], plus the square's top limb t[15] at position 7
+  Fe<P> r;
+#ifdef __CUDA_ARCH__
+  asm("add.cc.u32  %0, %8,  %16;\n\t"
+      "addc.cc.u32 %1, %9,  %17;\n\t"
+      "addc.cc.u32 %2, %10, %18;\n\t"
+      "addc.cc.u32 %3, %11, %19;\n\t"
+      "addc.cc.u32 %4, %12, %20;\n\t"
+      "addc.cc.u32 %5, %13, %21;\n\t"
+      "addc.cc.u32 %6, %14, %22;\n\t"
+      "addc.u32    %7, %15, %23;"
+      : "=r"(r.l[0]), "=r"(r.l[1]), "=r"(r.l[2]), "=r"(r.l[3]), "=r"(r.l[4]), "=r"(r.l[5]), "=r"(r.l[6]),
+        "=r"(r.l[7])
+      : "r"(ev[0]), "r"(ev[1]), "r"(ev[2]), "r"(ev[3]), "r"(ev[4]), "r"(ev[5]), "r"(ev[6]), "r"(ev[7]),
+        "r"(od[1]), "r"(od[2]), "r"(od[3]), "r"(od[4]), "r"(od[5]), "r"(od[6]), "r"(od[7]), "r"(t[15]));
+#else
+  detail::CC k;
+  r.l[0] = k.add_cc(ev[0], od[1]);
+  for (int i = 1; i < 7; i++) {
+    uint64_t v = (uint64_t)ev[i] + od[i + 1] + k.c;
+    r.l[i] = (uint32_t)v;
+    k.c = (uint32_t)(v >> 32);
+  }
+  r.l[7] = ev[7] + t[15] + k.c;
+#endif
+  return reduce_once(r);
+}
+
 #ifndef GPW_FF_PORTABLE_MUL
 template <class P>
 GPW_HD Fe<P> mul(const Fe<P>& a, const Fe<P>& b) {
@@ -557,7 +886,11 @@ GPW_HD Fe<P> mul(const Fe<P>& a, const Fe<P>& b) {
 
 template <class P>
 GPW_HD Fe<P> sqr(const Fe<P>& a) {
+#ifndef GPW_FF_PORTABLE_MUL
+  return mont_sqr_wide(a);
+#else
   return mul(a, a);
+#endif
 }
 
 // a b - c d: one Montgomery reduction for both products (mont_mul2 with the second product negated through c)

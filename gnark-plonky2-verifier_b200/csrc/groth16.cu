@@ -29,6 +29,30 @@ __global__ void k_h_pointwise(Fr* __restrict__ a, const Fr* __restrict__ b, cons
   stfr(a + i, mul(sub(mul(ldfr(a + i), ldfr(b + i)), ldfr(c + i)), k));
 }
 
+// a[i] *= b[i]
+__global__ void k_fr_mul_inplace(Fr* __restrict__ a, const Fr* __restrict__ b, size_t n) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  stfr(a + i, mul(ldfr(a + i), ldfr(b + i)));
+}
+
+// computeH, last step: v and c hold polynomial coefficients in BIT-REVERSED order; h = (v - c) * k is left in v in natural
+// order (the subtraction, the scaling and the bit-reversal permutation in one pass)
+__global__ void k_h_finish_bitrev(Fr* __restrict__ v, const Fr* __restrict__ c, int L, Fr k) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (1u << L)) return;
+  const uint32_t j = L ? (__brev(i) >> (32 - L)) : 0u;
+  if (i > j) return;
+  const Fr xi = mul(sub(ldfr(v + i), ldfr(c + i)), k);
+  if (i == j) {
+    stfr(v + i, xi);
+    return;
+  }
+  const Fr xj = mul(sub(ldfr(v + j), ldfr(c + j)), k);
+  stfr(v + i, xj);
+  stfr(v + j, xi);
+}
+
 __global__ void k_fr_convert(Fr* __restrict__ a, size_t n, int to) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
@@ -230,19 +254,37 @@ extern "C" int gpw_groth16_compute_h_dev(gpw_ctx* ctx, uint64_t a_dev, uint64_t 
     return GPW_EINVAL;
   }
   const size_t N = (size_t)1 << logN;
-  // evaluations on H -> coefficients (bit-reversed) -> evaluations on the coset g.H (natural)
-  uint64_t v[3] = {a_dev, b_dev, c_dev};
-  for (int i = 0; i < 3; i++) {
+  if (logN < 0 || logN > 27) {
+    set_error("compute_h: logN=%d out of range", logN);
+    return GPW_EINVAL;
+  }
+  GPW_CUDA(cudaSetDevice(ctx->device));
+  // gnark's computeH transforms a, b AND c to the coset g.H (3 inverse + 3 coset-forward transforms), forms
+  // (A.B - C) / Z_H there and goes back (1 coset-inverse): 7 transforms. The same h with 6: let W = A B = lo + X^N hi.
+  // The coset-inverse transform of the pointwise products A(g w^i) B(g w^i) is V = lo + g^N hi (degree < N, since
+  // (g w^i)^N = g^N); on H the products are the c_i of a satisfied system, so C = lo + hi; hence
+  //   h = (A B - C) / (X^N - 1) = hi = (V - C) / (g^N - 1),
+  // and C (coefficients) is one inverse transform of c - its trip to the coset and back is the identity and is skipped.
+  // Field element for field element gnark's h (the coset-inverse transform is linear); an unsatisfied system never
+  // reaches this point as a proof (GPW_EUNSAT).
+  // a, b: evaluations on H -> coefficients (bit-reversed) -> evaluations on the coset g.H (natural)
+  uint64_t v[2] = {a_dev, b_dev};
+  for (int i = 0; i < 2; i++) {
     GPW_TRY(gpw_ntt_fr_dev(ctx, v[i], logN, /*inverse*/ 1, /*coset*/ 0, /*in_bitrev*/ 0, /*out_bitrev*/ 1));
     GPW_TRY(gpw_ntt_fr_dev(ctx, v[i], logN, 0, 1, 1, 0));
   }
+  k_fr_mul_inplace<<<div_up(N, 256), 256, 0, ctx->stream>>>((Fr*)a_dev, (const Fr*)b_dev, N);
+  GPW_CHECK_LAUNCH();
+  GPW_TRY(gpw_ntt_fr_dev(ctx, a_dev, logN, 1, 1, 0, 1));  // V, bit-reversed
+  GPW_TRY(gpw_ntt_fr_dev(ctx, c_dev, logN, 1, 0, 0, 1));  // C, bit-reversed
   // Z_H(g w^k) = g^N - 1 on the whole coset
   Fr g = fr_from_u64_host(5);
   Fr gN = g;
   for (int i = 0; i < logN; i++) gN = sqr(gN);
   Fr zinv = inv(sub(gN, Fr::one()));
-  GPW_TRY(gpw_fr_h_pointwise_dev(ctx, a_dev, b_dev, c_dev, N, reinterpret_cast<const uint64_t*>(&zinv)));
-  GPW_TRY(gpw_ntt_fr_dev(ctx, a_dev, logN, 1, 1, 0, 0));
+  k_h_finish_bitrev<<<div_up(N, 256), 256, 0, ctx->stream>>>((Fr*)a_dev, (const Fr*)c_dev, logN, zinv);
+  GPW_CHECK_LAUNCH();
+  ctx->launches += 2;
   return GPW_OK;
 }
 

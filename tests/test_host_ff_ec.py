@@ -33,6 +33,32 @@ def test_mont_mul_matches_bigint(field, impl):
 
 
 @pytest.mark.parametrize("field", [0, 1])
+def test_dedicated_squaring_matches_bigint(field):
+    # mont_sqr_wide (36 + 64 IMAD.WIDE: cross products once, doubled, plain REDC) - host emulation of the GPU schedule.
+    # Limb patterns of all-ones / single bits exercise every carry of the cross-sum rows, the merge and the doubling.
+    rng = random.Random(300 + field)
+    mod = MODS[field]
+    a = _rand_elems(rng, mod, 3000)
+    special = [mod // 2, mod // 2 + 1, (1 << 253) - 1, (1 << 224) - 1, (1 << 192) - 1, (1 << 32) - 1, 1 << 31, 1 << 63, 1 << 252,
+               0xffffffff00000000ffffffff00000000ffffffff00000000ffffffff % mod,
+               0x00000000ffffffff00000000ffffffff00000000ffffffff00000000ffffffff % mod]
+    for k in range(8):
+        special.append(0xffffffff << (32 * k) if k < 7 else 0x0fffffff << 224)
+        special.append(((1 << 254) - 1) ^ (0xffffffff << (32 * k)))
+    special = [x % mod for x in special]
+    a[4:4 + len(special)] = special
+    # canonical inputs near the modulus matter, and so do Montgomery forms: feed the raw integers as limbs as well
+    raw = gpw.ints_to_limbs(a)
+    am = gpw.host_ff_to_mont(field, raw)
+    for limbs in (am, raw):
+        sq = gpw.limbs_to_ints(gpw.host_ff_mul(field, 2, limbs, limbs))
+        ref = gpw.limbs_to_ints(gpw.host_ff_mul(field, 1, limbs, limbs))
+        assert sq == ref
+    got = gpw.limbs_to_ints(gpw.host_ff_from_mont(field, gpw.host_ff_mul(field, 2, am, am)))
+    assert got == [x * x % mod for x in a]
+
+
+@pytest.mark.parametrize("field", [0, 1])
 def test_dual_product_mul_matches_bigint(field):
     # a b - c d under ONE Montgomery reduction (mont_mul2): extreme operands exercise the accumulator's head-room
     rng = random.Random(200 + field)
