@@ -56,18 +56,26 @@ struct DevCircuit {
 };
 constexpr uint32_t LONG_LE_TERMS = 2048;
 
-enum SegKind { SEG_NARROW, SEG_WIDE, SEG_COUNT, SEG_COMMIT };
+enum SegKind { SEG_NARROW, SEG_WIDE, SEG_COUNT, SEG_COMMIT, SEG_POSEIDON };
 struct Segment {
   SegKind kind;
   uint32_t lo, hi;  // level range [lo, hi)
   uint32_t stream_off = 0, first_words = 0;  // SEG_NARROW: location of its staged chunk stream
-  // SEG_WIDE: the level's instruction range cut into runs of (batched Fr inversions | everything else)
+  // SEG_WIDE: the level's instruction range cut into runs of (batched Fr inversions | Poseidon-BN254 macros | everything else)
   struct Part {
     uint32_t s, t;
     bool inv;
+    bool poseidon = false;
   };
   std::vector<Part> parts;
+  // SEG_POSEIDON: the Poseidon-BN254 macro instructions [ps, pt) of level `lo`, run by the four-lane grid kernel BEFORE the
+  // narrow segment that starts at the same level; that narrow segment leaves them out of its first level (skip_s, skip_t).
+  uint32_t ps = 0, pt = 0;
+  uint32_t skip_s = 0, skip_t = 0;
 };
+// a level's Poseidon-BN254 macros leave the spine CTA for the grid kernel from this many permutations on (the spine CTA
+// runs one permutation per thread: 784 dependent multiplications at one warp's pace, whatever their number)
+constexpr uint32_t POSEIDON4_MIN = 16;
 
 // levels with at least this many instructions run as grid launches across all SMs, narrower ones on the proof's
 // persistent spine CTA (GPW_WIDE_THRESHOLD overrides it at circuit-compile time, for experiments). Measured on
@@ -261,7 +269,7 @@ __device__ void exec_op(const DevCircuit& c, const Fr* W, uint32_t op_nout, cons
       O.put(1,from_u64(x[0] & 0xffffffffull));
       break;
     }
-    case fe::OP_INVZERO: O.put(0,inv(eval_ref(c, W, A))); break;
+    case fe::OP_INVZERO: O.put(0,inv_euclid(eval_ref(c, W, A))); break;  // (shift-and-subtract: ~3x the pace of the Fermat chain on a lone warp)
     case fe::OP_BITS: {
       uint64_t x[4];
       to_u64x4(eval_ref(c, W, A), x);
@@ -274,7 +282,7 @@ __device__ void exec_op(const DevCircuit& c, const Fr* W, uint32_t op_nout, cons
     case fe::OP_DIV: {
       Fr d = eval_ref(c, W, B);
       if (d.is_zero()) atomicCAS(err, 0, ERR_DIV0);
-      O.put(0,mul(eval_ref(c, W, A), inv(d)));
+      O.put(0,mul(eval_ref(c, W, A), inv_euclid(d)));
       break;
     }
     case fe::OP_DECOMP: {
@@ -333,10 +341,10 @@ __device__ __forceinline__ void exec_instr(const DevCircuit& c, Fr* W, const DIn
 // so one contiguous copy brings everything an instruction needs except the wire values themselves. The CTA keeps
 // two chunk buffers in shared memory and prefetches chunk i+1 with ONE TMA bulk copy (cp.async.bulk + mbarrier) while it
 // executes chunk i: the only exposed global-memory latency per level is the load of the operand wires.
-constexpr uint32_t CHUNK_MAX_WORDS = 6144;  // 24 KB per buffer
+constexpr uint32_t CHUNK_MAX_WORDS = 12288;  // 48 KB per buffer
 // + the Poseidon-Goldilocks macro's trace (1992 integers of 192 bits) and its 2 x 12-word exchange buffers
 constexpr size_t GLM_TRACE_WORDS64 = (size_t)glm::N_OUT * 3 + 24;
-constexpr size_t STAGED_SMEM_BYTES = 2 * CHUNK_MAX_WORDS * 4 + RING_SLOTS * sizeof(Fr) + GLM_TRACE_WORDS64 * 8 + 16;  // 48 + 64 + 47 KB + 2 mbarriers
+constexpr size_t STAGED_SMEM_BYTES = 2 * CHUNK_MAX_WORDS * 4 + RING_SLOTS * sizeof(Fr) + GLM_TRACE_WORDS64 * 8 + 16;  // 96 + 64 + 47 KB + 2 mbarriers
 constexpr uint32_t CHUNK_FLAG_GL_MACRO = 1;  // chunk header word [3]: the chunk is ONE OP_POSEIDON_GL instruction
 // The spine CTA is latency bound and shares nothing: when other proofs' MSM / NTT kernels run next to it (several
 // proofs in flight, wrap.cu) their warps would saturate the SM's IMAD pipe and stretch every level of the spine. It
@@ -433,10 +441,27 @@ __global__ void __launch_bounds__(NARROW_THREADS)
       mbar_expect_tx(&chunk_bar[cur ^ 1], next_words * 4);
       tma_bulk_load(&buf[cur ^ 1][0], next_src, next_words * 4, &chunk_bar[cur ^ 1]);
     }
+    // one instruction record of the chunk
+    auto run_record = [&](uint32_t i) {
+      const uint32_t* rec = ch + ch[4 + i];
+      const uint32_t nA = rec[2], nB = rec[3], nC = rec[4], nD = rec[6];
+      const uint32_t* t = rec + 7;
+      LeRef A{t, t + 1, nA & 0x7fffffffu, 2, (nA >> 31) != 0, ring};
+      t += 2 * (nA & 0x7fffffffu);
+      LeRef B{t, t + 1, nB & 0x3fffffffu, 2, (nB >> 31) != 0, ring};
+      if (nB & 0x40000000u) B = A;  // encoder: B is the same expression as A, its terms are not repeated
+      else t += 2 * (nB & 0x3fffffffu);
+      LeRef Cc{t, t + 1, nC & 0x7fffffffu, 2, (nC >> 31) != 0, ring};
+      t += 2 * (nC & 0x7fffffffu);
+      LeRef D{t, t + 1, nD & 0x7fffffffu, 2, (nD >> 31) != 0, ring};
+      exec_op(c, W, rec[0], OutRef{W, rec[1], ring, rec[5]}, A, B, Cc, D, e, h);
+    };
     if (ch[3] == CHUNK_FLAG_GL_MACRO) {
-      // One whole Poseidon-Goldilocks permutation, cooperatively: 12 threads fetch the state, warp 0 evaluates the
-      // permutation natively (lane k owns element k) leaving the 1992 hint / product integers in shared memory, then
-      // all threads convert them to Montgomery form and store them to their wires and to the ring.
+      // Record 0 is one whole Poseidon-Goldilocks permutation, cooperatively: 12 threads fetch the state, warp 0 evaluates
+      // the permutation natively (lane k owns element k) leaving the 1992 hint / product integers in shared memory, then all
+      // threads convert them to Montgomery form and store them to their wires and to the ring. The permutation is a ~45 us
+      // dependency chain on ONE warp: the chunk's other records - instructions of the same level, independent of it - are
+      // executed by warps 1..7 meanwhile.
       const uint32_t* rec = ch + ch[4];
       const uint32_t nout = rec[0] >> 8;
       const uint32_t* t = rec + 7;
@@ -451,12 +476,17 @@ __global__ void __launch_bounds__(NARROW_THREADS)
       }
       __syncthreads();
       lap(1);
-      if (threadIdx.x < 32)
+      if (threadIdx.x < 32) {
         glm::trace_warp(threadIdx.x < 12 ? glm_io[threadIdx.x] : 0ull, glm_io + 12, c.gl_tables, [&](uint32_t slot, const glm::U192& v) {
           glm_trace[3 * slot] = v.l[0];
           glm_trace[3 * slot + 1] = v.l[1];
           glm_trace[3 * slot + 2] = v.l[2];
         });
+      } else {
+        for (uint32_t i = 1 + (threadIdx.x - 32); i < n_instr; i += blockDim.x - 32) run_record(i);
+      }
+      if (blockDim.x == 32)  // (GPW_SPINE_THREADS=32 experiments: no helper warps)
+        for (uint32_t i = 1 + threadIdx.x; i < n_instr; i += 32) run_record(i);
       __syncthreads();
       lap(2);
       for (uint32_t k = threadIdx.x; k < nout; k += blockDim.x) {
@@ -465,20 +495,8 @@ __global__ void __launch_bounds__(NARROW_THREADS)
         st_w(ring + ((slot0 + k) & (RING_SLOTS - 1)), v);
       }
       pc[5]++;
-    } else
-    for (uint32_t i = threadIdx.x; i < n_instr; i += blockDim.x) {
-      const uint32_t* rec = ch + ch[4 + i];
-      const uint32_t nA = rec[2], nB = rec[3], nC = rec[4], nD = rec[6];
-      const uint32_t* t = rec + 7;
-      LeRef A{t, t + 1, nA & 0x7fffffffu, 2, (nA >> 31) != 0, ring};
-      t += 2 * (nA & 0x7fffffffu);
-      LeRef B{t, t + 1, nB & 0x3fffffffu, 2, (nB >> 31) != 0, ring};
-      if (nB & 0x40000000u) B = A;  // encoder: B is the same expression as A, its terms are not repeated
-      else t += 2 * (nB & 0x3fffffffu);
-      LeRef Cc{t, t + 1, nC & 0x7fffffffu, 2, (nC >> 31) != 0, ring};
-      t += 2 * (nC & 0x7fffffffu);
-      LeRef D{t, t + 1, nD & 0x7fffffffu, 2, (nD >> 31) != 0, ring};
-      exec_op(c, W, rec[0], OutRef{W, rec[1], ring, rec[5]}, A, B, Cc, D, e, h);
+    } else {
+      for (uint32_t i = threadIdx.x; i < n_instr; i += blockDim.x) run_record(i);
     }
     src = next_src;
     words = next_words;
@@ -512,6 +530,27 @@ __global__ void __launch_bounds__(128)
   Fr* W = wires + (size_t)blockIdx.y * wire_stride;
   for (uint32_t i = s + blockIdx.x * blockDim.x + threadIdx.x; i < t; i += gridDim.x * blockDim.x)
     exec_instr(c, W, c.instr[i], err + blockIdx.y, hist + (size_t)blockIdx.y * 65536);
+}
+
+// grid.y = proof; the Poseidon-BN254 macro instructions [s, t) of one level, FOUR lanes per permutation (lane q evaluates
+// input expression q and owns state element q, poseidon_bn254_trace4), 8 permutations per one-warp CTA so that the
+// ~20..170 permutations of a Merkle-path level spread over as many SMs as possible: the level is a dependency chain,
+// what counts is the pace of a single warp.
+__global__ void __launch_bounds__(32)
+    k_tape_poseidon4(DevCircuit c, Fr* __restrict__ wires, size_t wire_stride, uint32_t s, uint32_t t) {
+  Fr* W = wires + (size_t)blockIdx.y * wire_stride;
+  const uint32_t lane = threadIdx.x, q = lane & 3u;
+  const uint32_t i = s + blockIdx.x * 8u + (lane >> 2);
+  const bool valid = i < t;
+  const DInstr in = c.instr[valid ? i : s];
+  const LeRef R = csr_ref(c, in.le[q]);
+  Fr x = eval_ref(c, W, R);
+  const uint32_t const_mask = (__ballot_sync(0xffffffffu, ref_is_const(R)) >> (lane & ~3u)) & 0xfu;
+  const Bn254PoseidonTables T{c.bn_tables, c.bn_tables + 88, c.bn_tables + 88 + 392, c.bn_tables + 88 + 392 + 16};
+  Fr* out = W + in.out;
+  poseidon_bn254_trace4(x, const_mask, T, [&](uint32_t idx, const Fr& v) {
+    if (valid) st_w(out + idx, v);
+  });
 }
 
 // The Fr inversions of a wide level - gnark's IsZero hint (one per range check) and the 2.5 M divisions of the
@@ -705,9 +744,21 @@ static int finish_compile(gpw_circuit* c) {
   for (uint32_t l = 0; l < L; l++) level_off[l + 1] += level_off[l];
   // execution plan
   c->plan.clear();
-  uint32_t run_lo = 0;
+  static const bool poseidon4 = !getenv("GPW_NO_POSEIDON4");  // (debugging aid: everything on the one-thread-per-permutation path)
+  uint32_t run_lo = 0, run_skip_s = 0, run_skip_t = 0;
   auto flush = [&](uint32_t upto) {
-    if (upto > run_lo) c->plan.push_back({SEG_NARROW, run_lo, upto});
+    if (upto > run_lo) {
+      Segment n{SEG_NARROW, run_lo, upto};
+      n.skip_s = run_skip_s;
+      n.skip_t = run_skip_t;
+      c->plan.push_back(n);
+    }
+    run_skip_s = run_skip_t = 0;
+  };
+  // instructions of a level are sorted by op: 0 = generic, 1 = Fr inversion (batched-inverse kernel), 2 = Poseidon-BN254 macro
+  auto op_class = [&](uint32_t i) -> int {
+    const uint32_t op = di[i].op_nout & 0xffu;
+    return (op == fe::OP_INVZERO || op == fe::OP_DIV) ? 1 : op == fe::OP_POSEIDON_BN254 ? 2 : 0;
   };
   for (uint32_t l = 0; l < L; l++) {
     const uint32_t cnt = level_off[l + 1] - level_off[l];
@@ -716,23 +767,21 @@ static int finish_compile(gpw_circuit* c) {
       flush(l);
       if (cnt) {
         Segment w{SEG_WIDE, l, l + 1};
-        // instructions of a level are sorted by op: runs of Fr inversions go to the batched-inverse kernel
-        auto is_inv = [&](uint32_t i) {
-          const uint32_t op = di[i].op_nout & 0xffu;
-          return op == fe::OP_INVZERO || op == fe::OP_DIV;
-        };
         uint32_t i = level_off[l];
         while (i < level_off[l + 1]) {
           uint32_t j = i;
-          const bool iv = is_inv(i);
-          while (j < level_off[l + 1] && is_inv(j) == iv) j++;
-          w.parts.push_back({i, j, iv && (j - i) >= 1024});
+          const int cl = op_class(i);
+          while (j < level_off[l + 1] && op_class(j) == cl) j++;
+          Segment::Part part{i, j, cl == 1 && (j - i) >= 1024};
+          part.poseidon = poseidon4 && cl == 2 && (j - i) >= POSEIDON4_MIN;
+          w.parts.push_back(part);
           i = j;
         }
-        // merge neighbouring generic parts (short inversion runs stay on the generic path)
+        // merge neighbouring generic parts (short inversion / permutation runs stay on the generic path)
         std::vector<Segment::Part> merged;
         for (const auto& p : w.parts) {
-          if (!merged.empty() && !merged.back().inv && !p.inv) merged.back().t = p.t;
+          const bool plain = !p.inv && !p.poseidon;
+          if (!merged.empty() && plain && !merged.back().inv && !merged.back().poseidon) merged.back().t = p.t;
           else merged.push_back(p);
         }
         w.parts = merged;
@@ -741,6 +790,23 @@ static int finish_compile(gpw_circuit* c) {
       if (l == count_level) c->plan.push_back({SEG_COUNT, l, l + 1});
       if (l == commit_level) c->plan.push_back({SEG_COMMIT, l, l + 1});
       run_lo = l + 1;
+    } else if (poseidon4) {
+      // a narrow level with enough Poseidon-BN254 macros: the spine stops in front of it, the four-lane grid kernel runs the
+      // permutations, and the spine resumes AT this level without them (instructions of one level are independent)
+      uint32_t ps = level_off[l], pt;
+      while (ps < level_off[l + 1] && op_class(ps) != 2) ps++;
+      pt = ps;
+      while (pt < level_off[l + 1] && op_class(pt) == 2) pt++;
+      if (pt - ps >= POSEIDON4_MIN) {
+        flush(l);
+        Segment g{SEG_POSEIDON, l, l + 1};
+        g.ps = ps;
+        g.pt = pt;
+        c->plan.push_back(g);
+        run_lo = l;
+        run_skip_s = ps;
+        run_skip_t = pt;
+      }
     }
   }
   flush(L);
@@ -770,19 +836,31 @@ static int finish_compile(gpw_circuit* c) {
       seg.first_words = 0;
       size_t prev_hdr = (size_t)-1;
       for (uint32_t l = seg.lo; l < seg.hi; l++) {
-        uint32_t i = level_off[l];
-        const uint32_t end = level_off[l + 1];
+        // the level's instructions in chunk order: a Poseidon-Goldilocks macro FIRST (it opens a chunk and the level's other
+        // instructions fill the rest of it - warp 0 runs the permutation while the other warps execute them), then the rest.
+        // The first level of a segment may leave a run of instructions (skip_s, skip_t) to a preceding SEG_POSEIDON.
+        const bool cut = l == seg.lo && seg.skip_t > seg.skip_s;
+        std::vector<DInstr> dl;
+        dl.reserve(level_off[l + 1] - level_off[l]);
+        for (int pass = 0; pass < 2; pass++)
+          for (uint32_t k = level_off[l]; k < level_off[l + 1]; k++) {
+            if (cut && k >= seg.skip_s && k < seg.skip_t) continue;
+            const bool glm = (di[k].op_nout & 0xffu) == fe::OP_POSEIDON_GL;
+            if (glm == (pass == 0)) dl.push_back(di[k]);
+          }
+        uint32_t i = 0;
+        const uint32_t end = (uint32_t)dl.size();
         while (i < end) {
           // greedily take instructions [i, j) that fit one chunk
-          uint32_t j = i, words = 4;
+          uint32_t j = i, words = 4, outs_sum = 0;
           const auto& mouts = api.MacroOuts();
-          auto is_gl_macro = [&](uint32_t k) { return (di[k].op_nout & 0xffu) == fe::OP_POSEIDON_GL; };
+          auto is_gl_macro = [&](uint32_t k) { return (dl[k].op_nout & 0xffu) == fe::OP_POSEIDON_GL; };
           while (j < end) {
-            if (is_gl_macro(j) && j > i) break;  // a Poseidon-Goldilocks macro gets a chunk of its own
-            uint32_t rec = 7 + le_words(di[j].le[0]) + le_words(di[j].le[1]) + le_words(di[j].le[2]) + le_words(di[j].le[3]);
-            if (is_gl_macro(j)) rec += di[j].op_nout >> 8;
-            if ((di[j].op_nout >> 8) >= RING_SLOTS) {
-              set_error("tape instruction with %u outputs exceeds the ring", di[j].op_nout >> 8);
+            if (is_gl_macro(j) && j > i) break;  // a Poseidon-Goldilocks macro opens a chunk
+            uint32_t rec = 7 + le_words(dl[j].le[0]) + le_words(dl[j].le[1]) + le_words(dl[j].le[2]) + le_words(dl[j].le[3]);
+            if (is_gl_macro(j)) rec += dl[j].op_nout >> 8;
+            if ((dl[j].op_nout >> 8) >= RING_SLOTS) {
+              set_error("tape instruction with %u outputs exceeds the ring", dl[j].op_nout >> 8);
               return GPW_EINVAL;
             }
             if (rec + 5 > CHUNK_MAX_WORDS) {
@@ -790,9 +868,14 @@ static int finish_compile(gpw_circuit* c) {
               return GPW_EINVAL;
             }
             if (words + 1 + rec > CHUNK_MAX_WORDS - 4) break;
+            // the records of a chunk write their ring slots in no particular order: together they must not wrap around the
+            // ring (two wires of one chunk on one slot); a macro's own outputs are stored after the others (below)
+            if (!is_gl_macro(j)) {
+              if (outs_sum + (dl[j].op_nout >> 8) > RING_SLOTS) break;
+              outs_sum += dl[j].op_nout >> 8;
+            }
             words += 1 + rec;
             j++;
-            if (is_gl_macro(j - 1)) break;
           }
           const size_t base = stream.size();
           const uint32_t n = j - i;
@@ -804,14 +887,14 @@ static int finish_compile(gpw_circuit* c) {
           // operand reads the ring instead of HBM if its slot cannot have been overwritten before the END of the
           // consuming chunk (the chunk's own outputs are written concurrently with its reads)
           uint64_t seq_end = ring_seq;
-          for (uint32_t k = i; k < j; k++) seq_end += di[k].op_nout >> 8;
+          for (uint32_t k = i; k < j; k++) seq_end += dl[k].op_nout >> 8;
           if (dbg) {  // warp-level cost model: lanes of a warp run in lock step, the slowest lane sets the pace
             for (uint32_t w0 = i; w0 < j; w0 += 32) {
               uint32_t worst[3] = {0, 0, 0};
               for (uint32_t k = w0; k < std::min(j, w0 + 32); k++) {
                 uint32_t cnt[3] = {0, 0, 0};
                 for (int t = 0; t < 4; t++) {
-                  uint32_t le = di[k].le[t];
+                  uint32_t le = dl[k].le[t];
                   if (le == NO_LE) continue;
                   for (uint32_t q = off[le]; q < off[le + 1]; q++) {
                     if (lc[q] <= 1) continue;
@@ -819,18 +902,31 @@ static int finish_compile(gpw_circuit* c) {
                   }
                 }
                 for (int t = 0; t < 3; t++) worst[t] = std::max(worst[t], cnt[t]);
-                dbg_thread[di[k].op_nout & 0xff][0] += cnt[0];
-                dbg_thread[di[k].op_nout & 0xff][1] += cnt[1];
-                dbg_thread[di[k].op_nout & 0xff][2] += cnt[2];
+                dbg_thread[dl[k].op_nout & 0xff][0] += cnt[0];
+                dbg_thread[dl[k].op_nout & 0xff][1] += cnt[1];
+                dbg_thread[dl[k].op_nout & 0xff][2] += cnt[2];
               }
               for (int t = 0; t < 3; t++) dbg_warp[t] += worst[t];
               dbg_warps++;
             }
             dbg_chunks++;
           }
+          // ring slots in the order the chunk WRITES them: a macro (record 0) stores its outputs after the chunk's other
+          // records have run (k_tape_staged), so it takes the last slots of the chunk - a slot always holds the newest wire
+          std::vector<uint64_t> seq_start(j - i);
+          {
+            uint64_t rs = ring_seq;
+            const bool macro_first = is_gl_macro(i);
+            for (uint32_t k = i + (macro_first ? 1u : 0u); k < j; k++) {
+              seq_start[k - i] = rs;
+              rs += dl[k].op_nout >> 8;
+            }
+            if (macro_first) seq_start[0] = rs;
+          }
           for (uint32_t k = i; k < j; k++) {
             stream[base + 4 + (k - i)] = (uint32_t)(stream.size() - base);
-            const DInstr& in = di[k];
+            const DInstr& in = dl[k];
+            uint64_t my_seq = seq_start[k - i];
             stream.push_back(in.op_nout);
             stream.push_back(in.out);
             const bool same_ab = (in.op_nout & 0xff) == fe::OP_MUL && in.le[1] != NO_LE && in.le[1] == in.le[0];
@@ -839,12 +935,12 @@ static int finish_compile(gpw_circuit* c) {
               if (t == 1 && same_ab) stream.push_back(0xC0000000u);
               else stream.push_back(le == NO_LE ? 0u : ((off[le + 1] - off[le]) | 0x80000000u));
             }
-            stream.push_back((uint32_t)(ring_seq % RING_SLOTS));
+            stream.push_back((uint32_t)(my_seq % RING_SLOTS));
             stream.push_back(in.le[3] == NO_LE ? 0u : ((off[in.le[3] + 1] - off[in.le[3]]) | 0x80000000u));
             const bool glm_instr = (in.op_nout & 0xffu) == fe::OP_POSEIDON_GL;
             for (uint32_t o = 0; o < (in.op_nout >> 8); o++) {
               const uint32_t ow = glm_instr ? mouts[in.out + o] : in.out + o;
-              wire_seq[ow] = ring_seq++;
+              wire_seq[ow] = my_seq++;
               wire_seg[ow] = seg_id;
             }
             for (int t = 0; t < 4; t++) {
@@ -862,6 +958,7 @@ static int finish_compile(gpw_circuit* c) {
             if (glm_instr)
               for (uint32_t o = 0; o < (in.op_nout >> 8); o++) stream.push_back(mouts[in.out + o]);
           }
+          ring_seq = seq_end;
           while ((stream.size() - base) % 4) stream.push_back(0);
           const uint32_t cw = (uint32_t)(stream.size() - base);
           if (prev_hdr == (size_t)-1) seg.first_words = cw;
@@ -1042,9 +1139,17 @@ static int run_segments(gpw_circuit* c, gpw_ctx* ctx, Fr* wires, size_t stride, 
       }
       GPW_CHECK_LAUNCH();
       ctx->launches++;
+    } else if (s.kind == SEG_POSEIDON) {
+      dim3 grid(div_up(s.pt - s.ps, 8), n_proofs);
+      k_tape_poseidon4<<<grid, 32, 0, st>>>(c->dc, wires, stride, s.ps, s.pt);
+      GPW_CHECK_LAUNCH();
+      ctx->launches++;
     } else if (s.kind == SEG_WIDE) {
       for (const Segment::Part& p : s.parts) {
-        if (p.inv) {
+        if (p.poseidon) {
+          dim3 grid(div_up(p.t - p.s, 8), n_proofs);
+          k_tape_poseidon4<<<grid, 32, 0, st>>>(c->dc, wires, stride, p.s, p.t);
+        } else if (p.inv) {
           dim3 grid(div_up(p.t - p.s, 128 * INV_G), n_proofs);
           k_tape_wide_inv<<<grid, 128, 0, st>>>(c->dc, wires, stride, err, p.s, p.t);
         } else {
