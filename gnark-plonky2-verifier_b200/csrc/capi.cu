@@ -73,6 +73,15 @@ extern "C" int gpw_ctx_create(int device, gpw_ctx** out) {
   gpw_ctx* c = new gpw_ctx();
   c->device = device;
   GPW_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  {
+    int least = 0, greatest = 0;
+    GPW_CUDA(cudaDeviceGetStreamPriorityRange(&least, &greatest));
+    GPW_CUDA(cudaStreamCreateWithPriority(&c->stream_hi, cudaStreamNonBlocking, greatest));
+    GPW_CUDA(cudaEventCreateWithFlags(&c->ev_hop, cudaEventDisableTiming));
+    for (int i = 0; i < 2; i++) GPW_CUDA(cudaEventCreateWithFlags(&c->slot_done[i], cudaEventDisableTiming));
+    for (auto& p : c->pend)
+      for (auto& e : p.ev) GPW_CUDA(cudaEventCreate(&e));
+  }
   cudaDeviceProp prop;
   GPW_CUDA(cudaGetDeviceProperties(&prop, device));
   c->sm_count = prop.multiProcessorCount;
@@ -88,6 +97,16 @@ extern "C" void gpw_ctx_destroy(gpw_ctx* ctx) {
   gpw_comm_destroy(ctx);
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
+  if (ctx->stream_hi) {
+    cudaStreamSynchronize(ctx->stream_hi);
+    cudaStreamDestroy(ctx->stream_hi);
+  }
+  if (ctx->ev_hop) cudaEventDestroy(ctx->ev_hop);
+  for (auto& e : ctx->slot_done)
+    if (e) cudaEventDestroy(e);
+  for (auto& p : ctx->pend)
+    for (auto& e : p.ev)
+      if (e) cudaEventDestroy(e);
   for (auto& kv : ctx->scratch)
     if (kv.second.p) cudaFree(kv.second.p);
   for (auto& kv : ctx->ntt) {
@@ -128,6 +147,10 @@ extern "C" int gpw_ctx_set_option(gpw_ctx* ctx, const char* key, int64_t value) 
       return GPW_EINVAL;
     }
     ctx->msm_affine_rounds = (int)value;
+    return GPW_OK;
+  }
+  if (!strcmp(key, "msm_overlap")) {  // 1 (default): the wrap prover overlaps an MSM's tail with the next MSM (common.cuh)
+    ctx->msm_overlap = value != 0;
     return GPW_OK;
   }
   set_error("ctx_set_option: unknown option '%s'", key);

@@ -52,6 +52,37 @@ struct gpw_ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
   bool own_stream = true;
+  // ---- deferred MSMs (msm_impl.cuh, used by the wrap prover) ------------------------------------------------------------
+  // An MSM ends in short latency-bound grids (bucket fix-up, two-level window reduction, sums) and a host-side Horner over
+  // <= 32 window sums. Run back to back, every MSM of a proof leaves the device nearly idle for that tail and then waits for
+  // the host. In deferred mode (msm_defer_begin .. msm_finish_all) an MSM call only ENQUEUES: sort + bucket accumulation on
+  // `stream`, the tail on `stream_hi` - a second stream of the context at the device's greatest priority, so that its small
+  // CTAs take the next free slots while the NEXT MSM's accumulation fills the rest of the device - and the window sums land
+  // in pinned memory; msm_finish() waits for the MSM's event and folds them on the host. Scratch that the tail still reads
+  // while the next MSM starts is double-buffered (tag suffix a / b by call parity).
+  cudaStream_t stream_hi = nullptr;
+  cudaEvent_t ev_hop = nullptr;
+  struct MsmPending {
+    int group = 0;  // 1 = G1, 2 = G2
+    const void* hw = nullptr;      // pinned: 2 nw window sums (XYZZ)
+    const uint32_t* Mp = nullptr;  // pinned: number of sorted entries
+    int nw = 0, c = 0, win_lo = 0;
+    uint32_t chunk = 0;
+    size_t n = 0;
+    uint64_t* out = nullptr;
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};  // start, sorted, accumulated, done
+    float acc_ms = 0, total_ms = 0;
+    uint64_t digits = 0;
+    bool open = false;
+  };
+  static constexpr int MAX_PENDING = 16;
+  MsmPending pend[MAX_PENDING];
+  int n_pend = 0;          // MSMs enqueued since msm_defer_begin
+  bool msm_defer = false;  // msm_dev_impl leaves the result to msm_finish()
+  int msm_parity = 0;      // scratch double buffer of the next deferred MSM
+  cudaEvent_t slot_done[2] = {nullptr, nullptr};  // tail of the last MSM that used scratch set a / b
+  bool slot_used[2] = {false, false};
+  bool msm_overlap = true;  // option "msm_overlap": 0 = every MSM synchronous on `stream` (the round-1 behaviour)
   int sm_count = 148;
   uint64_t launches = 0;
   std::map<std::string, gpw::Scratch> scratch;
@@ -83,16 +114,26 @@ struct gpw_ctx {
   // and wait with cudaStreamSynchronize instead.
   uint8_t* pin = nullptr;
   size_t pin_off = 0;
-  static constexpr size_t PIN_CAP = 1 << 16;
+  static constexpr size_t PIN_CAP = 1 << 18;
   void* pin_take(size_t bytes) {
     bytes = (bytes + 15) & ~(size_t)15;
     if (pin_off + bytes > PIN_CAP) {  // wrap around: everything staged so far must have been consumed
       cudaStreamSynchronize(stream);
+      if (stream_hi) cudaStreamSynchronize(stream_hi);
       pin_off = 0;
     }
     void* p = pin + pin_off;
     pin_off += bytes;
     return p;
+  }
+
+  // makes sure the next `bytes` of staging come without a wrap-around (results of deferred MSMs stay put until finished)
+  void pin_reserve(size_t bytes) {
+    if (pin_off + bytes > PIN_CAP) {
+      cudaStreamSynchronize(stream);
+      if (stream_hi) cudaStreamSynchronize(stream_hi);
+      pin_off = 0;
+    }
   }
 
   int get_scratch(const char* name, size_t bytes, void** out);

@@ -71,3 +71,45 @@ extern "C" int gpw_msm_cumulative_stats(gpw_ctx* ctx, int group, int reset, doub
     }
   return GPW_OK;
 }
+
+// ---- deferred MSMs (common.cuh): internal to libgpw, used by the wrap prover ---------------------------------------------
+extern "C" int gpwi_msm_finish_g2(gpw_ctx* ctx, int idx);
+
+// msm_defer_begin: from here on gpw_msm_*_dev calls on this context only enqueue their work and return at once
+extern "C" int gpwi_msm_defer_begin(gpw_ctx* ctx) {
+  if (!ctx) return GPW_EINVAL;
+  if (!ctx->msm_overlap) return GPW_OK;  // synchronous MSMs: every call finishes itself
+  GPW_CUDA(cudaSetDevice(ctx->device));
+  ctx->pin_reserve(96 * 1024);  // window sums of a whole proof's MSMs stay in the staging area until finished
+  ctx->msm_defer = true;
+  ctx->n_pend = 0;
+  return GPW_OK;
+}
+
+// result of the idx-th MSM since msm_defer_begin (waits for it; idempotent)
+extern "C" int gpwi_msm_finish(gpw_ctx* ctx, int idx) {
+  if (!ctx || idx < 0 || idx >= gpw_ctx::MAX_PENDING) return GPW_EINVAL;
+  if (!ctx->msm_defer || idx >= ctx->n_pend) return GPW_OK;
+  GPW_CUDA(cudaSetDevice(ctx->device));
+  gpw_ctx::MsmPending& P = ctx->pend[idx];
+  return P.group == 2 ? gpwi_msm_finish_g2(ctx, idx) : msm_finish_impl<Fp>(ctx, P);
+}
+
+// finishes every MSM still open and leaves deferred mode; `stream` is ordered after all of their work
+extern "C" int gpwi_msm_defer_end(gpw_ctx* ctx) {
+  if (!ctx) return GPW_EINVAL;
+  if (!ctx->msm_defer) return GPW_OK;
+  int rc = GPW_OK;
+  for (int i = 0; i < ctx->n_pend; i++) {
+    const int r = gpwi_msm_finish(ctx, i);
+    if (rc == GPW_OK) rc = r;
+  }
+  ctx->msm_defer = false;
+  ctx->n_pend = 0;
+  for (int p = 0; p < 2; p++)
+    if (ctx->slot_used[p]) {
+      cudaStreamWaitEvent(ctx->stream, ctx->slot_done[p], 0);
+      ctx->slot_used[p] = false;
+    }
+  return rc;
+}

@@ -26,3 +26,8 @@ extern "C" int gpw_msm_g2_shared_dev(gpw_ctx* ctx, uint64_t scalars_dev, uint64_
   return msm_dev_impl<Fp2>(ctx, (const Fr*)scalars_dev, (const Affine<Fp2>*)points_dev, n, scalars_mont, window_bits, 0, 0, out_affine,
                            "msm2", 0, sort_tag, reuse != 0);
 }
+
+extern "C" int gpwi_msm_finish_g2(gpw_ctx* ctx, int idx) {
+  if (!ctx || idx < 0 || idx >= gpw_ctx::MAX_PENDING) return GPW_EINVAL;
+  return msm_finish_impl<Fp2>(ctx, ctx->pend[idx]);
+}

@@ -519,6 +519,44 @@ static int choose_window(size_t n) {
   return c;
 }
 
+// Second half of an MSM: waits for its window sums (pinned memory) and folds them on the host,
+// R = sum_w 2^(c w) (T_w + chunk U_w) with T_w / U_w the level-0 / level-1 sums of window w (k_msm_window_partial).
+template <class F>
+static int msm_finish_impl(gpw_ctx* ctx, gpw_ctx::MsmPending& P) {
+  if (!P.open) return GPW_OK;
+  P.open = false;
+  GPW_CUDA(cudaEventSynchronize(P.ev[3]));
+  GPW_CUDA(cudaEventElapsedTime(&P.acc_ms, P.ev[1], P.ev[2]));
+  GPW_CUDA(cudaEventElapsedTime(&P.total_ms, P.ev[0], P.ev[3]));
+  const XYZZ<F>* hw = (const XYZZ<F>*)P.hw;
+  const int nw = P.nw, c = P.c;
+  P.digits = *P.Mp;
+  ctx->msm_acc_ms = P.acc_ms;
+  ctx->msm_total_ms = P.total_ms;
+  ctx->msm_digits = P.digits;
+  {
+    const int g = sizeof(Affine<F>) == 64 ? 0 : 1;
+    ctx->msm_acc_ms_sum[g] += P.acc_ms;
+    ctx->msm_total_ms_sum[g] += P.total_ms;
+    ctx->msm_points_sum[g] += P.n;
+    ctx->msm_digits_sum[g] += P.digits;
+    ctx->msm_calls[g] += 1;
+  }
+  XYZZ<F> R = XYZZ<F>::inf();
+  for (int w = nw - 1; w >= 0; w--) {
+    for (int k = 0; k < c; k++) R = dbl(R);
+    // window sum = level-0 sum + chunk * level-1 sum
+    XYZZ<F> l1 = hw[nw + w];
+    for (uint32_t k = 1; k < P.chunk; k <<= 1) l1 = dbl(l1);
+    add_full(R, hw[w]);
+    add_full(R, l1);
+  }
+  for (int k = 0; k < c * P.win_lo; k++) R = dbl(R);  // (fixed-base mode: one bucket set, win_lo = 0 -> R = hw[0])
+  Affine<F> a = to_affine(R);
+  memcpy(P.out, &a, sizeof(a));
+  return GPW_OK;
+}
+
 // fixed_windows == 0: windowed Pippenger over `points` (n bases).
 // fixed_windows == W > 0 (fixed-base mode): `points` is a table of W n bases, entry w n + i = 2^(c w) P_i
 // (gpw_msm_g1_fixed_table); W must equal the number of c-bit windows of a scalar. Every digit of every scalar then
@@ -581,18 +619,28 @@ static int msm_dev_impl(gpw_ctx* ctx, const Fr* scalars, const Affine<F>* points
 
   uint32_t *counts, *offsets, *cursor, *sorted, *tail_key, *tail_list, *ntail, *nbig, *big_list, *block_sums;
   XYZZ<F>*buckets, *head, *tail, *partials, *wsums;
-  std::string T(tag), ST(sort_tag ? sort_tag : tag);
+  // deferred mode (common.cuh): the tail of the previous MSM may still read its scratch while this one starts - two sets
+  const bool defer = ctx->msm_defer;
+  const int parity = defer ? (ctx->msm_parity & 1) : 0;
+  if (defer && ctx->n_pend >= gpw_ctx::MAX_PENDING) {
+    set_error("msm: too many deferred MSMs");
+    return GPW_EINVAL;
+  }
+  gpw_ctx::MsmPending& PD = ctx->pend[defer ? ctx->n_pend : gpw_ctx::MAX_PENDING - 1];
+  std::string T(tag);
+  if (defer) T += parity ? ".b" : ".a";
+  const std::string ST(sort_tag ? std::string(sort_tag) : T);
   GPW_TRY(ctx->get_scratch((ST + ".counts").c_str(), (size_t)(B + 1) * 4 * 3 + 64, (void**)&counts));
   offsets = counts + (B + 1);
   cursor = offsets + (B + 1);
-  ntail = cursor + (B + 1);
-  nbig = ntail + 1;
   const uint32_t nscan_blocks = (B + SCAN_BLOCK - 1) / SCAN_BLOCK;
   GPW_TRY(ctx->get_scratch((ST + ".scanblk").c_str(), (size_t)nscan_blocks * 4 + 16, (void**)&block_sums));
   GPW_TRY(ctx->get_scratch((ST + ".sorted").c_str(), (size_t)max_entries * 4 + 16, (void**)&sorted));
-  GPW_TRY(ctx->get_scratch((T + ".keys").c_str(), (size_t)ntasks * 4 * 3, (void**)&tail_key));
+  GPW_TRY(ctx->get_scratch((T + ".keys").c_str(), (size_t)ntasks * 4 * 3 + 16, (void**)&tail_key));
   tail_list = tail_key + ntasks;
   big_list = tail_list + ntasks;
+  ntail = big_list + ntasks;  // per-run counters live with the run's own scratch (a shared sort is read-only once built)
+  nbig = ntail + 1;
   GPW_TRY(ctx->get_scratch((T + ".buckets").c_str(), (size_t)B * sizeof(XYZZ<F>), (void**)&buckets));
   GPW_TRY(ctx->get_scratch((T + ".head").c_str(), (size_t)ntasks * sizeof(XYZZ<F>), (void**)&head));
   GPW_TRY(ctx->get_scratch((T + ".tail").c_str(), (size_t)ntasks * sizeof(XYZZ<F>), (void**)&tail));
@@ -651,11 +699,13 @@ static int msm_dev_impl(gpw_ctx* ctx, const Fr* scalars, const Affine<F>* points
     }
   }
 
-  GPW_CUDA(cudaEventRecord(ctx->ev[0], st));
+  if (defer && ctx->slot_used[parity]) GPW_CUDA(cudaStreamWaitEvent(st, ctx->slot_done[parity], 0));  // scratch set is free again
+  if (defer && rounds > 0 && ctx->slot_used[parity ^ 1])  // the batch-affine scratch is single-buffered: no overlap with it on
+    GPW_CUDA(cudaStreamWaitEvent(st, ctx->slot_done[parity ^ 1], 0));
+  GPW_CUDA(cudaEventRecord(PD.ev[0], st));
   GPW_CUDA(cudaMemsetAsync(buckets, 0, (size_t)B * sizeof(XYZZ<F>), st));
-  if (reuse_sort) {
-    GPW_CUDA(cudaMemsetAsync(ntail, 0, 8, st));  // ntail, nbig: the only per-run state in the sort's scratch
-  } else {
+  GPW_CUDA(cudaMemsetAsync(ntail, 0, 8, st));  // ntail, nbig
+  if (!reuse_sort) {
     GPW_CUDA(cudaMemsetAsync(counts, 0, (size_t)(B + 1) * 4 * 3 + 64, st));
     const int TPB = 256;
     k_msm_digits<false><<<div_up(n, TPB), TPB, 0, st>>>(scalars, n, mont, c, nwin, win_lo, win_hi, fixed_windows, counts, nullptr);
@@ -670,7 +720,7 @@ static int msm_dev_impl(gpw_ctx* ctx, const Fr* scalars, const Affine<F>* points
     GPW_CHECK_LAUNCH();
     ctx->launches += 5;
   }
-  GPW_CUDA(cudaEventRecord(ctx->ev[1], st));
+  GPW_CUDA(cudaEventRecord(PD.ev[1], st));
   // ---- batch-affine rounds (msm_affine.cuh): pairwise tree over the sorted list, then XYZZ for what is left --------------
   const Affine<F>* acc_points = points;
   const uint32_t* acc_sorted = sorted;
@@ -718,38 +768,46 @@ static int msm_dev_impl(gpw_ctx* ctx, const Fr* scalars, const Affine<F>* points
   k_msm_accumulate<F><<<div_up(acc_ntasks, MSM_ACC_THREADS), MSM_ACC_THREADS, MSM_ACC_THREADS * sizeof(XYZZ<F>), st>>>(
       acc_points, acc_sorted, acc_offsets, B, buckets, head, tail, tail_key, tail_list, ntail);
   GPW_CHECK_LAUNCH();
-  GPW_CUDA(cudaEventRecord(ctx->ev[2], st));
-  // development aid (GPW_DEBUG_MSM=1): split of the tail into fix-up / window reduction / sums
-  static const bool dbg_phases = getenv("GPW_DEBUG_MSM") != nullptr;
+  GPW_CUDA(cudaEventRecord(PD.ev[2], st));
+  // development aid (GPW_DEBUG_MSM=1, synchronous MSMs only): split of the tail into fix-up / window reduction / sums
+  static const bool dbg_env = getenv("GPW_DEBUG_MSM") != nullptr;
+  const bool dbg_phases = dbg_env && !defer;
   cudaEvent_t dbg_ev[3] = {nullptr, nullptr, nullptr};
   if (dbg_phases)
     for (auto& e : dbg_ev) cudaEventCreate(&e);
-  k_msm_fixup<F><<<ctx->sm_count * 8, 128, 0, st>>>(head, tail, acc_offsets, tail_key, tail_list, ntail, big_list, nbig, buckets);
+  // the tail: short latency-bound grids. Deferred: on the context's high-priority stream, beside the next MSM.
+  static const bool tail_stream = !getenv("GPW_MSM_TAIL_STREAM") || atoi(getenv("GPW_MSM_TAIL_STREAM")) != 0;
+  const cudaStream_t gs = (defer && ctx->stream_hi && tail_stream) ? ctx->stream_hi : st;
+  if (gs != st) {
+    GPW_CUDA(cudaEventRecord(ctx->ev_hop, st));
+    GPW_CUDA(cudaStreamWaitEvent(gs, ctx->ev_hop, 0));
+  }
+  k_msm_fixup<F><<<ctx->sm_count * 8, 128, 0, gs>>>(head, tail, acc_offsets, tail_key, tail_list, ntail, big_list, nbig, buckets);
   GPW_CHECK_LAUNCH();
   {
     const int fb_threads = sizeof(XYZZ<F>) > 128 ? 128 : 256;
-    k_msm_fixup_big<F><<<ctx->sm_count * 2, fb_threads, fb_threads * sizeof(XYZZ<F>), st>>>(head, tail, acc_offsets, tail_key, big_list,
+    k_msm_fixup_big<F><<<ctx->sm_count * 2, fb_threads, fb_threads * sizeof(XYZZ<F>), gs>>>(head, tail, acc_offsets, tail_key, big_list,
                                                                                           nbig, buckets);
   }
   GPW_CHECK_LAUNCH();
-  if (dbg_phases) cudaEventRecord(dbg_ev[0], st);
-  k_msm_window_partial<F><<<div_up((size_t)nw * nchunks, 128), 128, 0, st>>>(buckets, offsets, half, chunk, (uint32_t)nw, 1u, partials,
+  if (dbg_phases) cudaEventRecord(dbg_ev[0], gs);
+  k_msm_window_partial<F><<<div_up((size_t)nw * nchunks, 128), 128, 0, gs>>>(buckets, offsets, half, chunk, (uint32_t)nw, 1u, partials,
                                                                              chunk_sums);
   GPW_CHECK_LAUNCH();
-  k_msm_window_partial<F><<<div_up((size_t)nw * nchunks2, 128), 128, 0, st>>>(chunk_sums, nullptr, nchunks, chunk2, (uint32_t)nw, 0u,
+  k_msm_window_partial<F><<<div_up((size_t)nw * nchunks2, 128), 128, 0, gs>>>(chunk_sums, nullptr, nchunks, chunk2, (uint32_t)nw, 0u,
                                                                               partials2, nullptr);
   GPW_CHECK_LAUNCH();
-  if (dbg_phases) cudaEventRecord(dbg_ev[1], st);
+  if (dbg_phases) cudaEventRecord(dbg_ev[1], gs);
   // per-window sums of an array of `cnt` partials per window -> dst[0 .. nw)  (two rounds above 2048 partials)
   auto sum_partials = [&](const XYZZ<F>* src, uint32_t cnt, uint32_t groups, XYZZ<F>* tmp, XYZZ<F>* dst) -> int {
     if (groups == 1) {
-      k_msm_window_final<F><<<dim3(1, nw), 128, 128 * sizeof(XYZZ<F>), st>>>(src, cnt, WINDOW_FINAL_PER_CTA, dst);
+      k_msm_window_final<F><<<dim3(1, nw), 128, 128 * sizeof(XYZZ<F>), gs>>>(src, cnt, WINDOW_FINAL_PER_CTA, dst);
       GPW_CHECK_LAUNCH();
       ctx->launches += 1;
     } else {
-      k_msm_window_final<F><<<dim3(groups, nw), 128, 128 * sizeof(XYZZ<F>), st>>>(src, cnt, WINDOW_FINAL_PER_CTA, tmp);
+      k_msm_window_final<F><<<dim3(groups, nw), 128, 128 * sizeof(XYZZ<F>), gs>>>(src, cnt, WINDOW_FINAL_PER_CTA, tmp);
       GPW_CHECK_LAUNCH();
-      k_msm_window_final<F><<<dim3(1, nw), 128, 128 * sizeof(XYZZ<F>), st>>>(tmp, groups, WINDOW_FINAL_PER_CTA, dst);
+      k_msm_window_final<F><<<dim3(1, nw), 128, 128 * sizeof(XYZZ<F>), gs>>>(tmp, groups, WINDOW_FINAL_PER_CTA, dst);
       GPW_CHECK_LAUNCH();
       ctx->launches += 2;
     }
@@ -760,45 +818,37 @@ static int msm_dev_impl(gpw_ctx* ctx, const Fr* scalars, const Affine<F>* points
   ctx->launches += 5;
   const XYZZ<F>* hw = (const XYZZ<F>*)ctx->pin_take((size_t)2 * nw * sizeof(XYZZ<F>));
   const uint32_t* Mp = (const uint32_t*)ctx->pin_take(4);
-  GPW_CUDA(cudaMemcpyAsync((void*)hw, wsums, (size_t)2 * nw * sizeof(XYZZ<F>), cudaMemcpyDeviceToHost, st));
-  GPW_CUDA(cudaMemcpyAsync((void*)Mp, offsets + B, 4, cudaMemcpyDeviceToHost, st));
-  GPW_CUDA(cudaEventRecord(ctx->ev[3], st));
-  GPW_CUDA(cudaStreamSynchronize(st));
-  GPW_CUDA(cudaEventElapsedTime(&ctx->msm_acc_ms, ctx->ev[1], ctx->ev[2]));
-  GPW_CUDA(cudaEventElapsedTime(&ctx->msm_total_ms, ctx->ev[0], ctx->ev[3]));
+  GPW_CUDA(cudaMemcpyAsync((void*)hw, wsums, (size_t)2 * nw * sizeof(XYZZ<F>), cudaMemcpyDeviceToHost, gs));
+  GPW_CUDA(cudaMemcpyAsync((void*)Mp, offsets + B, 4, cudaMemcpyDeviceToHost, gs));
+  GPW_CUDA(cudaEventRecord(PD.ev[3], gs));
+  PD.group = sizeof(Affine<F>) == 64 ? 1 : 2;
+  PD.hw = hw;
+  PD.Mp = Mp;
+  PD.nw = nw;
+  PD.c = c;
+  PD.win_lo = win_lo;
+  PD.chunk = chunk;
+  PD.n = n;
+  PD.out = out_affine;
+  PD.open = true;
+  if (defer) {
+    GPW_CUDA(cudaEventRecord(ctx->slot_done[parity], gs));
+    ctx->slot_used[parity] = true;
+    ctx->msm_parity ^= 1;
+    ctx->n_pend++;
+    return GPW_OK;
+  }
+  GPW_TRY(msm_finish_impl<F>(ctx, PD));
   if (dbg_phases) {
     float t_sort, t_fix, t_part, t_sum;
-    cudaEventElapsedTime(&t_sort, ctx->ev[0], ctx->ev[1]);
-    cudaEventElapsedTime(&t_fix, ctx->ev[2], dbg_ev[0]);
+    cudaEventElapsedTime(&t_sort, PD.ev[0], PD.ev[1]);
+    cudaEventElapsedTime(&t_fix, PD.ev[2], dbg_ev[0]);
     cudaEventElapsedTime(&t_part, dbg_ev[0], dbg_ev[1]);
-    cudaEventElapsedTime(&t_sum, dbg_ev[1], ctx->ev[3]);
+    cudaEventElapsedTime(&t_sum, dbg_ev[1], PD.ev[3]);
     fprintf(stderr, "[gpw msm] %-6s n=%8zu c=%2d: sort %.2f | accumulate %.2f | fix-up %.2f | window partial %.2f | sums + copy %.2f ms\n", tag, n, c,
             t_sort, ctx->msm_acc_ms, t_fix, t_part, t_sum);
     for (auto& e : dbg_ev) cudaEventDestroy(e);
   }
-  const uint32_t M = *Mp;
-  ctx->msm_digits = M;
-  {
-    const int g = sizeof(Affine<F>) == 64 ? 0 : 1;
-    ctx->msm_acc_ms_sum[g] += ctx->msm_acc_ms;
-    ctx->msm_total_ms_sum[g] += ctx->msm_total_ms;
-    ctx->msm_points_sum[g] += n;
-    ctx->msm_digits_sum[g] += M;
-    ctx->msm_calls[g] += 1;
-  }
-  // Horner over the window sums on the host: R = sum_w 2^(c (w)) W_w
-  XYZZ<F> R = XYZZ<F>::inf();
-  for (int w = nw - 1; w >= 0; w--) {
-    for (int k = 0; k < c; k++) R = dbl(R);
-    // window sum = level-0 sum + chunk * level-1 sum
-    XYZZ<F> l1 = hw[nw + w];
-    for (uint32_t k = 1; k < chunk; k <<= 1) l1 = dbl(l1);
-    add_full(R, hw[w]);
-    add_full(R, l1);
-  }
-  for (int k = 0; k < c * win_lo; k++) R = dbl(R);  // (fixed-base mode: one bucket set, win_lo = 0 -> R = hw[0])
-  Affine<F> a = to_affine(R);
-  memcpy(out_affine, &a, sizeof(a));
   return GPW_OK;
 }
 

@@ -161,6 +161,9 @@ int gpw_msm_g1_fixed_dev(gpw_ctx* ctx, uint64_t s, uint64_t table, size_t n, int
 int gpw_msm_g1_shared_dev(gpw_ctx* ctx, uint64_t s, uint64_t p, size_t n, int mont, int c, int fixed_windows, const char* sort_tag, int reuse,
                           uint64_t* out);
 int gpw_msm_g2_shared_dev(gpw_ctx* ctx, uint64_t s, uint64_t p, size_t n, int mont, int c, const char* sort_tag, int reuse, uint64_t* out);
+int gpwi_msm_defer_begin(gpw_ctx* ctx);
+int gpwi_msm_finish(gpw_ctx* ctx, int idx);
+int gpwi_msm_defer_end(gpw_ctx* ctx);
 }
 
 #include "wrap_internal.cuh"
@@ -455,6 +458,10 @@ extern "C" int gpw_wrap_prove_dev(gpw_wrap_key* k, uint64_t inputs_dev, const ui
     return GPW_EINVAL;
   }
   GPW_CUDA(cudaSetDevice(k->ctx->device));
+  {
+    static const char* overlap_env = getenv("GPW_MSM_OVERLAP");
+    k->lanes[0]->ctx->msm_overlap = overlap_env ? atoi(overlap_env) != 0 : true;  // a lone proof: see gpw_wrap_prove_many
+  }
   return wrap_one(k, k->lanes[0], inputs_dev, r_canon, s_canon, check, out_proof);
 }
 
@@ -468,23 +475,32 @@ static int wrap_stage2(gpw_wrap_key* k, WrapLane* L, const uint64_t* r_canon, co
   cudaEvent_t* ev = L->tev + 2;  // 7 events
   memset(out_proof, 0, 64 * 8);
   const bool dbg = getenv("GPW_DEBUG_WRAP") != nullptr;
-  auto report = [&](const char* what, size_t n) {
-    if (dbg)
-      fprintf(stderr, "[gpw wrap] MSM %-4s n=%8zu total %7.2f ms accumulate %7.2f ms digits %llu\n", what, n, ctx->msm_total_ms,
-              ctx->msm_acc_ms, (unsigned long long)ctx->msm_digits);
-  };
   GPW_CUDA(cudaEventRecord(ev[0], st));
   GPW_CUDA(cudaEventRecord(ev[1], st));
-  // commitment to the committed wires (range-check limbs + multiplicities) and its proof of knowledge
+  // The MSMs of the proof are DEFERRED (common.cuh): each call enqueues its sort + accumulation on the lane's stream and its
+  // latency-bound tail on the lane's high-priority stream, so the tail of one MSM runs beside the accumulation of the next
+  // and the host never waits between them; results are collected by gpwi_msm_finish / gpwi_msm_defer_end.
+  // (results first: the guard below may still write them when an error path unwinds)
   G1Affine D{Fp::zero(), Fp::zero()}, PoK{Fp::zero(), Fp::zero()};
+  G1Affine mA, mA2{Fp::zero(), Fp::zero()}, mB1, mK1, mK2, mZ;
+  G2Affine mB2;
+  struct DeferGuard {
+    gpw_ctx* c;
+    ~DeferGuard() { gpwi_msm_defer_end(c); }
+  } defer_guard{ctx};
+  GPW_TRY(gpwi_msm_defer_begin(ctx));
+  const char* msm_names[gpw_ctx::MAX_PENDING] = {};
+  int n_msm = 0;
+  // commitment to the committed wires (range-check limbs + multiplicities) and its proof of knowledge
   uint64_t X[4] = {0, 0, 0, 0};
   if (k->n_committed) {
     uint64_t sc = (uint64_t)(wires + k->limb_start);
     // commitment and proof of knowledge: same scalars, one bucket sort
     GPW_TRY(gpw_msm_g1_shared_dev(ctx, sc, (uint64_t)k->CK, k->n_committed, 1, 0, 0, "sortC", 0, (uint64_t*)&D));
-    report("CK", k->n_committed);
+    msm_names[n_msm++] = "CK";
     GPW_TRY(gpw_msm_g1_shared_dev(ctx, sc, (uint64_t)k->CKs, k->n_committed, 1, 0, 0, "sortC", 1, (uint64_t*)&PoK));
-    report("CKs", k->n_committed);
+    msm_names[n_msm++] = "CKs";
+    GPW_TRY(gpwi_msm_finish(ctx, 0));  // the challenge needs D now; the proof of knowledge is collected at the end
     uint8_t ser[64];
     ser_g1_be(D, ser);
     hash_to_fr(ser, 64, "bsb22-commitment", X);
@@ -511,32 +527,26 @@ static int wrap_stage2(gpw_wrap_key* k, WrapLane* L, const uint64_t* r_canon, co
   k_gather_fr<<<div_up(k->nB, 256), 256, 0, st>>>(wires, k->suppB, k->nB, L->gathB);
   GPW_CHECK_LAUNCH();
   ctx->launches += 2;
-  G1Affine mA, mB1, mK1, mK2, mZ;
-  G2Affine mB2;
   {
     const uint32_t head = k->nA - k->nA_tail;
     GPW_TRY(gpw_msm_g1_dev(ctx, (uint64_t)L->gathA, (uint64_t)k->A, head, 1, 0, 0, 0, (uint64_t*)&mA));
-    report("A", head);
+    msm_names[n_msm++] = "A";
     if (k->nA_tail) {
-      G1Affine mA2;
       // the same wires as the K2 MSM below (when both tables exist and cover the same range): K2 reuses this sort
       GPW_TRY(gpw_msm_g1_shared_dev(ctx, (uint64_t)(L->gathA + head), (uint64_t)k->At, k->nA_tail, 1, FIXED_CQ, FIXED_WQ, "sortQ", 0,
                                     (uint64_t*)&mA2));
-      report("A2", k->nA_tail);
-      G1XYZZ t = G1XYZZ::from_affine(mA);
-      add_mixed(t, mA2, false);
-      mA = to_affine(t);
+      msm_names[n_msm++] = "A2";
     }
   }
   GPW_TRY(gpw_msm_g1_shared_dev(ctx, (uint64_t)L->gathB, (uint64_t)k->B1, k->nB, 1, 0, 0, "sortB", 0, (uint64_t*)&mB1));
-  report("B1", k->nB);
+  msm_names[n_msm++] = "B1";
   GPW_TRY(gpw_msm_g2_shared_dev(ctx, (uint64_t)L->gathB, (uint64_t)k->B2, k->nB, 1, 0, "sortB", 1, (uint64_t*)&mB2));
-  report("B2", k->nB);
+  msm_names[n_msm++] = "B2";
   // K: private wires that are not committed = [1 + n_pub, limb_start) U [limb_start + n_committed, m), minus the challenge wire
   const uint32_t k_lo = 1 + k->n_pub;
   const uint32_t c_lo = k->n_committed ? k->limb_start : k->m, c_hi = c_lo + k->n_committed;
   GPW_TRY(gpw_msm_g1_dev(ctx, (uint64_t)(wires + k_lo), (uint64_t)(k->K + k_lo), c_lo - k_lo, 1, 0, 0, 0, (uint64_t*)&mK1));
-  report("K1", c_lo - k_lo);
+  msm_names[n_msm++] = "K1";
   mK2 = G1Affine{Fp::zero(), Fp::zero()};
   if (k->k2_lo < k->m) {
     const uint32_t n2 = k->m - k->k2_lo;
@@ -544,11 +554,24 @@ static int wrap_stage2(gpw_wrap_key* k, WrapLane* L, const uint64_t* r_canon, co
       GPW_TRY(gpw_msm_g1_shared_dev(ctx, k->share_q_sort ? (uint64_t)(L->gathA + (k->nA - k->nA_tail)) : (uint64_t)(wires + k->k2_lo),
                                     (uint64_t)k->K2t, n2, 1, FIXED_CQ, FIXED_WQ, "sortQ", k->share_q_sort ? 1 : 0, (uint64_t*)&mK2));
     else GPW_TRY(gpw_msm_g1_dev(ctx, (uint64_t)(wires + k->k2_lo), (uint64_t)(k->K + k->k2_lo), n2, 1, 0, 0, 0, (uint64_t*)&mK2));
-    report("K2", n2);
+    msm_names[n_msm++] = "K2";
   }
   if (k->Zt) GPW_TRY(gpw_msm_g1_fixed_dev(ctx, (uint64_t)L->va, (uint64_t)k->Zt, N - 1, 1, FIXED_C, FIXED_W, (uint64_t*)&mZ));
   else GPW_TRY(gpw_msm_g1_dev(ctx, (uint64_t)L->va, (uint64_t)k->Z, N - 1, 1, 0, 0, 0, (uint64_t*)&mZ));
-  report("Z", N - 1);
+  msm_names[n_msm++] = "Z";
+  if (ctx->msm_defer) {
+    const int n_done = ctx->n_pend;
+    GPW_TRY(gpwi_msm_defer_end(ctx));  // collects every result; the lane's stream is ordered behind all tails
+    if (dbg)
+      for (int i = 0; i < n_done && i < n_msm; i++)
+        fprintf(stderr, "[gpw wrap] MSM %-4s n=%8zu total %7.2f ms accumulate %7.2f ms digits %llu\n", msm_names[i], ctx->pend[i].n,
+                ctx->pend[i].total_ms, ctx->pend[i].acc_ms, (unsigned long long)ctx->pend[i].digits);
+  }
+  if (k->nA_tail) {
+    G1XYZZ t = G1XYZZ::from_affine(mA);
+    add_mixed(t, mA2, false);
+    mA = to_affine(t);
+  }
   GPW_CUDA(cudaEventRecord(ev[6], st));
   GPW_CUDA(cudaStreamSynchronize(st));
   for (int i = 0; i < 6; i++) GPW_CUDA(cudaEventElapsedTime(&L->t_ms[i], ev[i], ev[i + 1]));
@@ -625,6 +648,12 @@ extern "C" int gpw_wrap_prove_many(gpw_wrap_key* k, const uint64_t* inputs, int 
     GPW_TRY(lane_create(k, nullptr, &l));
     k->lanes.push_back(l);
   }
+  // Deferred MSMs (tail of one MSM beside the accumulation of the next, no host wait in between) shorten a LONE proof by
+  // ~10 ms; with several proofs in flight the other lanes already fill those gaps, and queueing a whole proof's kernels at
+  // once was measured to cost throughput (12.9 -> 10.4 proofs/s at 6 lanes: the one-SM solve spines then wait behind
+  // hundreds of queued bulk CTAs). So: overlap for one lane, synchronous MSMs for a stream of proofs.
+  static const char* overlap_env = getenv("GPW_MSM_OVERLAP");
+  for (int j = 0; j < n_lanes; j++) k->lanes[j]->ctx->msm_overlap = overlap_env ? atoi(overlap_env) != 0 : n_lanes == 1;
   const size_t in_words = (size_t)k->n_inputs * 4;
   std::atomic<int> next{0};
   std::atomic<int> first_rc{GPW_OK};
