@@ -18,6 +18,7 @@
 // The arithmetic is integer-pipe bound (11.5 Montgomery multiplies per element), not HBM bound.
 #include "common.cuh"
 #include "ff.cuh"
+#include "tma.cuh"
 
 namespace gpw {
 
@@ -53,35 +54,44 @@ struct NttPass {
   const Fr* scale_out;  // optional elementwise table applied on store
   int scale_in_bitrev, scale_out_bitrev;
   int has_scale_const;  // multiply every output by scale_const on store (the 1/N of a plain inverse transform)
+  int tma;              // tile rows staged by TMA bulk copies (column-in-lo tiles of NTT_COLS columns: 128-byte rows)
   Fr scale_const;
 };
 
-// shared-memory tile: the two 16-byte halves of an element live in two separate arrays, so that the 8 lanes of a
-// quarter warp reading 8 consecutive elements with LDS.128 touch 8 x 16 contiguous bytes (no bank conflict); with the
-// halves interleaved (one 32-byte struct per element) every such access is a 2-way conflict
+// Shared-memory tile of 32-byte elements, addressed in 16-byte chunks. SWIZZLED layout: half h of element e lives at chunk
+// 2e + (h ^ ((e >> 2) & 1)) - the 8 lanes of a quarter warp reading 8 consecutive elements with LDS.128 then touch 8
+// different 16-byte bank groups on each of their two loads (elements 0..3 read chunks 0,2,4,6, elements 4..7 chunks
+// 9,11,13,15); with the plain layout (half h at 2e + h) every such access is a 2-way conflict. The swap is done in the
+// ADDRESS (each lane fetches its logical low half from wherever it lives), so no register is moved. The plain layout is
+// what a TMA bulk copy leaves behind: the first butterfly stage of a TMA-staged tile reads plain and writes swizzled.
 struct NttTile {
-  uint4* lo;
-  uint4* hi;
+  uint4* ch;
+  template <bool SW>
   __device__ __forceinline__ Fr ld(uint32_t e) const {
+    const uint32_t s = SW ? ((e >> 2) & 1u) : 0u;
     Fr r;
     uint4* d = reinterpret_cast<uint4*>(&r);
-    d[0] = lo[e];
-    d[1] = hi[e];
+    d[0] = ch[2 * e + s];
+    d[1] = ch[2 * e + (s ^ 1u)];
     return r;
   }
+  template <bool SW>
   __device__ __forceinline__ void st(uint32_t e, const Fr& v) const {
-    const uint4* s = reinterpret_cast<const uint4*>(&v);
-    lo[e] = s[0];
-    hi[e] = s[1];
+    const uint32_t s = SW ? ((e >> 2) & 1u) : 0u;
+    const uint4* p = reinterpret_cast<const uint4*>(&v);
+    ch[2 * e + s] = p[0];
+    ch[2 * e + (s ^ 1u)] = p[1];
   }
 };
 
 // One stage for NB butterflies of a thread: all operands (and twiddles) are loaded first, then the NB independent
 // Montgomery multiplications run back to back (they interleave in the IMAD pipe), then everything is stored - loads and
 // stores through the same shared-memory pointers would otherwise keep the compiler from overlapping the butterflies.
-template <int NB>
+// LDSW = false: first stage of a TMA-staged tile (plain layout as the bulk copies left it; the elementwise input scale of
+// a coset transform, which the register path applies while loading, is applied here).
+template <int NB, bool LDSW>
 __device__ __forceinline__ void ntt_butterflies(const NttTile& sm, const Fr* __restrict__ tw, const NttPass& P, uint32_t bf0,
-                                                uint32_t bf_stride, int lb, uint32_t lo_base, uint32_t halfN) {
+                                                uint32_t bf_stride, int lb, uint32_t lo_base, uint32_t hi, uint32_t halfN) {
   const uint32_t cols = (uint32_t)P.cols;
   const uint32_t mask = (1u << lb) - 1u;
   const int shift = P.L - 1 - (lb + P.lobits);
@@ -100,8 +110,14 @@ __device__ __forceinline__ void ntt_butterflies(const NttTile& sm, const Fr* __r
     triv[i] = e == 0;
     // inverse transforms use w^-e = -w^(N/2-e): the sign is folded into the butterfly below
     w[i] = ld_fr(tw + (triv[i] ? 0u : (P.inverse ? halfN - e : e)));
-    u[i] = sm.ld(i0[i]);
-    v[i] = sm.ld(i1[i]);
+    u[i] = sm.ld<LDSW>(i0[i]);
+    v[i] = sm.ld<LDSW>(i1[i]);
+    if (!LDSW && P.scale_in) {  // (TMA tiles are column-in-lo tiles)
+      const uint32_t g0 = (hi << (P.lobits + P.k)) | (t0 << P.lobits) | (lo_base + c);
+      const uint32_t g1 = g0 | (1u << (lb + P.lobits));
+      u[i] = mul(u[i], ld_fr(P.scale_in + (P.scale_in_bitrev ? bitrev(g0, P.L) : g0)));
+      v[i] = mul(v[i], ld_fr(P.scale_in + (P.scale_in_bitrev ? bitrev(g1, P.L) : g1)));
+    }
   }
 #pragma unroll
   for (int i = 0; i < NB; i++) {
@@ -121,17 +137,18 @@ __device__ __forceinline__ void ntt_butterflies(const NttTile& sm, const Fr* __r
   }
 #pragma unroll
   for (int i = 0; i < NB; i++) {
-    sm.st(i0[i], u[i]);
-    sm.st(i1[i], v[i]);
+    sm.st<true>(i0[i], u[i]);
+    sm.st<true>(i1[i], v[i]);
   }
 }
 
-__global__ void __launch_bounds__(256) k_ntt_pass(Fr* __restrict__ data, const Fr* __restrict__ tw, NttPass P) {
+__global__ void __launch_bounds__(128, 7) k_ntt_pass(Fr* __restrict__ data, const Fr* __restrict__ tw, NttPass P) {
   extern __shared__ uint4 smem_raw[];
+  __shared__ uint64_t tile_bar;
   const int k = P.k, cols = P.cols;
   const uint32_t tile = 1u << k;
   const uint32_t nelem = tile * cols;
-  const NttTile sm{smem_raw, smem_raw + nelem};
+  const NttTile sm{smem_raw};
   const uint32_t tid = threadIdx.x;
   // CTA -> (hi, lo_base) or (tile_base)
   uint64_t cta = blockIdx.x;
@@ -148,32 +165,51 @@ __global__ void __launch_bounds__(256) k_ntt_pass(Fr* __restrict__ data, const F
     if (P.col_in_lo) return (hi << (P.lobits + k)) | (t << P.lobits) | (lo_base + c);
     return ((hi + c) << k) | t;
   };
-  // load
-  for (uint32_t e = tid; e < nelem; e += blockDim.x) {
-    uint32_t c = e % cols, t = e / cols;
-    uint32_t gi = gindex(t, c);
-    Fr v = ld_fr(data + gi);
-    if (P.scale_in) {
-      uint32_t si = P.scale_in_bitrev ? bitrev(gi, P.L) : gi;
-      v = mul(v, ld_fr(P.scale_in + si));
+  if (P.tma) {
+    // TMA staging: row t of the tile (NTT_COLS neighbouring columns = 128 contiguous bytes of global memory) is one bulk
+    // copy into its 128 bytes of shared memory; the 2^k copies of the CTA complete on one mbarrier by byte count. No
+    // thread moves data through registers; the tile arrives in the plain layout and the first stage re-swizzles it.
+    if (tid == 0) {
+      mbar_init(&tile_bar, 1);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+      mbar_expect_tx(&tile_bar, nelem * (uint32_t)sizeof(Fr));
     }
-    sm.st(e, v);
+    __syncthreads();
+    for (uint32_t t = tid; t < tile; t += blockDim.x)
+      tma_bulk_load(smem_raw + (size_t)t * (2 * NTT_COLS), data + gindex(t, 0), NTT_COLS * (uint32_t)sizeof(Fr), &tile_bar);
+    mbar_wait(&tile_bar, 0);
+  } else {
+    for (uint32_t e = tid; e < nelem; e += blockDim.x) {
+      uint32_t c = e % cols, t = e / cols;
+      uint32_t gi = gindex(t, c);
+      Fr v = ld_fr(data + gi);
+      if (P.scale_in) {
+        uint32_t si = P.scale_in_bitrev ? bitrev(gi, P.L) : gi;
+        v = mul(v, ld_fr(P.scale_in + si));
+      }
+      sm.st<true>(e, v);
+    }
+    __syncthreads();
   }
-  __syncthreads();
   const uint32_t halfN = 1u << (P.L - 1);
   const uint32_t nbf = nelem / 2;
   for (int q = 0; q < k; q++) {
     const int lb = P.dit ? q : (k - 1 - q);  // local pair bit
     // one butterfly at a time per thread: thread-level parallelism (7 CTAs of 128 threads per SM at 64 registers) beats
     // unrolling 4 butterflies per thread (148 registers, 3 CTAs per SM: measured 2.3 ms instead of 1.9 ms for 2^23)
+    if (q == 0 && P.tma) {
 #pragma unroll 1
-    for (uint32_t bf = tid; bf < nbf; bf += blockDim.x) ntt_butterflies<1>(sm, tw, P, bf, 0, lb, lo_base, halfN);
+      for (uint32_t bf = tid; bf < nbf; bf += blockDim.x) ntt_butterflies<1, false>(sm, tw, P, bf, 0, lb, lo_base, hi, halfN);
+    } else {
+#pragma unroll 1
+      for (uint32_t bf = tid; bf < nbf; bf += blockDim.x) ntt_butterflies<1, true>(sm, tw, P, bf, 0, lb, lo_base, hi, halfN);
+    }
     __syncthreads();
   }
   for (uint32_t e = tid; e < nelem; e += blockDim.x) {
     uint32_t c = e % cols, t = e / cols;
     uint32_t gi = gindex(t, c);
-    Fr v = sm.ld(e);
+    Fr v = sm.ld<true>(e);
     if (P.scale_out) {
       uint32_t si = P.scale_out_bitrev ? bitrev(gi, P.L) : gi;
       v = mul(v, ld_fr(P.scale_out + si));
@@ -283,12 +319,14 @@ static int launch_pass(gpw_ctx* ctx, Fr* data, const NttTables* tb, NttPass P) {
     while (cols > (1 << P.lobits)) cols >>= 1;
   }
   P.cols = cols;
+  static const bool tma_on = !getenv("GPW_NTT_TMA") || atoi(getenv("GPW_NTT_TMA")) != 0;
+  P.tma = (tma_on && P.col_in_lo && cols == NTT_COLS && P.k >= 1) ? 1 : 0;
   const uint32_t nelem = (1u << P.k) * cols;
   const uint32_t ctas = N / nelem;
   int threads = (int)(nelem / 2);
   static const int max_threads = getenv("GPW_NTT_THREADS") ? atoi(getenv("GPW_NTT_THREADS")) : 128;
   if (threads > max_threads) threads = max_threads;
-  if (threads > 256) threads = 256;  // launch bounds of k_ntt_pass
+  if (threads > 128) threads = 128;  // launch bounds of k_ntt_pass
   if (threads < 32) threads = 32;
   k_ntt_pass<<<ctas, threads, nelem * sizeof(Fr), ctx->stream>>>(data, (const Fr*)tb->tw, P);
   GPW_CHECK_LAUNCH();

@@ -18,6 +18,7 @@
 
 #include "common.cuh"
 #include "ff.cuh"
+#include "tma.cuh"
 #include "gl.cuh"
 #include "host/frontend.h"
 #include "host/gadgets.h"
@@ -367,31 +368,7 @@ static size_t spine_smem_bytes() {
 // stream), the copy engine moves it while all 256 threads work on the current chunk, and completion is signalled on a
 // shared-memory mbarrier by byte count - no thread spends instructions on the transfer (the 16-byte cp.async loop this
 // replaces cost every thread ~6 copies + a commit per chunk, ~1 000 chunks per proof on a latency-bound CTA).
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void tma_bulk_load(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                   (uint32_t)__cvta_generic_to_shared(smem_dst)),
-               "l"(gmem_src), "r"(bytes), "r"((uint32_t)__cvta_generic_to_shared(bar))
-               : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  const uint32_t a = (uint32_t)__cvta_generic_to_shared(bar);
-  uint32_t done;
-  do {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(done)
-        : "r"(a), "r"(parity)
-        : "memory");
-  } while (!done);
-}
+// (helpers: tma.cuh)
 
 __global__ void __launch_bounds__(NARROW_THREADS)
     k_tape_staged(DevCircuit c, const uint32_t* __restrict__ stream, uint32_t first_words, Fr* __restrict__ wires, size_t wire_stride,
@@ -617,14 +594,17 @@ __global__ void k_set_inputs(Fr* __restrict__ wires, size_t wire_stride, const u
   st_w(W + 1 + i, from_u64x4(x));
 }
 
-// one CTA per long linear expression: strided partial sums, then a shared-memory tree
-__global__ void __launch_bounds__(1024) k_eval_long_les(DevCircuit c, const Fr* __restrict__ W) {
-  __shared__ uint4 sm_raw[1024 * 2];
+// Long linear expressions (the two sides of the log-derivative identity: 65 536 and ~2.5 M terms). grid = (expression,
+// slice): every CTA sums a strided slice of the terms (registers, then a shared-memory tree) into part[expression][slice];
+// k_sum_long_les adds the LONG_SLICES partial sums. (One CTA per expression took 2.4 ms on one SM for the 2.5 M-term row.)
+constexpr uint32_t LONG_SLICES = 128;
+__global__ void __launch_bounds__(256) k_eval_long_les(DevCircuit c, const Fr* __restrict__ W, Fr* __restrict__ part) {
+  __shared__ uint4 sm_raw[256 * 2];
   Fr* sm = reinterpret_cast<Fr*>(sm_raw);
   const uint32_t le = c.long_le[blockIdx.x];
   const uint32_t s = c.le_off[le], e = c.le_off[le + 1];
   Fr acc = Fr::zero();
-  for (uint32_t k = s + threadIdx.x; k < e; k += blockDim.x) {
+  for (uint32_t k = s + blockIdx.y * blockDim.x + threadIdx.x; k < e; k += gridDim.y * blockDim.x) {
     const uint32_t cid = c.le_coeff[k];
     const Fr v = ld_w(W + c.le_wire[k]);
     if (cid == 0) acc = add(acc, v);
@@ -634,6 +614,22 @@ __global__ void __launch_bounds__(1024) k_eval_long_les(DevCircuit c, const Fr* 
   st_w(sm + threadIdx.x, acc);
   __syncthreads();
   for (uint32_t d = blockDim.x >> 1; d >= 1; d >>= 1) {
+    if (threadIdx.x < d) {
+      acc = add(acc, ld_w(sm + threadIdx.x + d));
+      st_w(sm + threadIdx.x, acc);
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) st_w(part + (size_t)blockIdx.x * gridDim.y + blockIdx.y, acc);
+}
+
+__global__ void __launch_bounds__(LONG_SLICES) k_sum_long_les(DevCircuit c, const Fr* __restrict__ part) {
+  __shared__ uint4 sm_raw[LONG_SLICES * 2];
+  Fr* sm = reinterpret_cast<Fr*>(sm_raw);
+  Fr acc = ld_w(part + (size_t)blockIdx.x * LONG_SLICES + threadIdx.x);
+  st_w(sm + threadIdx.x, acc);
+  __syncthreads();
+  for (uint32_t d = LONG_SLICES >> 1; d >= 1; d >>= 1) {
     if (threadIdx.x < d) {
       acc = add(acc, ld_w(sm + threadIdx.x + d));
       st_w(sm + threadIdx.x, acc);
@@ -1285,17 +1281,20 @@ extern "C" int gpw_r1cs_eval_on(gpw_circuit* c, gpw_ctx* lane, uint64_t wires_de
   GPW_CUDA(cudaSetDevice(ctx->device));
   // [0..1]: unsatisfied count / first bad row; then the lane's values of the circuit's long linear expressions
   unsigned long long* bad;
-  GPW_TRY(ctx->get_scratch("solve.bad", 64 + 8 * sizeof(Fr), (void**)&bad));
+  GPW_TRY(ctx->get_scratch("solve.bad", 64 + 8 * sizeof(Fr) + 8 * LONG_SLICES * sizeof(Fr), (void**)&bad));
   DevCircuit dc = c->dc;
   dc.long_val = reinterpret_cast<Fr*>(bad + 8);
+  Fr* long_part = dc.long_val + 8;
   unsigned long long* init = (unsigned long long*)ctx->pin_take(16);
   init[0] = 0;
   init[1] = ~0ull;
   GPW_CUDA(cudaMemcpyAsync(bad, init, 16, cudaMemcpyHostToDevice, ctx->stream));
   if (dc.n_long) {
-    k_eval_long_les<<<dc.n_long, 1024, 0, ctx->stream>>>(dc, (const Fr*)wires_dev);
+    k_eval_long_les<<<dim3(dc.n_long, LONG_SLICES), 256, 0, ctx->stream>>>(dc, (const Fr*)wires_dev, long_part);
     GPW_CHECK_LAUNCH();
-    ctx->launches++;
+    k_sum_long_les<<<dc.n_long, LONG_SLICES, 0, ctx->stream>>>(dc, long_part);
+    GPW_CHECK_LAUNCH();
+    ctx->launches += 2;
   }
   if (dc.n_cons) {  // (a circuit without constraints - a NoopGate on its own - is trivially satisfied)
     k_r1cs_eval<<<div_up(dc.n_cons, 128), 128, 0, ctx->stream>>>(dc, (const Fr*)wires_dev, (Fr*)a_dev, (Fr*)b_dev, (Fr*)c_dev, bad, bad + 1);
