@@ -476,15 +476,21 @@ def main():
     sampler.join(timeout=2)
     ms_e2e, _, proofs2 = timed_stream(args.steps, many_inputs.data_ptr())
     steps_e2e = args.steps
-    # single-proof latency (one lane, nothing else on the device), inputs resident: this run also times the dominant
-    # kernel alone for the roofline
+    # single-proof latency (one lane, nothing else on the device), inputs resident. A lone proof overlaps the tail of each
+    # MSM with the accumulation of the next (libgpw's deferred MSMs) ...
     n_lat = max(3, min(8, args.steps // 2))
+    ms_lat, _, stats, proofs3 = timed(step_resident, n_lat, 1)
+    latency_ms = ms_lat / n_lat
+    # ... so the dominant kernel is timed for the roofline in a second single-proof run with that overlap switched off:
+    # every k_msm_accumulate launch then has the device to itself
+    ctx.set_option("msm_overlap", 0)
     key.msm_cumulative_stats(1, reset=True)
     key.msm_cumulative_stats(2, reset=True)
-    ms_lat, _, stats, proofs3 = timed(step_resident, n_lat, 1)
+    ms_roof, _, _, proofs4 = timed(step_resident, n_lat, 1)
     g1 = key.msm_cumulative_stats(1)
     g2 = key.msm_cumulative_stats(2)
-    latency_ms = ms_lat / n_lat
+    ctx.set_option("msm_overlap", -1)
+    proofs3 = proofs3 + proofs4
     assert all((p["raw"] == proofs[0]["raw"]).all() for p in proofs + proofs2 + proofs3), "proof not reproducible across steps"
     assert proofs[0]["n_unsatisfied"] == 0
 
@@ -510,26 +516,26 @@ def main():
         "e2e": {"value": e2e_value, "unit": "proofs/s", "h2d_bytes_per_step": int(inputs.nbytes), "d2h_bytes_per_step": 512},
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     # dram__bytes_read.sum + dram__bytes_write.sum of one captured launch (profiles/r01_msm_accumulate_ncu.md,
-                     # capture A): the Z MSM, 8 388 607 full-width points, 12 non-zero digits each against the fixed-base table
+                     # dram__bytes_read.sum + dram__bytes_write.sum of one captured launch (profiles/r02_final_kernels_ncu.md,
+                     # the Z launch): the Z MSM, 8 388 607 full-width points, 12 non-zero digits each against the fixed-base table
                      # -> 13.9 GB vs 805 MB algorithmic: every digit gathers its own 64-byte precomputed base
                      "traffic": 13925827096, "traffic_launch_points": 8388607,
                      "peak_source": peak_kind, "kernel": "k_msm_accumulate<Fp> (MSM G1 bucket accumulation)",
                      "launches_per_step": g1["calls"] / n_lat, "avg_launch_ms": avg_ms,
                      "avg_points_per_launch": g1["points"] / max(g1["calls"], 1),
                      "nonzero_digits_per_point": g1["digits"] / max(g1["points"], 1),
-                     "kernel_share_of_step": g1["accumulate_ms"] / ms_lat,
-                     "timed_in": "the single-proof latency run (one lane, kernel alone on the device), CUDA events on the launching stream",
+                     "kernel_share_of_step": g1["accumulate_ms"] / ms_roof,  # share of one proof run alone, kernels back to back (what the ncu launch list shows)
+                     "timed_in": "a single-proof run with the MSM overlap off (one lane, kernel alone on the device), CUDA events on the launching stream",
                      "msm_g1_whole_GBps": 96.0 * g1["points"] / (g1["total_ms"] * 1e-3) / 1e9 if g1["total_ms"] else None,
                      "msm_g2_whole_GBps": 160.0 * g2["points"] / (g2["total_ms"] * 1e-3) / 1e9 if g2["total_ms"] else None,
-                     # the bound that actually holds: additions/s against the IMAD.WIDE issue ceiling. One mixed addition = 8
-                     # Montgomery multiplications of 136 IMAD + the dual-product Y3 of 200 = 1 288; IMAD.WIDE issues one warp
-                     # instruction per 4 cycles per SM sub-partition: 148 SMs x 32 lanes/clk x 1.965 GHz / 1 288
+                     # the bound that actually holds: additions/s against the IMAD.WIDE issue ceiling. One mixed addition = 6
+                     # Montgomery multiplications of 136 IMAD + 2 squarings of 108 + the dual-product Y3 of 200 = 1 232; IMAD.WIDE
+                     # issues one warp instruction per 4 cycles per SM sub-partition: 148 SMs x 32 lanes/clk x 1.965 GHz / 1 232
                      "integer_pipe": {"achieved_Gadds_per_s": g1["digits"] / (g1["accumulate_ms"] * 1e-3) / 1e9 if g1["accumulate_ms"] else None,
-                                      "peak_Gadds_per_s": 148 * 32 * 1.965 / 1288.0,
-                                      "frac": (g1["digits"] / (g1["accumulate_ms"] * 1e-3) / 1e9) / (148 * 32 * 1.965 / 1288.0)
+                                      "peak_Gadds_per_s": 148 * 32 * 1.965 / 1232.0,
+                                      "frac": (g1["digits"] / (g1["accumulate_ms"] * 1e-3) / 1e9) / (148 * 32 * 1.965 / 1232.0)
                                       if g1["accumulate_ms"] else None},
-                     "note": "BN254 MSM is integer-pipe (IMAD) bound, ~1290 IMAD.WIDE per 96-byte point-digit; the HBM fraction is "
+                     "note": "BN254 MSM is integer-pipe (IMAD) bound, ~1230 IMAD.WIDE per 96-byte point-digit; the HBM fraction is "
                              "low by construction (BASELINE.md 4)"},
         "clocks": sampler.summary(),
         "pipelining": "gpw_wrap_prove_many: %d proofs in flight per GPU (host thread + stream + scratch each)" % args.lanes,

@@ -149,8 +149,12 @@ extern "C" int gpw_ctx_set_option(gpw_ctx* ctx, const char* key, int64_t value) 
     ctx->msm_affine_rounds = (int)value;
     return GPW_OK;
   }
-  if (!strcmp(key, "msm_overlap")) {  // 1 (default): the wrap prover overlaps an MSM's tail with the next MSM (common.cuh)
-    ctx->msm_overlap = value != 0;
+  if (!strcmp(key, "msm_overlap")) {  // the wrap prover's deferred MSMs (common.cuh): -1 automatic (default), 0 off, 1 on
+    if (value < -1 || value > 1) {
+      set_error("msm_overlap must be -1, 0 or 1");
+      return GPW_EINVAL;
+    }
+    ctx->msm_overlap_mode = (int)value;
     return GPW_OK;
   }
   set_error("ctx_set_option: unknown option '%s'", key);

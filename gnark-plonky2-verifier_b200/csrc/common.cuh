@@ -82,7 +82,8 @@ struct gpw_ctx {
   int msm_parity = 0;      // scratch double buffer of the next deferred MSM
   cudaEvent_t slot_done[2] = {nullptr, nullptr};  // tail of the last MSM that used scratch set a / b
   bool slot_used[2] = {false, false};
-  bool msm_overlap = true;  // option "msm_overlap": 0 = every MSM synchronous on `stream` (the round-1 behaviour)
+  bool msm_overlap = true;  // this call: deferred MSMs allowed (set by the wrap entry points from msm_overlap_mode)
+  int msm_overlap_mode = -1;  // option "msm_overlap": -1 = automatic (a lone proof overlaps, a stream of proofs does not), 0 / 1 = forced
   int sm_count = 148;
   uint64_t launches = 0;
   std::map<std::string, gpw::Scratch> scratch;

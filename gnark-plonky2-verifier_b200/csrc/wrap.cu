@@ -460,7 +460,8 @@ extern "C" int gpw_wrap_prove_dev(gpw_wrap_key* k, uint64_t inputs_dev, const ui
   GPW_CUDA(cudaSetDevice(k->ctx->device));
   {
     static const char* overlap_env = getenv("GPW_MSM_OVERLAP");
-    k->lanes[0]->ctx->msm_overlap = overlap_env ? atoi(overlap_env) != 0 : true;  // a lone proof: see gpw_wrap_prove_many
+    const int overlap_mode = overlap_env ? atoi(overlap_env) : k->ctx->msm_overlap_mode;
+    k->lanes[0]->ctx->msm_overlap = overlap_mode < 0 ? true : overlap_mode != 0;  // a lone proof: see gpw_wrap_prove_many
   }
   return wrap_one(k, k->lanes[0], inputs_dev, r_canon, s_canon, check, out_proof);
 }
@@ -653,7 +654,8 @@ extern "C" int gpw_wrap_prove_many(gpw_wrap_key* k, const uint64_t* inputs, int 
   // once was measured to cost throughput (12.9 -> 10.4 proofs/s at 6 lanes: the one-SM solve spines then wait behind
   // hundreds of queued bulk CTAs). So: overlap for one lane, synchronous MSMs for a stream of proofs.
   static const char* overlap_env = getenv("GPW_MSM_OVERLAP");
-  for (int j = 0; j < n_lanes; j++) k->lanes[j]->ctx->msm_overlap = overlap_env ? atoi(overlap_env) != 0 : n_lanes == 1;
+  const int overlap_mode = overlap_env ? atoi(overlap_env) : k->ctx->msm_overlap_mode;  // option "msm_overlap" of the key's context
+  for (int j = 0; j < n_lanes; j++) k->lanes[j]->ctx->msm_overlap = overlap_mode < 0 ? n_lanes == 1 : overlap_mode != 0;
   const size_t in_words = (size_t)k->n_inputs * 4;
   std::atomic<int> next{0};
   std::atomic<int> first_rc{GPW_OK};
