@@ -218,6 +218,17 @@ def test_prove_many_lanes_match_single_proofs(ctx, step):
     key.set_lanes(2)
     out2 = key.prove_many(dev.data_ptr(), n, [r for r, _ in rs], [s for _, s in rs], check=True)
     assert all((a["raw"] == b["raw"]).all() for a, b in zip(out, out2))
+    # deferred MSMs (a lone proof overlaps the tail of each MSM with the next one, csrc/common.cuh) change no byte: forced off,
+    # forced on for a stream of two lanes, and the one-lane stream (automatic: on) all reproduce the single proofs
+    ctx.set_option("msm_overlap", 0)
+    assert (key.prove(inputs, *rs[0], check=True)["raw"] == single[0]).all()
+    ctx.set_option("msm_overlap", 1)
+    out3 = key.prove_many(dev.data_ptr(), 3, [r for r, _ in rs[:3]], [s for _, s in rs[:3]], check=True)
+    ctx.set_option("msm_overlap", -1)
+    key.set_lanes(1)
+    out4 = key.prove_many(dev.data_ptr(), 2, [r for r, _ in rs[:2]], [s for _, s in rs[:2]], check=True)
+    assert all((a["raw"] == b).all() for a, b in zip(out3, single)) and all((a["raw"] == b).all() for a, b in zip(out4, single))
+    key.set_lanes(2)
     # a bad proof in the stream fails the call loudly (unsatisfiable -> GPW_EUNSAT), it is not skipped
     bad = many_host.copy()
     bad[2, circ.info["public"] + 40, 0] ^= 1
