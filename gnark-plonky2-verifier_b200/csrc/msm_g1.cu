@@ -83,6 +83,7 @@ extern "C" int gpwi_msm_defer_begin(gpw_ctx* ctx) {
   ctx->pin_reserve(96 * 1024);  // window sums of a whole proof's MSMs stay in the staging area until finished
   ctx->msm_defer = true;
   ctx->n_pend = 0;
+  ctx->msm_parity = 0;  // every proof walks the two scratch sets in the same order: their sizes settle after the first proof
   return GPW_OK;
 }
 
