@@ -240,6 +240,9 @@ constexpr int MSM_ACC_THREADS = 128;
 #ifndef MSM_ACC_MIN_CTAS
 #define MSM_ACC_MIN_CTAS 3  /* 4 (a 128-register cap) was measured: no faster, the kernel is IMAD-pipe bound, not occupancy bound */
 #endif
+#ifndef MSM_ACC_MIN_CTAS_G2
+#define MSM_ACC_MIN_CTAS_G2 2  /* G2: 254 registers; 3 CTAs per SM (a 168-register cap, 624 bytes of spills) was measured: 10.0 instead of 9.06 ms for B2 */
+#endif
 
 // One thread per task of MSM_TASK consecutive sorted entries, walked by ONE flat loop so that all lanes of a warp
 // execute the same mixed addition in lock step (the earlier nested per-run loops left ~55 % of the lanes idle:
@@ -248,7 +251,7 @@ constexpr int MSM_ACC_THREADS = 128;
 // wires make bucket (window 0, digit 1) millions of entries long - merge their 128 partials in shared memory, so
 // the fix-up pass sees one partial per CTA instead of one per thread.
 template <class F>
-__global__ void __launch_bounds__(MSM_ACC_THREADS, sizeof(F) == sizeof(Fp) ? MSM_ACC_MIN_CTAS : 2)
+__global__ void __launch_bounds__(MSM_ACC_THREADS, sizeof(F) == sizeof(Fp) ? MSM_ACC_MIN_CTAS : MSM_ACC_MIN_CTAS_G2)
     k_msm_accumulate(const Affine<F>* __restrict__ points, const uint32_t* __restrict__ sorted,
                      const uint32_t* __restrict__ offsets, uint32_t B, XYZZ<F>* __restrict__ buckets,
                      XYZZ<F>* __restrict__ head, XYZZ<F>* __restrict__ tail, uint32_t* __restrict__ tail_key,

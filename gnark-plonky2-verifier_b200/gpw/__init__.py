@@ -10,7 +10,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(os.path.dirname(_HERE), "libgpw.so")
+LIB_PATH = os.environ.get("GPW_LIB") or os.path.join(os.path.dirname(_HERE), "libgpw.so")  # (GPW_LIB: development builds)
 
 R_MOD = 21888242871839275222246405745257275088548364400416034343698204186575808495617
 P_MOD = 21888242871839275222246405745257275088696311157297823662689037894645226208583
