@@ -893,6 +893,15 @@ GPW_HD Fe<P> sqr(const Fe<P>& a) {
 #endif
 }
 
+// Squaring for LATENCY-bound code (a lone warp walking a dependency chain: the solve spine, k_tape_poseidon4): the dedicated
+// squaring saves 28 IMAD.WIDE but its critical path is longer than the multiplication's (cross sums -> merge -> doubling ->
+// diagonal chain -> eight shift-in + reduction rows, ~215 dependent instructions against ~130), and such code waits for
+// exactly that path. Measured on the Merkle levels: see DESIGN.md.
+template <class P>
+GPW_HD Fe<P> sqr_chain(const Fe<P>& a) {
+  return mul(a, a);
+}
+
 // a b - c d: one Montgomery reduction for both products (mont_mul2 with the second product negated through c)
 template <class P>
 GPW_HD Fe<P> mul_sub2(const Fe<P>& a, const Fe<P>& b, const Fe<P>& c, const Fe<P>& d) {

@@ -17,8 +17,8 @@ struct Bn254PoseidonTables {
 
 template <class Emit>
 GPW_HD void bn254_exp5_emit(Fr& x, bool emit_wires, Emit& emit) {
-  Fr x2 = sqr(x);
-  Fr x4 = sqr(x2);
+  Fr x2 = sqr_chain(x);
+  Fr x4 = sqr_chain(x2);
   Fr x5 = mul(x4, x);
   if (emit_wires) {
     emit(x2);
@@ -112,8 +112,8 @@ __device__ __forceinline__ void poseidon_bn254_trace4(Fr& x, uint32_t const_mask
   const uint32_t rank0 = (uint32_t)__popc(~const_mask & ((1u << q) - 1u) & 0xfu);  // emitting lanes before this one, round 0
   const bool skip0 = (const_mask >> q) & 1u;
   auto sbox = [&](uint32_t idx, bool do_emit) {
-    const Fr x2 = sqr(x);
-    const Fr x4 = sqr(x2);
+    const Fr x2 = sqr_chain(x);
+    const Fr x4 = sqr_chain(x2);
     const Fr x5 = mul(x4, x);
     if (do_emit) {
       emit(idx, x2);

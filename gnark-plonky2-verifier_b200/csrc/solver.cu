@@ -221,7 +221,7 @@ __device__ void exec_op(const DevCircuit& c, const Fr* W, uint32_t op_nout, cons
     case fe::OP_MUL: {
       const Fr a = eval_ref(c, W, A);
       const bool same = B.wires == A.wires && B.n == A.n;  // x * x (S-boxes): evaluate the operand once
-      Fr r = same ? sqr(a) : mul(a, eval_ref(c, W, B));
+      Fr r = same ? sqr_chain(a) : mul(a, eval_ref(c, W, B));
       if (Cc.present) r = add(r, eval_ref(c, W, Cc));
       O.put(0,r);
       break;
