@@ -172,9 +172,10 @@ __global__ void __launch_bounds__(128, 7) k_ntt_pass(Fr* __restrict__ data, cons
     if (tid == 0) {
       mbar_init(&tile_bar, 1);
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-      mbar_expect_tx(&tile_bar, nelem * (uint32_t)sizeof(Fr));
     }
     __syncthreads();
+    if (tid == 0) mbar_expect_tx(&tile_bar, nelem * (uint32_t)sizeof(Fr));
+    __syncthreads();  // the byte count is registered before any copy can complete on the barrier
     for (uint32_t t = tid; t < tile; t += blockDim.x)
       tma_bulk_load(smem_raw + (size_t)t * (2 * NTT_COLS), data + gindex(t, 0), NTT_COLS * (uint32_t)sizeof(Fr), &tile_bar);
     mbar_wait(&tile_bar, 0);
