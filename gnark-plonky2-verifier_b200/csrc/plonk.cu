@@ -43,6 +43,8 @@ int gpw_witness_solve_phase1_on(gpw_circuit* c, gpw_ctx* lane, uint64_t inputs_d
 int gpw_witness_solve_phase2_on(gpw_circuit* c, gpw_ctx* lane, const uint64_t* ch, int n_proofs, uint64_t wires_dev, size_t wire_stride);
 int gpw_ntt_fr_dev(gpw_ctx* ctx, uint64_t data_dev, int logn, int inverse, int coset, int in_bitrev, int out_bitrev);
 int gpw_msm_g1_dev(gpw_ctx* ctx, uint64_t s, uint64_t p, size_t n, int mont, int c, int lo, int hi, uint64_t* out);
+int gpw_msm_g1_fixed_table(gpw_ctx* ctx, uint64_t points_dev, size_t n, int window_bits, int n_windows, uint64_t table_dev);
+int gpw_msm_g1_fixed_dev(gpw_ctx* ctx, uint64_t s, uint64_t table, size_t n, int mont, int c, int n_windows, uint64_t* out);
 }
 
 namespace gpw {
@@ -419,6 +421,11 @@ struct gpw_plonk_key {
   // MSM skips most digits, whereas their coefficient forms are full-width. (Generated from tau like the monomial SRS; for a
   // ceremony SRS it would come from an inverse FFT "in the exponent".)
   G1Affine* srs_lagrange = nullptr;
+  // fixed-base table of the monomial SRS, 2^(22 w) [tau^i] G1 for the 12 windows of a scalar (25.8 GB at 2^25): the six
+  // commitments to full-width coefficient vectors of every proof (Z, t0..t2, the two opening polynomials) then need 12 instead
+  // of 16 bucket additions per scalar into one bucket set (the Z MSM of the Groth16 path does the same). Built when the
+  // device has the room (GPW_PLONK_FIXED=0 switches it off); nullptr: plain windowed MSM.
+  G1Affine* srs_t = nullptr;
   G2Affine tau2;            // [tau] G2
   G1Affine vk_com[9];       // [qL] [qR] [qM] [qO] [qC] [Qcp] [S1] [S2] [S3]
   Fr k1, k2, omega;
@@ -501,7 +508,10 @@ struct Transcript {
   }
 };
 
+constexpr int PLONK_FIXED_C = 22, PLONK_FIXED_W = (254 + PLONK_FIXED_C) / PLONK_FIXED_C;
 int commit(gpw_plonk_key* k, const Fr* coef, G1Affine* out) {
+  if (k->srs_t)
+    return gpw_msm_g1_fixed_dev(k->ctx, (uint64_t)coef, (uint64_t)k->srs_t, k->N, 1, PLONK_FIXED_C, PLONK_FIXED_W, (uint64_t*)out);
   return gpw_msm_g1_dev(k->ctx, (uint64_t)coef, (uint64_t)k->srs, k->N, 1, 0, 0, 0, (uint64_t*)out);
 }
 // the same commitment from the polynomial's values on H (Lagrange-basis SRS)
@@ -685,6 +695,21 @@ extern "C" int gpw_plonk_setup(gpw_ctx* ctx, gpw_circuit* circ, const uint8_t* s
     k->allocs.pop_back();
     Fr tc = from_mont(tau);
     k->tau2 = to_affine(host_scalar_mul(generator<Fp2>(), tc.l));
+  }
+  {  // fixed-base table of the monomial SRS, if the device has the room for it next to the proofs' scratch
+    static const bool want = !getenv("GPW_PLONK_FIXED") || atoi(getenv("GPW_PLONK_FIXED")) != 0;
+    const size_t need = (size_t)N * PLONK_FIXED_W * sizeof(G1Affine);
+    size_t free_b = 0, total_b = 0;
+    // (small domains: the reduction of 2^21 buckets would cost more than the four additions per scalar it saves)
+    if (want && N >= (1u << 22) && (uint64_t)N * PLONK_FIXED_W < (1ull << 31) && cudaMemGetInfo(&free_b, &total_b) == cudaSuccess &&
+        free_b > need + ((size_t)24 << 30)) {
+      if ((rc = dalloc(k, (void**)&k->srs_t, need))) return fail(rc);
+      if ((rc = gpw_msm_g1_fixed_table(ctx, (uint64_t)k->srs, N, PLONK_FIXED_C, PLONK_FIXED_W, (uint64_t)k->srs_t))) return fail(rc);
+      if (cudaStreamSynchronize(st) != cudaSuccess) {
+        set_error("plonk_setup: fixed-base table failed: %s", cudaGetErrorString(cudaGetLastError()));
+        return fail(GPW_ECUDA);
+      }
+    }
   }
   // verifying key: commitments to the selectors and the permutation polynomials
   for (int i = 0; i < 6; i++)
