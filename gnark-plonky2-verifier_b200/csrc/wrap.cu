@@ -425,9 +425,22 @@ static int wrap_one(gpw_wrap_key* k, WrapLane* L, uint64_t inputs_dev, const uin
   cudaStream_t st = L->ctx->stream;
   cudaEvent_t e0 = L->tev[0], e1 = L->tev[1];
   GPW_CUDA(cudaEventRecord(e0, st));
-  GPW_TRY(gpw_witness_solve_phase1_on(k->circ, L->ctx, inputs_dev, 1, (uint64_t)L->wires, k->m));
+  // The solve (one-CTA spine segments + the Merkle levels' small grids) runs on the context's HIGH-PRIORITY stream: the spine
+  // CTA needs a whole SM to itself and, at equal priority, waits behind every bulk CTA the other lanes have queued before it -
+  // with a whole proof's MSMs queued at once (deferred MSMs) that starved it (10.4 proofs/s); in front of them it is 13.6
+  // against 13.2 with synchronous MSMs. GPW_SPINE_HI=0: the lane's ordinary stream.
+  static const bool spine_hi = !getenv("GPW_SPINE_HI") || atoi(getenv("GPW_SPINE_HI")) != 0;
+  const cudaStream_t hs = (spine_hi && L->ctx->stream_hi) ? L->ctx->stream_hi : st;
+  if (hs != st) {
+    GPW_CUDA(cudaEventRecord(L->ctx->ev_hop, st));
+    GPW_CUDA(cudaStreamWaitEvent(hs, L->ctx->ev_hop, 0));
+    L->ctx->stream = hs;
+  }
+  int rc1 = gpw_witness_solve_phase1_on(k->circ, L->ctx, inputs_dev, 1, (uint64_t)L->wires, k->m);
+  L->ctx->stream = st;
+  GPW_TRY(rc1);
   float t1 = 0;
-  GPW_CUDA(cudaEventRecord(e1, st));
+  GPW_CUDA(cudaEventRecord(e1, hs));
   GPW_CUDA(cudaEventSynchronize(e1));
   GPW_CUDA(cudaEventElapsedTime(&t1, e0, e1));
   int rc = wrap_stage2(k, L, r_canon, s_canon, check, out_proof);
@@ -649,13 +662,14 @@ extern "C" int gpw_wrap_prove_many(gpw_wrap_key* k, const uint64_t* inputs, int 
     GPW_TRY(lane_create(k, nullptr, &l));
     k->lanes.push_back(l);
   }
-  // Deferred MSMs (tail of one MSM beside the accumulation of the next, no host wait in between) shorten a LONE proof by
-  // ~10 ms; with several proofs in flight the other lanes already fill those gaps, and queueing a whole proof's kernels at
-  // once was measured to cost throughput (12.9 -> 10.4 proofs/s at 6 lanes: the one-SM solve spines then wait behind
-  // hundreds of queued bulk CTAs). So: overlap for one lane, synchronous MSMs for a stream of proofs.
+  // Deferred MSMs (tail of one MSM beside the accumulation of the next, no host wait in between) shorten a lone proof by
+  // ~10 ms and, with the solve spines on the high-priority stream (wrap_one), raise the throughput of a stream of proofs from
+  // 13.2 to 13.6 proofs/s - saturated from 3 lanes on instead of 6. (Without the prioritised spine, queueing a whole proof's
+  // kernels at once starved the one-SM spines behind hundreds of bulk CTAs: 10.4 proofs/s.) Option "msm_overlap" of the key's
+  // context / GPW_MSM_OVERLAP: -1 automatic (on), 0 off, 1 on.
   static const char* overlap_env = getenv("GPW_MSM_OVERLAP");
-  const int overlap_mode = overlap_env ? atoi(overlap_env) : k->ctx->msm_overlap_mode;  // option "msm_overlap" of the key's context
-  for (int j = 0; j < n_lanes; j++) k->lanes[j]->ctx->msm_overlap = overlap_mode < 0 ? n_lanes == 1 : overlap_mode != 0;
+  const int overlap_mode = overlap_env ? atoi(overlap_env) : k->ctx->msm_overlap_mode;
+  for (int j = 0; j < n_lanes; j++) k->lanes[j]->ctx->msm_overlap = overlap_mode != 0;
   const size_t in_words = (size_t)k->n_inputs * 4;
   std::atomic<int> next{0};
   std::atomic<int> first_rc{GPW_OK};
